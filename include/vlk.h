@@ -1,0 +1,187 @@
+/*
+ * libvlk — C ABI of the B200 (sm_100a) kernels behind the captioning / GPT-2 training step of
+ * theophile-lt/gpt2-vision-language.
+ *
+ * The reference has no FFI of its own: every entry point below replaces one or more PyTorch library calls
+ * made from the reference's nn.Module code (file:line cited per function, paths relative to the reference
+ * repo root).  Conventions:
+ *   - plain C types only; all pointers are DEVICE pointers unless the name says host;
+ *   - bf16 tensors are `void*` to 2-byte brain-float storage, row-major, innermost dim contiguous;
+ *   - every function is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing,
+ *     keeps no global mutable state and never synchronises;
+ *   - return 0 on success, a negative VLK_ERR_* on invalid shape / alignment / arch, a positive value is a
+ *     cudaError_t from the launch.  Nothing throws across the ABI; vlk_last_error_string() has the text.
+ */
+#ifndef VLK_H_
+#define VLK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLK_VERSION 100 /* 0.1.0 */
+
+#define VLK_OK 0
+#define VLK_ERR_INVALID_ARG (-1)
+#define VLK_ERR_ALIGNMENT (-2)
+#define VLK_ERR_UNSUPPORTED (-3)
+#define VLK_ERR_ARCH (-4)
+#define VLK_ERR_DRIVER (-5)
+
+/* Activation selector for GEMM epilogues. Three GELUs live on the path:
+ * tanh (source/gpt2/train_gpt2.py:51), erf (source/gpt2_q_former/model.py:128),
+ * quick x*sigmoid(1.702x) (HF transformers activations.py, CLIP MLP). */
+#define VLK_ACT_NONE 0
+#define VLK_ACT_GELU_TANH 1
+#define VLK_ACT_GELU_ERF 2
+#define VLK_ACT_QUICK_GELU 3
+
+int vlk_version(void);
+const char* vlk_last_error_string(void);
+/* Number of SMs of the current device (148 on B200); negative on error. */
+int vlk_num_sms(void);
+/* Number of libvlk kernel launches issued by this process so far (bench.py reports it as gpu_launches). */
+long long vlk_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Dense contraction on the tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+ *   D[M,N] = epi( alpha * op(A)[M,K] . op(B)[K,N] )
+ *   transA == 0: A stored [M,K] (lda = row stride in elements); transA == 1: A stored [K,M].
+ *   transB == 0: B stored [N,K] — the nn.Linear weight layout, i.e. x @ W^T; transB == 1: B stored [K,N].
+ *   epi, in this order: v = alpha*acc; v += bias[n]; aux_out[m,n] = v; v = act(v) (dact == 0) or
+ *   v *= act'(aux_in[m,n]) (dact != 0); v *= *scale; v += residual[m,n]; D[m,n] = bf16(v)
+ *   (or fp32 when out_fp32 != 0).  Any of bias / residual / aux_in / aux_out / scale may be NULL.
+ *   If bias_grad is non-NULL (fp32 [N], pre-zeroed) the column sums of the *A-side operand rows* are not
+ *   computed here — see vlk_colsum_bf16.
+ * Replaces: nn.Linear / F.linear at train_gpt2.py:35,42,56-58,121; gpt2_linear/model.py:128;
+ *   gpt2_cross-att/model.py:49-57,83; gpt2_q_former/model.py:126-130,160 and the in/out projections of
+ *   nn.MultiheadAttention (:119,:123); HF modeling_clip.py q/k/v/out_proj, fc1/fc2, patch_embedding,
+ *   visual_projection; plus their autograd dgrad / wgrad GEMMs.
+ * Requirements: M,N,K > 0; K % 8 == 0, N % 8 == 0; lda/ldb/ldd/ldr/ld_aux % 8 == 0; 16-byte aligned bases.
+ */
+int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                  int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
+                  void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
+                  void* stream);
+
+/* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
+int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);
+
+/* dst[c, r] = src[r, c] for bf16 matrices (ld in elements). */
+int vlk_transpose_bf16(const void* src, void* dst, int rows, int cols, int ld_src, int ld_dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim, fp32 statistics (nn.LayerNorm at train_gpt2.py:66-72,94;
+ * gpt2_cross-att/model.py:91-95; gpt2_q_former/model.py:118-125; CLIP pre/post/layer norms).
+ * fwd: y = (x-mean)*rstd*gamma + beta; mean/rstd (fp32 [rows]) may be NULL for inference.
+ * bwd: dx always; dgamma/dbeta (fp32 [cols], ACCUMULATED into) may both be NULL for frozen norms.
+ *      If dx_accum != 0, dx += result (residual-stream accumulation).
+ */
+int vlk_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+                      int rows, int cols, float eps, void* stream);
+int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                      void* dx, float* dgamma, float* dbeta, int rows, int cols, int dx_accum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Scaled-dot-product attention, head dim 64, fp32 softmax (F.scaled_dot_product_attention at
+ * train_gpt2.py:40, gpt2_cross-att/model.py:55; nn.MultiheadAttention math at gpt2_q_former/model.py:135,140;
+ * CLIPAttention).  Q/K/V/O are addressed as  base + b*batch_stride + t*row_stride + h*64  (elements), so the
+ * packed c_attn / kv_proj / in_proj outputs are consumed in place with no head transpose.
+ * lse (fp32 [B,H,Tq], natural log) is written when non-NULL and is required by the backward.
+ * bwd computes dQ, dK, dV (same addressing as their primals; written, not accumulated).
+ */
+int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                 long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                 int o_rs, int causal, float scale, void* stream);
+int vlk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                 void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs,
+                 long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs,
+                 int dq_rs, long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * 257 -> 33 token pooling: keep CLS, average the 16x16 patch grid into 4 rows x 8 cols of bins
+ * (bin (r,c) = patch rows 4r..4r+3, cols 2c..2c+1), then L2-normalise every token (eps 1e-12).
+ * pool_clip_197_to_33_avg_with_cls at gpt2_linear/model.py:240-254 (same in the other two model.py).
+ * in: [B,257,D] (bf16 or fp32 by in_fp32), out: [B,33,D] same dtype.  normalize == 0 skips the L2 step.
+ */
+int vlk_pool33_l2norm(const void* in, void* out, int B, int D, int in_fp32, int normalize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * out[b, prefix_len + t, :] = wte[ids[b,t], :] + wpe[pos0 + t, :];  out[b, 0:prefix_len, :] = prefix[b]
+ * (prefix may be NULL with prefix_len == 0).  GPT.forward train_gpt2.py:114-117 and the caption
+ * variant gpt2_linear/model.py:187-200 (image prefix gets no position embedding).
+ * ids are int64 as produced by the reference data path.
+ */
+int vlk_embed_concat_fwd(const long long* ids, const void* wte, const void* wpe, const void* prefix, void* out,
+                         int B, int T, int prefix_len, int C, int pos0, void* stream);
+/* Gradient of the above w.r.t. wte / wpe (fp32 accumulators [V,C], [block,C]); pretraining only. */
+int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte, float* dwpe, int B, int T, int prefix_len,
+                  int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Row-wise softmax cross-entropy statistics over materialised bf16 logits [rows, V] (ld in elements):
+ *   loss_row[r] = logsumexp(logits[r]) - logits[r, label[r]]   (0 for ignored rows: label < 0)
+ * and, in place, logits[r,:] <- (softmax(logits[r]) - onehot(label[r])) * grad_scale[r]  when
+ * write_grad != 0, where the caller supplies *inv_count (device fp32 scalar = 1/number of valid rows) and
+ * an optional per-row fp32 weight (x-attn masked mean, gpt2_cross-att/model.py:176-185).
+ * F.cross_entropy at train_gpt2.py:124; gpt2_linear/model.py:205-210 (ignore_index=-100).
+ * The vocab is processed chunk-by-chunk by the caller (lm_head GEMM per row block) so that the [M,50304]
+ * logits are never resident at once; see lmhead_ce in the host package.
+ */
+int vlk_softmax_ce_rows(void* logits, const long long* labels, const float* row_weight, float* loss_row,
+                        const float* inv_count, int rows, int V, int ld, int write_grad, void* stream);
+/* valid-count + mean: out[0] = sum(loss_row*w)/max(count,1), out[1] = 1/max(count,1), count = #labels>=0
+ * (or sum of weights when row_weight != NULL). */
+int vlk_ce_count(const long long* labels, const float* row_weight, float* out, int rows, void* stream);
+int vlk_ce_finalize(const float* loss_row, const float* row_weight, float* out, int rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused global-norm clip + AdamW over a table of tensors (clip_grad_norm_ at train_gpt2.py:472 and
+ * torch.optim.AdamW(betas, eps, fused) at train_gpt2.py:143).
+ *   pass 1  vlk_grad_sumsq: norm_sq[0] += sum over all grads of g^2  (fp32, caller zeroes)
+ *   pass 2  vlk_adamw_step: clip = min(1, max_norm/(sqrt(norm_sq)+1e-6)); g *= clip; standard decoupled AdamW.
+ * The table is a device array of vlk_tensor_desc; params/grads/moments are bf16 or fp32 per `dtype_fp32`.
+ * `grads` are left scaled?  No: gradients are read-only here; the clip factor is applied in registers.
+ */
+typedef struct vlk_tensor_desc {
+    void* param;
+    const void* grad;
+    void* exp_avg;
+    void* exp_avg_sq;
+    long long numel;
+    float weight_decay;
+    int pad_;
+} vlk_tensor_desc;
+
+int vlk_grad_sumsq(const vlk_tensor_desc* table, int n_tensors, long long max_numel, int dtype_fp32,
+                   float* norm_sq, void* stream);
+int vlk_adamw_step(const vlk_tensor_desc* table, int n_tensors, long long max_numel, int dtype_fp32,
+                   const float* norm_sq, float max_norm, const float* lr, float beta1, float beta2, float eps,
+                   const float* step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Elementwise helpers on the path.
+ */
+/* CLIP patch embedding as a GEMM: unfold pixel_values [B,3,224,224] (fp32 or bf16) into
+ * [B*256, Kpad] bf16 rows (k = c*196 + i*14 + j, zero-padded to Kpad). modeling_clip.py:148-154,209. */
+int vlk_im2col_patch14(const void* pixels, void* out, int B, int Kpad, int in_fp32, void* stream);
+/* x[b, 0, :] = cls + pos[0]; x[b, 1+p, :] = patch[b*256+p, :] + pos[1+p]   (modeling_clip.py:209-218) */
+int vlk_clip_assemble(const void* patch, const void* cls, const void* pos, void* out, int B, int D, void* stream);
+/* y = a + b (bf16), n elements, n % 8 == 0 */
+int vlk_add_bf16(const void* a, const void* b, void* y, long long n, void* stream);
+/* dst(bf16) <- src(fp32) and back */
+int vlk_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int vlk_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
+/* gate gradient for the x-attn block (gpt2_cross-att/model.py:101):
+ * out[0] += (1 - tanh(gate)^2) * sum(dy * y)  over n elements. */
+int vlk_gate_grad(const void* dy, const void* y, const float* gate, float* out, long long n, void* stream);
+/* argmax over the last dim of bf16 [rows, V] -> int64 ids (greedy decode). */
+int vlk_argmax_rows(const void* logits, long long* out, int rows, int V, int ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLK_H_ */

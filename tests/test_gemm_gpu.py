@@ -1,0 +1,100 @@
+"""tcgen05 GEMM (vlk_gemm_bf16) against a torch fp32 matmul on the same bf16-rounded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_act(x, act):
+    import torch.nn.functional as F
+    if act == "gelu_tanh":
+        return F.gelu(x, approximate="tanh")
+    if act == "gelu_erf":
+        return F.gelu(x)
+    if act == "quick_gelu":
+        return x * torch.sigmoid(1.702 * x)
+    return x
+
+
+def _check(out, ref, tol=2e-2):
+    out = out.float()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err / scale < tol, f"max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (4096, 768, 768), (16448, 1024, 1024),
+                                   (1984, 2304, 768), (2112, 768, 768), (300, 64, 192), (77, 264, 72),
+                                   (512, 50304, 768)])
+@pytest.mark.parametrize("bn", [None, 256, 128, 64])
+def test_gemm_nt_plain(cuda, M, N, K, bn, monkeypatch):
+    from gpt2_vision_language_b200 import ops
+    if bn is not None:
+        monkeypatch.setenv("VLK_GEMM_BN", str(bn))
+    else:
+        monkeypatch.delenv("VLK_GEMM_BN", raising=False)
+    if bn is not None and M * N > 20e6:
+        pytest.skip("forced-tile sweep only on small/medium shapes")
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = torch.randn(N, K, device=cuda, generator=g).bfloat16()
+    out = ops.gemm(a, b)
+    ref = a.float() @ b.float().t()
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("act", ["gelu_tanh", "gelu_erf", "quick_gelu", None])
+def test_gemm_epilogues(cuda, act):
+    from gpt2_vision_language_b200 import ops
+    M, N, K = 1000, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g).bfloat16()
+    res = torch.randn(M, N, device=cuda, generator=g).bfloat16()
+    scale = torch.tensor([0.37], device=cuda)
+    out, aux = ops.gemm(a, w, bias=bias, residual=res, act=act, aux_out=True, scale=scale, alpha=0.5)
+    pre = 0.5 * (a.float() @ w.float().t()) + bias.float()
+    _check(aux, pre)
+    ref = _ref_act(pre, act) * 0.37 + res.float()
+    _check(out, ref)
+    # activation-gradient epilogue: D = acc * act'(aux)
+    if act is not None:
+        dy = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+        wt = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+        d = ops.gemm(dy, wt, aux_in=aux, act=act, dact=True)
+        x = aux.float().requires_grad_(True)
+        _ref_act(x, act).backward(dy.float() @ wt.float().t())
+        _check(d, x.grad)
+
+
+@pytest.mark.parametrize("trans_a,trans_b", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (768, 768, 2112), (4096, 768, 2304), (1984, 768, 50304)])
+def test_gemm_transposed_operands(cuda, trans_a, trans_b, M, N, K):
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn((K, M) if trans_a else (M, K), device=cuda, generator=g).bfloat16()
+    b = torch.randn((K, N) if trans_b else (N, K), device=cuda, generator=g).bfloat16()
+    out = ops.gemm(a, b, trans_a=trans_a, trans_b=trans_b)
+    A = a.float().t() if trans_a else a.float()
+    Bm = b.float() if trans_b else b.float().t()
+    _check(out, A @ Bm)
+
+
+def test_gemm_fp32_out_and_strided(cuda):
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    big = torch.randn(640, 2304, device=cuda, generator=g).bfloat16()
+    a = big[:, 768:1536]  # strided view: lda = 2304
+    w = torch.randn(256, 768, device=cuda, generator=g).bfloat16()
+    out = ops.gemm(a, w, out_fp32=True)
+    assert out.dtype == torch.float32
+    _check(out, a.float() @ w.float().t(), tol=1e-3)
+
+
+def test_gemm_rejects_bad_args(cuda):
+    from gpt2_vision_language_b200 import ops
+    a = torch.randn(16, 12, device=cuda).bfloat16()
+    w = torch.randn(16, 12, device=cuda).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w)  # K % 8 != 0
