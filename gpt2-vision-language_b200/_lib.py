@@ -31,7 +31,7 @@ SIGNATURES = {
     "vlk_attn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_int, c_int, c_int, c_int,
                      c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int,
-                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float, c_void_p],
+                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float, c_void_p, c_void_p],
     "vlk_pool33_l2norm": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_embed_concat_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              c_void_p],

@@ -381,8 +381,11 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
                              float alpha, int out_fp32, void* stream) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
-    VLK_REQUIRE(K % 8 == 0 && N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d and K=%d must be multiples of 8",
-                N, K);
+    VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
+    // K itself is free: K-major operands only need 16-byte row strides (lda/ldb % 8), MN-major operands carry K
+    // as the outer TMA dimension; the K tail of the last 64-wide block is zero-filled by TMA.
+    VLK_REQUIRE(transA || K <= lda, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: lda=%d < K=%d", lda, K);
+    VLK_REQUIRE(transB || K <= ldb, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: ldb=%d < K=%d", ldb, K);
     VLK_REQUIRE(!transA || M % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: transA needs M %% 8 == 0 (M=%d)", M);
     VLK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0, VLK_ERR_ALIGNMENT,
                 "vlk_gemm_bf16: leading dims must be multiples of 8 (lda=%d ldb=%d ldd=%d)", lda, ldb, ldd);

@@ -1,0 +1,60 @@
+"""Data-parallel gradient exchange: one flat bf16 bucket, one NCCL all-reduce (AVG) per step.
+
+Replaces ``DDP(model, device_ids=[local_rank])`` (source/gpt2/train_gpt2.py:270, gpt2_linear/train.py:122,
+gpt2_cross-att/train.py:99).  Differences from stock DDP, all deliberate:
+  * only trainable parameters are reduced (0.6 M / 19.5 M / 28.9 M elements for the caption bridges);
+  * gradients live in ONE contiguous buffer (``p.grad`` are views), so the exchange is a single collective sized
+    for launch latency, not 25 MiB buckets;
+  * the per-forward broadcast of the unused ``attn.bias`` buffers is dropped;
+  * the scalar loss rides along in the same buffer's tail (train_gpt2.py:470-471 all-reduces it separately).
+The collective is ``torch.distributed.all_reduce`` (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU
+tests); averaging of per-rank mean losses / gradients replicates DDP semantics exactly (average of per-rank means,
+not re-weighted by token count — gpt2_linear/model.py:206-210).
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBucket:
+    def __init__(self, params, extra_slots=1):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dtype, device = self.params[0].dtype, self.params[0].device
+        if any(p.dtype != dtype for p in self.params):
+            raise ValueError("FlatGradBucket needs a single gradient dtype")
+        # 16-byte align every view so the fused optimizer can use vector loads
+        align = 16 // torch.empty((), dtype=dtype).element_size()
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + align - 1) // align * align
+        self.extra_off = total
+        total += (extra_slots + align - 1) // align * align
+        self.flat = torch.zeros(total, dtype=dtype, device=device)
+        for p, o in zip(self.params, offs):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.extra = self.flat[self.extra_off:self.extra_off + extra_slots]
+
+    def zero(self):
+        """Replaces optimizer.zero_grad(): one memset; the .grad views stay attached (static addresses)."""
+        self.flat.zero_()
+
+    def all_reduce(self, group=None):
+        """Average over ranks, in place, on the current stream."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:  # gloo has no AVG and no bf16 arithmetic: sum in fp32, divide
+                tmp = self.flat.float()
+                dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+                self.flat.copy_(tmp / dist.get_world_size(group))
+        return self.flat
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """One-time parameter broadcast from rank 0 (what DDP's constructor does); buffers are NOT re-broadcast
+    every forward."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)

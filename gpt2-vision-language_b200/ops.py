@@ -1,15 +1,21 @@
-"""Tensor-level wrappers over the libvlk C ABI (raw device pointers in, nothing allocated natively).
+"""Tensor-level wrappers and autograd Functions over the libvlk C ABI (include/vlk.h).
 
 Everything here runs on the CURRENT torch CUDA stream, is asynchronous and CUDA-graph capturable.
-PyTorch owns every buffer; the native side borrows pointers for the duration of a call.
+PyTorch owns every buffer; the native side borrows raw device pointers for the duration of a call
+(SURVEY 8b "Ownership").  There is no CPU or eager-PyTorch fallback: CPU tensors raise RuntimeError.
+
+Numerics contract (same as the reference's CUDA path, train_gpt2.py:264 + autocast): bf16 parameters,
+bf16 activations and gradients, fp32 accumulation / statistics / softmax / loss inside the kernels.
 """
+import math
+
 import torch
 
 from . import _lib
 from ._lib import check
 
-ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1, 2, 3
-_ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu_erf": 2, "quick_gelu": 3}
+ACT = {None: 0, "none": 0, "gelu_tanh": 1, "gelu_erf": 2, "quick_gelu": 3}
+BF16 = torch.bfloat16
 
 
 def _stream():
@@ -27,14 +33,26 @@ def _need_cuda(*ts):
 
 
 def _bf16c(t):
-    """bf16, 2-D view requirements are the caller's; ensure dtype + inner contiguity."""
-    if t.dtype != torch.bfloat16:
-        t = t.to(torch.bfloat16)
+    """bf16 with a contiguous innermost dim (row stride may be arbitrary)."""
+    if t.dtype != BF16:
+        t = t.to(BF16)
     if t.stride(-1) != 1:
         t = t.contiguous()
     return t
 
 
+def _rows(t):
+    """[..., C] -> contiguous 2-D [rows, C] view (copy only if needed)."""
+    t = _bf16c(t)
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1 or (t2.shape[0] > 1 and t2.stride(0) % 8 != 0):
+        t2 = t2.contiguous()
+    return t2
+
+
+# ======================================================================================================
+# raw ops
+# ======================================================================================================
 def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in=None, aux_out=False,
          scale=None, act=None, dact=False, alpha=1.0, out=None, out_fp32=False):
     """D = epi(alpha * op(a) @ op(b)) with the epilogue of vlk_gemm_bf16 (include/vlk.h).
@@ -52,10 +70,10 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
     if K != Kb:
         raise RuntimeError(f"gemm: contraction mismatch {K} vs {Kb}")
     if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else BF16)
     aux = None
     if aux_out:
-        aux = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+        aux = torch.empty((M, N), device=a.device, dtype=BF16)
     elif aux_in is not None:
         aux = aux_in
     if bias is not None:
@@ -67,7 +85,481 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
                            residual.stride(0) if residual is not None else 0,
                            _p(aux) if (dact or aux_in is not None) else 0,
                            _p(aux) if aux_out else 0, aux.stride(0) if aux is not None else 0,
-                           _p(scale), _ACT[act] if not isinstance(act, int) else act, int(dact), float(alpha),
+                           _p(scale), ACT[act] if not isinstance(act, int) else act, int(dact), float(alpha),
                            int(out_fp32), _stream())
     check(rc, "vlk_gemm_bf16")
     return (out, aux) if aux_out else out
+
+
+def colsum(x2d):
+    """fp32 [cols] column sums of a bf16 [rows, cols] matrix (bias gradients)."""
+    _need_cuda(x2d)
+    out = torch.empty(x2d.shape[1], device=x2d.device, dtype=torch.float32)
+    check(_lib.load().vlk_colsum_bf16(x2d.data_ptr(), out.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0),
+                                      _stream()), "vlk_colsum_bf16")
+    return out
+
+
+def transpose(x2d):
+    _need_cuda(x2d)
+    x2d = _bf16c(x2d)
+    out = torch.empty((x2d.shape[1], x2d.shape[0]), device=x2d.device, dtype=BF16)
+    check(_lib.load().vlk_transpose_bf16(x2d.data_ptr(), out.data_ptr(), x2d.shape[0], x2d.shape[1], x2d.stride(0),
+                                         out.stride(0), _stream()), "vlk_transpose_bf16")
+    return out
+
+
+def layernorm_fwd(x2d, weight, bias, eps=1e-5, save_stats=True):
+    _need_cuda(x2d, weight, bias)
+    rows, cols = x2d.shape
+    y = torch.empty_like(x2d)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x2d.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x2d.device, dtype=torch.float32)
+    check(_lib.load().vlk_layernorm_fwd(x2d.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _p(mean),
+                                        _p(rstd), rows, cols, float(eps), _stream()), "vlk_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False):
+    rows, cols = x2d.shape
+    if dx is None:
+        assert not accumulate
+        dx = torch.empty_like(x2d)
+    dg = db = None
+    if param_grads:
+        dg = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
+        db = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
+    check(_lib.load().vlk_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), dx.data_ptr(), _p(dg), _p(db), rows, cols, int(accumulate),
+                                        _stream()), "vlk_layernorm_bwd")
+    return dx, dg, db
+
+
+def _bt_strides(t):
+    """(batch stride, row stride) in elements of a [B,T,W] view whose last dim is contiguous."""
+    assert t.dim() == 3 and t.stride(2) == 1
+    return t.stride(0), t.stride(1)
+
+
+def attention_fwd(q, k, v, n_head, causal, scale=None, need_lse=True):
+    """q: [B,Tq,H*64] view, k/v: [B,Tk,H*64] views (slices of packed projections are fine). Returns o [B,Tq,H*64], lse."""
+    _need_cuda(q, k, v)
+    B, Tq, W = q.shape
+    Tk = k.shape[1]
+    assert W == n_head * 64, "libvlk attention is specialised for head_dim 64"
+    scale = 1.0 / math.sqrt(64) if scale is None else scale
+    o = torch.empty((B, Tq, W), device=q.device, dtype=BF16)
+    lse = torch.empty((B, n_head, Tq), device=q.device, dtype=torch.float32) if need_lse else None
+    (qb, qr), (kb, kr), (vb, vr), (ob, orr) = _bt_strides(q), _bt_strides(k), _bt_strides(v), _bt_strides(o)
+    check(_lib.load().vlk_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(lse), B, n_head, Tq,
+                                   Tk, qb, qr, kb, kr, vb, vr, ob, orr, int(causal), float(scale), _stream()),
+          "vlk_attn_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n_head, causal, scale=None):
+    """Writes dq/dk/dv (pre-allocated views with the primal shapes)."""
+    B, Tq, W = q.shape
+    Tk = k.shape[1]
+    scale = 1.0 / math.sqrt(64) if scale is None else scale
+    d_o = _bf16c(d_o)
+    if d_o.stride() != o.stride():
+        d_o = d_o.contiguous()
+        assert d_o.stride() == o.stride()
+    delta = torch.empty((B, n_head, Tq), device=q.device, dtype=torch.float32)
+    (qb, qr), (kb, kr), (vb, vr), (ob, orr) = _bt_strides(q), _bt_strides(k), _bt_strides(v), _bt_strides(o)
+    (dqb, dqr), (dkb, dkr), (dvb, dvr) = _bt_strides(dq), _bt_strides(dk), _bt_strides(dv)
+    check(_lib.load().vlk_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
+                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, n_head, Tq, Tk,
+                                   qb, qr, kb, kr, vb, vr, ob, orr, dqb, dqr, dkb, dkr, dvb, dvr, int(causal),
+                                   float(scale), delta.data_ptr(), _stream()), "vlk_attn_bwd")
+
+
+def pool33(tokens, normalize=True):
+    """[B,257,D] -> [B,33,D] (CLS + 4x8 average bins, optional per-token L2 normalise); bf16 or fp32."""
+    _need_cuda(tokens)
+    assert tokens.dim() == 3 and tokens.shape[1] == 257, "expects CLS + 16x16 patch tokens"
+    fp32 = tokens.dtype == torch.float32
+    if not fp32:
+        tokens = _bf16c(tokens)
+    tokens = tokens.contiguous()
+    B, _, D = tokens.shape
+    out = torch.empty((B, 33, D), device=tokens.device, dtype=tokens.dtype)
+    check(_lib.load().vlk_pool33_l2norm(tokens.data_ptr(), out.data_ptr(), B, D, int(fp32), int(normalize),
+                                        _stream()), "vlk_pool33_l2norm")
+    return out
+
+
+def embed_concat(ids, wte, wpe, prefix=None, pos0=0):
+    _need_cuda(ids, wte, wpe)
+    ids = ids.contiguous()
+    assert ids.dtype == torch.int64
+    B, T = ids.shape
+    C = wte.shape[1]
+    P = 0 if prefix is None else prefix.shape[1]
+    if prefix is not None:
+        prefix = _bf16c(prefix).contiguous()
+    out = torch.empty((B, P + T, C), device=ids.device, dtype=BF16)
+    check(_lib.load().vlk_embed_concat_fwd(ids.data_ptr(), wte.data_ptr(), wpe.data_ptr(), _p(prefix),
+                                           out.data_ptr(), B, T, P, C, int(pos0), _stream()), "vlk_embed_concat_fwd")
+    return out
+
+
+def add(a, b):
+    _need_cuda(a, b)
+    a, b = _bf16c(a).contiguous(), _bf16c(b).contiguous()
+    y = torch.empty_like(a)
+    check(_lib.load().vlk_add_bf16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream()), "vlk_add_bf16")
+    return y
+
+
+def argmax_rows(logits2d):
+    _need_cuda(logits2d)
+    rows, V = logits2d.shape
+    out = torch.empty(rows, device=logits2d.device, dtype=torch.int64)
+    check(_lib.load().vlk_argmax_rows(logits2d.data_ptr(), out.data_ptr(), rows, V, logits2d.stride(0), _stream()),
+          "vlk_argmax_rows")
+    return out
+
+
+def im2col_patch14(pixels, kpad=640):
+    _need_cuda(pixels)
+    assert pixels.shape[1:] == (3, 224, 224)
+    fp32 = pixels.dtype == torch.float32
+    if not fp32:
+        pixels = pixels.to(BF16)
+    pixels = pixels.contiguous()
+    B = pixels.shape[0]
+    out = torch.empty((B * 256, kpad), device=pixels.device, dtype=BF16)
+    check(_lib.load().vlk_im2col_patch14(pixels.data_ptr(), out.data_ptr(), B, kpad, int(fp32), _stream()),
+          "vlk_im2col_patch14")
+    return out
+
+
+def clip_assemble(patch2d, cls, pos, B):
+    D = patch2d.shape[1]
+    out = torch.empty((B, 257, D), device=patch2d.device, dtype=BF16)
+    check(_lib.load().vlk_clip_assemble(patch2d.data_ptr(), cls.data_ptr(), pos.data_ptr(), out.data_ptr(), B, D,
+                                        _stream()), "vlk_clip_assemble")
+    return out
+
+
+# ======================================================================================================
+# autograd Functions (what the drop-in nn.Modules are made of)
+# ======================================================================================================
+def _param_ok(*ps):
+    for p in ps:
+        if p is not None and (p.dtype != BF16 or not p.is_cuda):
+            raise RuntimeError(
+                "the B200 path needs bf16 CUDA parameters (the reference does model.to(device).to(torch.bfloat16), "
+                "source/gpt2/train_gpt2.py:263-264); got dtype=%s device=%s" % (p.dtype, p.device))
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b (+ residual).  nn.Linear forward + dgrad/wgrad, all on vlk_gemm_bf16."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        _param_ok(weight, bias)
+        x2 = _rows(x)
+        res2 = _rows(residual) if residual is not None else None
+        y = gemm(x2, weight, bias=bias, residual=res2)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = _rows(dy)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, weight, trans_b=True).view(ctx.x_shape)          # [M,N] x [N,K]
+        if ctx.needs_input_grad[1]:
+            dw = gemm(dy2, x2, trans_a=True, trans_b=True)                  # dy^T [N,M] x x [M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2).to(BF16)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres
+
+
+def linear(x, weight, bias=None, residual=None):
+    return LinearFn.apply(x, weight, bias, residual)
+
+
+class MLPFn(torch.autograd.Function):
+    """y = residual + act(x @ Wfc^T + bfc) @ Wproj^T + bproj with the activation and its gradient fused in the
+    GEMM epilogues (MLP at train_gpt2.py:46-59; Q-Former mlp at gpt2_q_former/model.py:126-130)."""
+
+    @staticmethod
+    def forward(ctx, x, w_fc, b_fc, w_proj, b_proj, residual, act):
+        _param_ok(w_fc, b_fc, w_proj, b_proj)
+        x2 = _rows(x)
+        res2 = _rows(residual) if residual is not None else None
+        need_bwd = any(ctx.needs_input_grad)
+        if need_bwd:
+            h, u = gemm(x2, w_fc, bias=b_fc, act=act, aux_out=True)
+        else:
+            h, u = gemm(x2, w_fc, bias=b_fc, act=act), None
+        y = gemm(h, w_proj, bias=b_proj, residual=res2)
+        if need_bwd:
+            wgrad = any(ctx.needs_input_grad[1:5])
+            ctx.save_for_backward(x2 if wgrad else None, u, h if wgrad else None, w_fc, w_proj)
+        ctx.act = act
+        ctx.x_shape = x.shape
+        ctx.has_res = residual is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, u, h, w_fc, w_proj = ctx.saved_tensors
+        dy2 = _rows(dy)
+        du = gemm(dy2, w_proj, trans_b=True, aux_in=u, act=ctx.act, dact=True)   # (dy @ Wproj) * act'(u)
+        dx = dwfc = dbfc = dwp = dbp = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(du, w_fc, trans_b=True).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dwfc = gemm(du, x2, trans_a=True, trans_b=True)
+        if ctx.needs_input_grad[2]:
+            dbfc = colsum(du).to(BF16)
+        if ctx.needs_input_grad[3]:
+            dwp = gemm(dy2, h, trans_a=True, trans_b=True)
+        if ctx.needs_input_grad[4]:
+            dbp = colsum(dy2).to(BF16)
+        if ctx.has_res and ctx.needs_input_grad[5]:
+            dres = dy
+        return dx, dwfc, dbfc, dwp, dbp, dres, None
+
+
+def mlp(x, w_fc, b_fc, w_proj, b_proj, residual=None, act="gelu_tanh"):
+    return MLPFn.apply(x, w_fc, b_fc, w_proj, b_proj, residual, act)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _param_ok(weight, bias)
+        x2 = _rows(x)
+        need_bwd = any(ctx.needs_input_grad)
+        y, mean, rstd = layernorm_fwd(x2, weight, bias, eps, save_stats=need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.x_shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx, dg, db = layernorm_bwd(_rows(dy).contiguous(), x2, weight, mean, rstd, param_grads=pg)
+        return (dx.view(ctx.x_shape) if ctx.needs_input_grad[0] else None,
+                dg.to(BF16) if (pg and ctx.needs_input_grad[1]) else None,
+                db.to(BF16) if (pg and ctx.needs_input_grad[2]) else None, None)
+
+
+def layernorm(x, weight, bias, eps=1e-5):
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+class SelfAttnFn(torch.autograd.Function):
+    """Attention over a packed projection qkv [B,T,3C] (c_attn output, train_gpt2.py:35-41; CLIP fused q/k/v;
+    nn.MultiheadAttention in_proj with q=k=v).  The gradient is written straight into a packed [B,T,3C] buffer."""
+
+    @staticmethod
+    def forward(ctx, qkv, n_head, causal):
+        qkv = _bf16c(qkv)
+        C = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        need_bwd = ctx.needs_input_grad[0]
+        o, lse = attention_fwd(q, k, v, n_head, causal, need_lse=need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(qkv, o, lse)
+        ctx.n_head, ctx.causal = n_head, causal
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        C = qkv.shape[-1] // 3
+        dqkv = torch.empty_like(qkv)
+        attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, d_o, lse, dqkv[..., :C],
+                      dqkv[..., C:2 * C], dqkv[..., 2 * C:], ctx.n_head, ctx.causal)
+        return dqkv, None, None
+
+
+def self_attention(qkv, n_head, causal):
+    return SelfAttnFn.apply(qkv, n_head, causal)
+
+
+class CrossAttnFn(torch.autograd.Function):
+    """q [B,T,C] attends to a packed kv [B,S,2C] (CrossAttention at gpt2_cross-att/model.py:45-57; the cross
+    nn.MultiheadAttention of the Q-Former, gpt2_q_former/model.py:140).  Non-causal."""
+
+    @staticmethod
+    def forward(ctx, q, kv, n_head):
+        q, kv = _bf16c(q), _bf16c(kv)
+        C = q.shape[-1]
+        need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        o, lse = attention_fwd(q, kv[..., :C], kv[..., C:], n_head, False, need_lse=need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(q, kv, o, lse)
+        ctx.n_head = n_head
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse = ctx.saved_tensors
+        C = q.shape[-1]
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        attention_bwd(q, kv[..., :C], kv[..., C:], o, d_o, lse, dq, dkv[..., :C], dkv[..., C:], ctx.n_head, False)
+        return dq, dkv, None
+
+
+def cross_attention(q, kv, n_head):
+    return CrossAttnFn.apply(q, kv, n_head)
+
+
+class GatedProjFn(torch.autograd.Function):
+    """x + tanh(gate) * (y @ W^T + b): the gated cross-attention residual of gpt2_cross-att/model.py:101.
+    tanh(gate) is a device scalar applied in the GEMM epilogue; the un-gated projection is kept (aux) for
+    the gate gradient  d gate = (1 - tanh^2) * sum(dout * proj)."""
+
+    @staticmethod
+    def forward(ctx, y, weight, bias, gate, residual):
+        _param_ok(weight, bias)
+        y2, res2 = _rows(y), _rows(residual)
+        tg = torch.tanh(gate.detach().float()).reshape(1)
+        need_gate = ctx.needs_input_grad[3]
+        if need_gate:
+            out, proj = gemm(y2, weight, bias=bias, scale=tg, residual=res2, aux_out=True)
+        else:
+            out, proj = gemm(y2, weight, bias=bias, scale=tg, residual=res2), None
+        ctx.save_for_backward(y2, weight, tg, proj, gate)
+        ctx.shape = y.shape
+        ctx.has_bias = bias is not None
+        return out.view(residual.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        y2, weight, tg, proj, gate = ctx.saved_tensors
+        d2 = _rows(dout).contiguous()
+        dy = dw = db = dgate = None
+        if ctx.needs_input_grad[3]:
+            acc = torch.zeros(1, device=d2.device, dtype=torch.float32)
+            g32 = gate.detach().float().reshape(1)
+            check(_lib.load().vlk_gate_grad(d2.data_ptr(), proj.data_ptr(), g32.data_ptr(), acc.data_ptr(),
+                                            d2.numel(), _stream()), "vlk_gate_grad")
+            dgate = acc.reshape(gate.shape).to(gate.dtype)
+        if ctx.needs_input_grad[0]:
+            dy = gemm(d2, weight, trans_b=True, scale=tg).view(ctx.shape)     # tanh(g) * dout @ W
+        if ctx.needs_input_grad[1]:
+            dw = gemm(d2, y2, trans_a=True, trans_b=True, scale=tg)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = (colsum(d2) * tg).to(BF16)
+        return dy, dw, db, dgate, dout if ctx.needs_input_grad[4] else None
+
+
+def gated_proj_residual(y, weight, bias, gate, residual):
+    return GatedProjFn.apply(y, weight, bias, gate, residual)
+
+
+class EmbedConcatFn(torch.autograd.Function):
+    """[prefix ; wte[ids] + wpe[pos]] (GPT.forward train_gpt2.py:114-117; caption variant
+    gpt2_linear/model.py:187-200: positions restart at 0 for the text, the image prefix has none)."""
+
+    @staticmethod
+    def forward(ctx, ids, wte, wpe, prefix):
+        _param_ok(wte, wpe)
+        out = embed_concat(ids, wte, wpe, prefix)
+        ctx.save_for_backward(ids)
+        ctx.P = 0 if prefix is None else prefix.shape[1]
+        ctx.wte_shape, ctx.wpe_shape = wte.shape, wpe.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dout = _bf16c(dout).contiguous()
+        dwte = dwpe = dprefix = None
+        need_wte, need_wpe = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if need_wte or need_wpe:
+            B, T = ids.shape
+            C = dout.shape[-1]
+            f_wte = torch.zeros(ctx.wte_shape, device=dout.device, dtype=torch.float32) if need_wte else None
+            f_wpe = torch.zeros(ctx.wpe_shape, device=dout.device, dtype=torch.float32) if need_wpe else None
+            check(_lib.load().vlk_embed_bwd(ids.data_ptr(), dout.data_ptr(), _p(f_wte), _p(f_wpe), B, T, ctx.P, C,
+                                            _stream()), "vlk_embed_bwd")
+            dwte = f_wte.to(BF16) if need_wte else None
+            dwpe = f_wpe.to(BF16) if need_wpe else None
+        if ctx.P and ctx.needs_input_grad[3]:
+            dprefix = dout[:, :ctx.P]
+        return None, dwte, dwpe, dprefix
+
+
+def embed(ids, wte, wpe, prefix=None):
+    return EmbedConcatFn.apply(ids, wte, wpe, prefix)
+
+
+class LMHeadCEFn(torch.autograd.Function):
+    """mean cross-entropy of (h @ W^T) against labels without ever holding the [rows, V] logits:
+    rows are processed in chunks small enough for the chunk's logits to stay L2-resident — lm_head GEMM,
+    in-place softmax-CE (loss + d logits), then the d h (and optional d W) GEMMs consume the chunk.
+    Replaces lm_head + F.cross_entropy at train_gpt2.py:121-124, gpt2_linear/model.py:172,204-210
+    (ignore_index=-100) and the masked mean of gpt2_cross-att/model.py:176-185 (row_weight = mask).
+    The gradient is produced in the forward pass and scaled by the incoming scalar in backward."""
+
+    CHUNK_ROWS = 512
+
+    @staticmethod
+    def forward(ctx, h, weight, labels, row_weight):
+        _param_ok(weight)
+        lib = _lib.load()
+        h2 = _rows(h)
+        rows, C = h2.shape
+        V = weight.shape[0]
+        labels = labels.reshape(-1).contiguous()
+        assert labels.dtype == torch.int64 and labels.numel() == rows
+        rw = row_weight.reshape(-1).float().contiguous() if row_weight is not None else None
+        dev = h2.device
+        stats = torch.zeros(2, device=dev, dtype=torch.float32)           # [loss, 1/count]
+        loss_row = torch.empty(rows, device=dev, dtype=torch.float32)
+        check(lib.vlk_ce_count(labels.data_ptr(), _p(rw), stats.data_ptr(), rows, _stream()), "vlk_ce_count")
+        need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        write_grad = need_dh or need_dw
+        dh = torch.empty_like(h2) if need_dh else None
+        dw = None
+        chunk = LMHeadCEFn.CHUNK_ROWS
+        logits = torch.empty((min(chunk, rows), V), device=dev, dtype=BF16)
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            lg = logits[: r1 - r0]
+            gemm(h2[r0:r1], weight, out=lg)
+            check(lib.vlk_softmax_ce_rows(lg.data_ptr(), labels[r0:r1].data_ptr(), _p(rw[r0:r1]) if rw is not None else 0,
+                                          loss_row[r0:r1].data_ptr(), stats[1:].data_ptr(), r1 - r0, V, lg.stride(0),
+                                          int(write_grad), _stream()), "vlk_softmax_ce_rows")
+            if need_dh:
+                gemm(lg, weight, trans_b=True, out=dh[r0:r1])                 # d logits [r,V] x W [V,C]
+            if need_dw:
+                if dw is None:
+                    dw = gemm(lg, h2[r0:r1], trans_a=True, trans_b=True)      # d logits^T x h
+                else:
+                    gemm(lg, h2[r0:r1], trans_a=True, trans_b=True, out=dw, residual=dw)
+        check(lib.vlk_ce_finalize(loss_row.data_ptr(), _p(rw), stats.data_ptr(), rows, _stream()), "vlk_ce_finalize")
+        ctx.save_for_backward(dh, dw)
+        ctx.h_shape = h.shape
+        return stats[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dh, dw = ctx.saved_tensors
+        g = dloss.to(BF16)
+        return (dh * g).view(ctx.h_shape) if dh is not None else None, (dw * g) if dw is not None else None, None, None
+
+
+def lmhead_ce(h, weight, labels, row_weight=None):
+    return LMHeadCEFn.apply(h, weight, labels, row_weight)

@@ -1,0 +1,86 @@
+"""The captioning training step as ONE replayable unit of GPU work.
+
+Reference step body: source/gpt2_linear/train.py:291-326 and source/gpt2_cross-att/train.py:272-303
+(batch -> device, labels = y.masked_fill(~m, -100), pool, autocast forward, backward, all-reduce,
+clip_grad_norm_(1.0), set lr, optimizer.step()) with the CLIP ViT-L/14 forward in front of it (north_star).
+
+``CaptionTrainStep`` owns static input buffers and (optionally) captures the whole step — CLIP forward, pooling,
+bridge, GPT-2 forward/backward, loss, gradient all-reduce, clip-norm + AdamW — into a CUDA graph, so a step is a
+single graph launch with no host work in between (shapes are static: B x 224 x 224 images, 31-token captions).
+"""
+import torch
+
+from . import ops
+from .caption import pool_clip_197_to_33_avg_with_cls
+from .dp import FlatGradBucket
+
+
+class CaptionTrainStep:
+    def __init__(self, model, clip_tower, kind, batch, text_len=31, lr=1e-3, weight_decay=0.1, max_norm=1.0,
+                 use_graph=True, pixels_dtype=torch.float32, group=None):
+        """kind: 'linear' | 'qformer' (GPT_Caption(patch_tokens, input_ids, labels)) or 'xattn'
+        (GPT(idx, z, targets, target_mask))."""
+        assert kind in ("linear", "qformer", "xattn")
+        self.model, self.clip, self.kind, self.group = model, clip_tower, kind, group
+        self.max_norm, self.use_graph = max_norm, use_graph
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.pixels = torch.zeros(batch, 3, 224, 224, device=dev, dtype=pixels_dtype)
+        self.x = torch.zeros(batch, text_len, device=dev, dtype=torch.int64)
+        self.y = torch.zeros(batch, text_len, device=dev, dtype=torch.int64)
+        self.mask = torch.ones(batch, text_len, device=dev, dtype=torch.bool)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float32)
+        self.norm = torch.zeros((), device=dev, dtype=torch.float32)
+        self.bucket = FlatGradBucket(model.parameters())
+        self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
+        self.graph = None
+        self._warm = 0
+
+    # -------------------------------------------------------------------------------------------------
+    def _body(self):
+        feats = self.clip(self.pixels)                                    # [B,257,768]
+        z = pool_clip_197_to_33_avg_with_cls(feats)                       # [B,33,768], unit-norm rows
+        self.bucket.zero()
+        if self.kind == "xattn":
+            _, loss = self.model(self.x, z=z, targets=self.y, target_mask=self.mask)
+        else:
+            labels = self.y.masked_fill(~self.mask, -100)
+            _, loss = self.model(z, self.x, labels=labels)
+        loss.backward()
+        self.bucket.extra[0] = loss.detach()                              # the loss rides in the gradient bucket
+        self.bucket.all_reduce(self.group)
+        self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
+        self.opt.step()
+        self.loss.copy_(self.bucket.extra[0])
+
+    def set_lr(self, lr):
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+
+    def load_batch(self, pixels, x, y, mask, non_blocking=True):
+        """Host (pinned) or device tensors -> the static input buffers."""
+        self.pixels.copy_(pixels, non_blocking=non_blocking)
+        self.x.copy_(x, non_blocking=non_blocking)
+        self.y.copy_(y, non_blocking=non_blocking)
+        self.mask.copy_(mask, non_blocking=non_blocking)
+
+    def run(self):
+        """One optimizer step on the current contents of the static buffers. Returns the (device) loss tensor."""
+        if not self.use_graph:
+            self._body()
+            return self.loss
+        if self.graph is None:
+            # two eager warm-up steps on a side stream (allocator / lazy state), then capture
+            if self._warm < 2:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._body()
+                torch.cuda.current_stream().wait_stream(s)
+                self._warm += 1
+                return self.loss
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+        self.graph.replay()
+        return self.loss

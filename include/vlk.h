@@ -53,13 +53,12 @@ long long vlk_launch_count(void);
  *   epi, in this order: v = alpha*acc; v += bias[n]; aux_out[m,n] = v; v = act(v) (dact == 0) or
  *   v *= act'(aux_in[m,n]) (dact != 0); v *= *scale; v += residual[m,n]; D[m,n] = bf16(v)
  *   (or fp32 when out_fp32 != 0).  Any of bias / residual / aux_in / aux_out / scale may be NULL.
- *   If bias_grad is non-NULL (fp32 [N], pre-zeroed) the column sums of the *A-side operand rows* are not
- *   computed here — see vlk_colsum_bf16.
  * Replaces: nn.Linear / F.linear at train_gpt2.py:35,42,56-58,121; gpt2_linear/model.py:128;
  *   gpt2_cross-att/model.py:49-57,83; gpt2_q_former/model.py:126-130,160 and the in/out projections of
  *   nn.MultiheadAttention (:119,:123); HF modeling_clip.py q/k/v/out_proj, fc1/fc2, patch_embedding,
  *   visual_projection; plus their autograd dgrad / wgrad GEMMs.
- * Requirements: M,N,K > 0; K % 8 == 0, N % 8 == 0; lda/ldb/ldd/ldr/ld_aux % 8 == 0; 16-byte aligned bases.
+ * Requirements: M,N,K > 0; N % 8 == 0 (and M % 8 == 0 when transA); lda/ldb/ldd/ldr/ld_aux % 8 == 0;
+ *   16-byte aligned bases.  K is free (the tail of the last 64-wide k-block is zero-filled by TMA).
  */
 int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                   int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
@@ -99,7 +98,7 @@ int vlk_attn_bwd(const void* q, const void* k, const void* v, const void* o, con
                  void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs,
                  long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs,
                  int dq_rs, long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
-                 void* stream);
+                 float* delta_scratch /* fp32 [B*H*Tq], overwritten */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * 257 -> 33 token pooling: keep CLS, average the 16x16 patch grid into 4 rows x 8 cols of bins
