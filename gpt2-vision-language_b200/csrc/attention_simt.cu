@@ -56,14 +56,14 @@ __device__ __forceinline__ float dot64(const float* __restrict__ qv, const bf16*
 __global__ void __launch_bounds__(kWarps * 32)
 attn_fwd_simt_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                      bf16* __restrict__ o, float* __restrict__ lse, int H, int Tq, int Tk, Addr qa, Addr ka, Addr va,
-                     Addr oa, int causal, float scale) {
+                     Addr oa, int causal, float scale, int q_row0) {
     __shared__ __align__(16) bf16 sK[TILE * LDS];
     __shared__ __align__(16) bf16 sV[TILE * LDS];
     __shared__ __align__(16) float sQ[ROWS_PER_BLOCK][D];
     __shared__ float sP[kWarps][TILE];
 
     const int b = blockIdx.z, h = blockIdx.y;
-    const int q0 = blockIdx.x * ROWS_PER_BLOCK;
+    const int q0 = q_row0 + blockIdx.x * ROWS_PER_BLOCK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bf16* qb = q + b * qa.bs + h * D;
     const bf16* kb = k + b * ka.bs + h * D;
@@ -338,11 +338,12 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
 
 int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                  int o_rs, int causal, float scale, cudaStream_t stream) {
-    const dim3 grid((Tq + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
+                  int o_rs, int causal, float scale, cudaStream_t stream, int q_row0) {
+    // rows [q_row0, Tq) of every (batch, head)
+    const dim3 grid((Tq - q_row0 + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
     attn_fwd_simt_kernel<<<grid, kWarps * 32, 0, stream>>>(
         static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v), static_cast<bf16*>(o),
-        lse, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, causal, scale);
+        lse, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, causal, scale, q_row0);
     VLK_CHECK_LAUNCH("vlk_attn_fwd(simt)");
     return VLK_OK;
 }
@@ -381,19 +382,4 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
         Addr{dv_bs, dv_rs}, causal, scale);
     VLK_CHECK_LAUNCH("vlk_attn_bwd(dkv)");
     return VLK_OK;
-}
-
-extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq,
-                            int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
-                            long long o_bs, int o_rs, int causal, float scale, void* stream) {
-    VLK_REQUIRE(q && k && v && o, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: null pointer");
-    VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: B=%d H=%d Tq=%d Tk=%d", B, H,
-                Tq, Tk);
-    VLK_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
-                    v_bs % 8 == 0 && o_bs % 8 == 0,
-                VLK_ERR_ALIGNMENT, "vlk_attn_fwd: strides must be multiples of 8 elements");
-    VLK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VLK_ERR_ALIGNMENT,
-                "vlk_attn_fwd: 16B alignment");
-    return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale,
-                         static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,316 @@
+// Attention forward on the tcgen05 tensor cores for mid-length sequences (64 < Tk <= 272: the CLIP ViT-L/14
+// encoder has 257 tokens, 16 heads x 64).  One CTA = 128 query rows of one (batch, head):
+//
+//   TMA:  Q [128 x 64], K [Tk x 64], V [Tk x 64]  -> shared memory (128B swizzle, zero-filled past the sequence)
+//   MMA1: S = Q K^T            (M=128, N=Tk padded to 16, K=64; fp32 in TMEM, 272 columns)
+//   softmax: thread t owns TMEM lane t = one query row -> no cross-thread reduction at all;
+//            row max, exp2, row sum in registers; un-normalised P written as bf16 into a swizzled K-major
+//            shared-memory tile
+//   MMA2: O = P V              (M=128, N=64, K=Tk; V is fed as an MN-major B operand, i.e. no transpose)
+//   epilogue: O / rowsum -> bf16 -> global; optional log-sum-exp for the backward pass.
+//
+// The whole key range fits one tile, so there is no online-softmax rescaling here; sequences longer than 272
+// use the streaming kernel in attention_simt.cu.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlk {
+
+int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                  long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                  int o_rs, int causal, float scale, cudaStream_t stream, int q_row0);
+
+namespace {
+
+constexpr int kMaxKeys = 272;
+constexpr int kQBytes = 128 * 128;                 // 128 rows x 64 bf16
+constexpr int kKVBytes = 35 * 1024;                // >= 272 rows x 128 B, multiple of 1024
+constexpr int kPSlabBytes = 128 * 128;             // 128 rows x 64 keys
+constexpr int kPSlabs = (kMaxKeys + 63) / 64;      // 5
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kQBytes;
+constexpr int kOffV = kOffK + kKVBytes;
+constexpr int kOffP = kOffV + kKVBytes;
+constexpr int kOffBar = kOffP + kPSlabs * kPSlabBytes;
+constexpr int kSmemBytes = kOffBar + 64 + 1024;    // barriers + tmem slot + alignment slack
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemO = 320;                   // O accumulator columns [320, 384)
+
+struct FwdParams {
+    bf16* o;
+    float* lse;
+    long long o_bs;
+    int o_rs;
+    int H, Tq, Tk, tkp, box_rows, causal;
+    float scale_log2e, scale;
+};
+
+__global__ void __launch_bounds__(128, 1)
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint64_t* bar_v = bar_qk + 1;
+    uint64_t* bar_s = bar_qk + 2;
+    uint64_t* bar_o = bar_qk + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int tkp = p.tkp;
+    const int n1 = tkp > 256 ? 256 : tkp, n2 = tkp - n1;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        ptx::mbar_init(bar_qk, 1);
+        ptx::mbar_init(bar_v, 1);
+        ptx::mbar_init(bar_s, 1);
+        ptx::mbar_init(bar_o, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (threadIdx.x == 0) {
+        const int nbox = tkp / p.box_rows;  // 1 or 2
+        const uint32_t kv_bytes = static_cast<uint32_t>(tkp) * 128u;
+        ptx::mbar_arrive_expect_tx(bar_qk, kQBytes + kv_bytes);
+        ptx::tma_load_3d(smem + kOffQ, &tmap_q, bar_qk, h * 64, q0, b);
+        for (int i = 0; i < nbox; ++i)
+            ptx::tma_load_3d(smem + kOffK + i * p.box_rows * 128, &tmap_k, bar_qk, h * 64, i * p.box_rows, b);
+        ptx::mbar_arrive_expect_tx(bar_v, kv_bytes);
+        for (int i = 0; i < nbox; ++i)
+            ptx::tma_load_3d(smem + kOffV + i * p.box_rows * 128, &tmap_v, bar_v, h * 64, i * p.box_rows, b);
+
+        // ---- S = Q K^T ----
+        ptx::mbar_wait(bar_qk, 0);
+        ptx::tc_fence_after_sync();
+        const uint32_t sq = ptx::smem_u32(smem + kOffQ), sk = ptx::smem_u32(smem + kOffK);
+        const uint32_t idesc1 = ptx::make_idesc_bf16_f32(128, n1, 0, 0);
+        const uint32_t idesc2 = ptx::make_idesc_bf16_f32(128, n2 > 0 ? n2 : 16, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024);
+            ptx::umma_bf16_ss(tmem, da, ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc1, k != 0);
+            if (n2 > 0)
+                ptx::umma_bf16_ss(tmem + 256, da, ptx::make_smem_desc_sw128(sk + 256 * 128 + k * 32, 16, 1024), idesc2,
+                                  k != 0);
+        }
+        ptx::umma_commit(bar_s);
+    }
+
+    // ---- softmax: thread = query row = TMEM lane ----
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after_sync();
+    const int row = threadIdx.x;                    // local query row
+    const int qi = q0 + row;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    int lim = p.Tk;                                 // keys [0, lim) are visible to this row
+    if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
+    if (lim < 1) lim = 1;                           // rows past Tq: keep the math finite, result is discarded
+    float m = -INFINITY;
+    for (int c = 0; c < tkp; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(trow + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
+    }
+    const float mb = m * p.scale_log2e;
+    float sum = 0.f;
+    uint8_t* prow = smem + kOffP + (row >> 3) * 1024 + (row & 7) * 128;
+    for (int c = 0; c < tkp; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(trow + c, r);
+        ptx::tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            e[i] = (c + i < lim) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
+        }
+        // round to bf16 first so that the row sum matches what the tensor core will multiply
+        uint4 lo, hi;
+        {
+            float t0[8], t1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                t0[i] = e[i];
+                t1[i] = e[8 + i];
+            }
+            lo = pack8(t0);
+            hi = pack8(t1);
+            float u0[8], u1[8];
+            unpack8(lo, u0);
+            unpack8(hi, u1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum += u0[i] + u1[i];
+        }
+        const int slab = c >> 6, chunk = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
+        uint8_t* base = prow + slab * kPSlabBytes;
+        *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = lo;
+        *reinterpret_cast<uint4*>(base + (((chunk + 1) ^ (row & 7)) << 4)) = hi;
+    }
+    // generic-proxy smem writes -> visible to the tensor core (async proxy), then CTA-wide hand-off
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        // ---- O = P V ----
+        ptx::mbar_wait(bar_v, 0);
+        ptx::tc_fence_after_sync();
+        const uint32_t sp = ptx::smem_u32(smem + kOffP), sv = ptx::smem_u32(smem + kOffV);
+        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B (= V) is MN-major
+        const int ksteps = tkp / 16;
+        for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = ptx::make_smem_desc_sw128(sp + (k >> 2) * kPSlabBytes + (k & 3) * 32, 16, 1024);
+            const uint64_t db = ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024);
+            ptx::umma_bf16_ss(tmem + kTmemO, da, db, idesc, k != 0);
+        }
+        ptx::umma_commit(bar_o);
+    }
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after_sync();
+    const float inv = 1.0f / sum;
+    if (qi < p.Tq) {
+        bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(trow + kTmemO + c, r);
+            ptx::tmem_ld_wait();
+            float t0[8], t1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                t0[i] = __uint_as_float(r[i]) * inv;
+                t1[i] = __uint_as_float(r[8 + i]) * inv;
+            }
+            stg16(orow + c, pack8(t0));
+            stg16(orow + c + 8, pack8(t1));
+        }
+        if (p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
+    } else {
+        // keep the warp converged for the .sync.aligned TMEM loads of its other lanes
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(trow + kTmemO + c, r);
+            ptx::tmem_ld_wait();
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// [B, T, W] bf16 view (W contiguous, row stride rs, batch stride bs): box = 64 x box_rows x 1, 128B swizzle.
+int make_tmap3(CUtensorMap* map, const void* base, int W, int T, int B, int rs, long long bs, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    VLK_REQUIRE(fn != nullptr, VLK_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLK_REQUIRE(r == CUDA_SUCCESS, VLK_ERR_DRIVER, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+    return VLK_OK;
+}
+
+}  // namespace
+}  // namespace vlk
+
+using namespace vlk;
+
+extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq,
+                            int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
+                            long long o_bs, int o_rs, int causal, float scale, void* stream) {
+    VLK_REQUIRE(q && k && v && o, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: null pointer");
+    VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: B=%d H=%d Tq=%d Tk=%d", B, H,
+                Tq, Tk);
+    VLK_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
+                    v_bs % 8 == 0 && o_bs % 8 == 0,
+                VLK_ERR_ALIGNMENT, "vlk_attn_fwd: strides must be multiples of 8 elements");
+    VLK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VLK_ERR_ALIGNMENT,
+                "vlk_attn_fwd: 16B alignment");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const char* force = getenv("VLK_ATTN_IMPL");
+    const bool want_tc = force ? (strcmp(force, "tcgen05") == 0) : (Tk > 64);
+    if (!want_tc || Tk > kMaxKeys || Tq < 64 || (force && strcmp(force, "simt") == 0))
+        return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                             scale, s, 0);
+
+    // full 128-row query blocks on the tensor cores; a short tail (e.g. the 257th CLIP token) on the CUDA cores
+    int tail = Tq % 128;
+    int tc_rows = Tq - tail;
+    if (tail > 32) {
+        tc_rows = Tq;
+        tail = 0;
+    }
+    static bool configured = false;
+    if (!configured) {
+        VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    FwdParams p;
+    p.o = static_cast<bf16*>(o);
+    p.lse = lse;
+    p.o_bs = o_bs;
+    p.o_rs = o_rs;
+    p.H = H;
+    p.Tq = Tq;
+    p.Tk = Tk;
+    p.tkp = (Tk + 15) / 16 * 16;
+    p.box_rows = p.tkp > 256 ? p.tkp / 2 : p.tkp;
+    p.causal = causal;
+    p.scale = scale;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap3(&tq, q, H * 64, Tq, B, q_rs, q_bs, 128);
+    if (rc) return rc;
+    rc = make_tmap3(&tk, k, H * 64, Tk, B, k_rs, k_bs, p.box_rows);
+    if (rc) return rc;
+    rc = make_tmap3(&tv, v, H * 64, Tk, B, v_rs, v_bs, p.box_rows);
+    if (rc) return rc;
+    const dim3 grid((tc_rows + 127) / 128, H, B);
+    attn_fwd_tcgen05_kernel<<<grid, 128, kSmemBytes, s>>>(tq, tk, tv, p);
+    VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05)");
+    if (tail > 0)
+        return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                             scale, s, tc_rows);
+    return VLK_OK;
+}

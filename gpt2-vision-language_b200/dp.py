@@ -5,8 +5,7 @@ gpt2_cross-att/train.py:99).  Differences from stock DDP, all deliberate (SURVEY
   * only trainable parameters are reduced (0.6 M / 19.5 M / 28.9 M elements for the caption bridges);
   * gradients live in ONE contiguous buffer (``p.grad`` are views), so the exchange is a single collective sized
     for launch latency, not 25 MiB buckets;
-  * the per-forward broadcast of the unused ``attn.bias`` buffers is dropped;
-  * the scalar loss rides along in the same buffer's tail (train_gpt2.py:470-471 all-reduces it separately).
+  * the per-forward broadcast of the unused ``attn.bias`` buffers is dropped.
 The collective is ``torch.distributed.all_reduce`` (NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU
 tests); averaging of per-rank mean losses / gradients replicates DDP semantics exactly (average of per-rank means,
 not re-weighted by token count — gpt2_linear/model.py:206-210).
@@ -16,7 +15,7 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    def __init__(self, params, extra_slots=1):
+    def __init__(self, params, extra_slots=0):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")

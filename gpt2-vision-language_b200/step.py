@@ -9,6 +9,7 @@ bridge, GPT-2 forward/backward, loss, gradient all-reduce, clip-norm + AdamW —
 single graph launch with no host work in between (shapes are static: B x 224 x 224 images, 31-token captions).
 """
 import torch
+import torch.distributed as dist
 
 from . import ops
 from .caption import pool_clip_197_to_33_avg_with_cls
@@ -47,11 +48,13 @@ class CaptionTrainStep:
             labels = self.y.masked_fill(~self.mask, -100)
             _, loss = self.model(z, self.x, labels=labels)
         loss.backward()
-        self.bucket.extra[0] = loss.detach()                              # the loss rides in the gradient bucket
+        self.loss.copy_(loss.detach())
         self.bucket.all_reduce(self.group)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)   # train_gpt2.py:470-471 (AVG)
+            self.loss.div_(dist.get_world_size(self.group))
         self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
         self.opt.step()
-        self.loss.copy_(self.bucket.extra[0])
 
     def set_lr(self, lr):
         for g in self.opt.param_groups:
