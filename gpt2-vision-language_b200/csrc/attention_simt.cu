@@ -5,6 +5,9 @@
 //
 // Addressing: element (b, t, h, d) of Q lives at q + b*q_bs + t*q_rs + h*64 + d (same for K, V, O and the
 // gradients), so packed c_attn / kv_proj / in_proj outputs are consumed without a head transpose.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vlk {
@@ -348,6 +351,13 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
     return VLK_OK;
 }
 
+bool attn_small_applicable(int Tq, int Tk);
+int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                   void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
+                   int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
+                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
+                   cudaStream_t stream);
+
 }  // namespace vlk
 
 using namespace vlk;
@@ -367,6 +377,12 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
     VLK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o), VLK_ERR_ALIGNMENT,
                 "vlk_attn_bwd: 16B alignment");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        const char* force = getenv("VLK_ATTN_IMPL");
+        if (attn_small_applicable(Tq, Tk) && !(force && strcmp(force, "simt") == 0))
+            return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
+                                  o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, s);
+    }
     float* scratch = delta;
     const dim3 gq((Tq + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
     attn_bwd_dq_kernel<<<gq, kWarps * 32, 0, s>>>(

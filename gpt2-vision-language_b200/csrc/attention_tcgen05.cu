@@ -24,6 +24,11 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
                   int o_rs, int causal, float scale, cudaStream_t stream, int q_row0);
 
+bool attn_small_applicable(int Tq, int Tk);
+int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                   int o_rs, int causal, float scale, cudaStream_t stream);
+
 namespace {
 
 constexpr int kMaxKeys = 272;
@@ -269,6 +274,9 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
                 "vlk_attn_fwd: 16B alignment");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const char* force = getenv("VLK_ATTN_IMPL");
+    if (attn_small_applicable(Tq, Tk) && !(force && strcmp(force, "simt") == 0))
+        return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                              scale, s);
     const bool want_tc = force ? (strcmp(force, "tcgen05") == 0) : (Tk > 64);
     if (!want_tc || Tk > kMaxKeys || Tq < 64 || (force && strcmp(force, "simt") == 0))
         return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,

@@ -26,6 +26,7 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kEpiStageBytes = 8192;  // per epilogue warp: input tile + output tile, each 32 rows x 128 B
 
 struct EpiParams {
     const bf16* bias;
@@ -37,6 +38,7 @@ struct EpiParams {
     int ldd, ldr, ld_aux;
     int act, dact, out_fp32;
     float alpha;
+    int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 };
 
 template <int BLOCK_N, int kStages>
@@ -44,7 +46,8 @@ struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kStagingOffset = kStages * kStageBytes;  // kNumEpiWarps x 4 KB epilogue transposers
+    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * kEpiStageBytes;
     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
     static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024B alignment
@@ -133,11 +136,209 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coalescing epilogue.  After tcgen05.ld a thread holds 32 consecutive columns of ONE row, so direct global
+// accesses touch 32 different rows per instruction (32 LSU wavefronts for 512 bytes) and the epilogue becomes
+// LSU-bound — it then throttles the tensor pipe through the TMEM hand-off.  Each epilogue warp therefore owns a
+// 4 KB staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled by row so both access patterns are
+// bank-conflict-free): results are written row-per-thread, then stored with 8 lanes per row, i.e. four full
+// 128-byte lines per instruction.  Residual / activation-gradient inputs take the same route in reverse.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t* stage_at(uint8_t* stage, int row, int chunk) {
+    return stage + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// Coalesced fetch of a 32-row x 64-column bf16 tile into registers (lane = 16-byte chunk lane&7 of rows lane>>3 + 4i),
+// issued well before the values are needed; stage_put() later drops them into the swizzled staging tile.
+__device__ __forceinline__ void tile_prefetch(uint4 (&pre)[8], const bf16* src, int ld, int row0, int col0, int M,
+                                              int ncols, int lane) {
+    const int k = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        pre[i] = make_uint4(0, 0, 0, 0);
+        if (row0 + r < M && k * 8 < ncols) pre[i] = ldg16(src + static_cast<size_t>(row0 + r) * ld + col0 + k * 8);
+    }
+}
+__device__ __forceinline__ void stage_put(uint8_t* stage, const uint4 (&pre)[8], int lane) {
+    const int k = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage_at(stage, i * 4 + (lane >> 3), k)) = pre[i];
+}
+
+__device__ __forceinline__ void stage_store_tile(const uint8_t* stage, bf16* dst, int ld, int row0, int col0, int M,
+                                                 int ncols, int lane) {
+    const int k = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        if (row0 + r < M && k * 8 < ncols)
+            stg16(dst + static_cast<size_t>(row0 + r) * ld + col0 + k * 8,
+                  *reinterpret_cast<const uint4*>(stage_at(const_cast<uint8_t*>(stage), r, k)));
+    }
+}
+
+// Which [M,N] input (if any) travels through the staging tile: the residual, else the activation-gradient input.
+__device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int& ld) {
+    if (ep.residual != nullptr) {
+        ld = ep.ldr;
+        return ep.residual;
+    }
+    ld = ep.ld_aux;
+    return ep.dact ? ep.aux_in : nullptr;
+}
+
+// Called BEFORE waiting for the accumulator: the epilogue warp is idle while the MMAs of its tile run, so the
+// first input tile is fetched under them.
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint4 (&pre)[8], int row0, int n0,
+                                                  int ncols_warp, int M, int N, int lane) {
+    if (ep.out_fp32 || ncols_warp < 64 || (ep.debug & 1) || n0 >= N) return;
+    int ld;
+    const bf16* in = epi_staged_input(ep, ld);
+    if (in != nullptr) tile_prefetch(pre, in, ld, row0, n0, M, min(64, N - n0), lane);
+}
+
+// One warp, its 32 accumulator rows (TMEM lanes), `ncols_warp` columns starting at global column n0.
+// stage = [input tile 4 KB | output tile 4 KB].
+__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint4 (&pre)[8], uint32_t taddr,
+                                              int row0, int n0, int ncols_warp, int M, int N, int lane) {
+    const int row = row0 + lane;
+    if (ep.debug & 1) return;
+    if (ep.out_fp32 || ncols_warp < 64) {
+        // fp32 output (rare) and 32-column slices keep the direct row-per-thread path
+#pragma unroll 1
+        for (int c = 0; c < ncols_warp; c += 32) {
+            const int col0 = n0 + c;
+            if (col0 >= N) break;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c, r);
+            ptx::tmem_ld_wait();
+            if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0));
+        }
+        return;
+    }
+    uint8_t* stage_in = stage;
+    uint8_t* stage_out = stage + 4096;
+    int staged_ld;
+    const bf16* staged_in = epi_staged_input(ep, staged_ld);
+    const bool aux_direct = ep.dact && ep.residual != nullptr;  // both present: aux_in falls back to direct loads
+    const float scale = ep.scale != nullptr ? __ldg(ep.scale) : 1.0f;
+#pragma unroll 1
+    for (int c = 0; c < ncols_warp; c += 64) {
+        const int col0 = n0 + c;
+        if (col0 >= N) break;  // warp-uniform
+        const int ncols = min(64, N - col0);
+        if (staged_in != nullptr) {
+            stage_put(stage_in, pre, lane);
+            __syncwarp();
+            // next input tile: in flight while this one is consumed
+            if (c + 64 < ncols_warp && col0 + 64 < N)
+                tile_prefetch(pre, staged_in, staged_ld, row0, col0 + 64, M, min(64, N - col0 - 64), lane);
+        }
+        // sweep 0 (only with aux_out): pre-activation tile; sweep 1: the output tile
+#pragma unroll 1
+        for (int sweep = (ep.aux_out != nullptr ? 0 : 1); sweep < 2; ++sweep) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h * 32 >= ncols) break;  // warp-uniform
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c + h * 32, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+                const int hc0 = col0 + h * 32;
+                const int hcols = min(32, N - hc0);
+                if (ep.bias != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q * 8 < hcols) {
+                            float b[8];
+                            unpack8(ldg16(ep.bias + hc0 + q * 8), b);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += b[i];
+                        }
+                    }
+                }
+                if (sweep == 1) {
+                    if (ep.dact) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q * 8 < hcols) {
+                                float u[8];
+                                if (aux_direct) {
+                                    if (row < M)
+                                        unpack8(ldg16(ep.aux_in + static_cast<size_t>(row) * ep.ld_aux + hc0 + q * 8), u);
+                                    else {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) u[i] = 0.f;
+                                    }
+                                } else {
+                                    unpack8(*reinterpret_cast<const uint4*>(stage_at(stage_in, lane, h * 4 + q)), u);
+                                }
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[q * 8 + i] *= act_grad(ep.act, u[i]);
+                            }
+                        }
+                    } else if (ep.act != VLK_ACT_NONE) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = act_apply(ep.act, v[i]);
+                    }
+                    if (ep.scale != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= scale;
+                    }
+                    if (ep.residual != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q * 8 < hcols) {
+                                float u[8];
+                                unpack8(*reinterpret_cast<const uint4*>(stage_at(stage_in, lane, h * 4 + q)), u);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[q * 8 + i] += u[i];
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = v[q * 8 + i];
+                    *reinterpret_cast<uint4*>(stage_at(stage_out, lane, h * 4 + q)) = pack8(t);
+                }
+            }
+            __syncwarp();
+            stage_store_tile(stage_out, sweep == 0 ? ep.aux_out : reinterpret_cast<bf16*>(ep.D),
+                             sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// Rasterisation of work units onto the output grid.  A wave of ~148 concurrently running CTAs should touch as few
+// distinct A and B tiles as possible, because what bounds this kernel is unique bytes leaving the L2 (operands
+// shared by concurrent CTAs are merged there).  Units are therefore walked in bands of `group` row-units: inside
+// a band the row index is fastest, then the column block, so a wave covers a (group x 148/group) patch of tiles.
+__device__ __forceinline__ void unit_to_mn(int u, int num_m_units, int num_n_blocks, int group, int& m_unit,
+                                           int& n_blk) {
+    const int band_units = group * num_n_blocks;
+    const int band = u / band_units;
+    const int rem = u - band * band_units;
+    const int rows = min(group, num_m_units - band * group);  // the last band may be shorter
+    n_blk = rem / rows;
+    m_unit = band * group + (rem - n_blk * rows);
+}
+
 // A_MN / B_MN: operand is MN-major in global memory (see file header).
-template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
+// CLUSTER: CTAs per thread-block cluster.  The CTAs of a cluster own CLUSTER consecutive 128-row blocks of the
+// same column block, so they need the same B tile: each CTA fetches 1/CLUSTER of it and TMA-multicasts the slice
+// into every CTA's shared memory.  L2->SM traffic per CTA and k-block drops from (128 + BN) to (128 + BN/CLUSTER)
+// rows of 128 B, which is what bounds this kernel (one SM needs ~94 B/clk un-shared, the L2 delivers ~45).
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN, int CLUSTER>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         int M, int N, int K, EpiParams ep) {
+                         int M, int N, int K, int group, EpiParams ep) {
     using L = SmemLayout<BLOCK_N, kStages>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries (descriptor base_offset = 0).
@@ -151,11 +352,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Work unit = CLUSTER vertically adjacent tiles; cluster c walks units c, c + num_clusters, ...  The last unit
+    // of a column may hang over the bottom edge: such a CTA runs the full protocol on zero-filled rows.
     const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_m_units = (num_m_blocks + CLUSTER - 1) / CLUSTER;
     const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m_blocks * num_n_blocks;
+    const int num_tiles = num_m_units * num_n_blocks;
     const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages; power of two >= 32
+    const int cta_rank = CLUSTER > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+    const int unit0 = blockIdx.x / CLUSTER, unit_stride = gridDim.x / CLUSTER;
+    constexpr uint16_t kMcastMask = static_cast<uint16_t>((1u << CLUSTER) - 1);
 
     if (warp_idx == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
@@ -164,7 +371,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp_idx == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], CLUSTER);  // released by the MMA warp of every CTA in the cluster
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full_bar[s], 1);
@@ -177,18 +384,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    if (CLUSTER > 1) ptx::cluster_sync_all(); else __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
+        if (lane == 0 && !(ep.debug & 2)) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % num_m_blocks;
-                const int n_blk = tile / num_m_blocks;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+                int m_unit, n_blk;
+                unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+                const int m_blk = m_unit * CLUSTER + cta_rank;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
@@ -202,13 +410,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], m_blk * BLOCK_M, kb * BLOCK_K);
                         ptx::tma_load_2d(sa + 8192, &tmap_a, &full_bar[stage], m_blk * BLOCK_M + 64, kb * BLOCK_K);
                     }
-                    if constexpr (!B_MN) {
-                        ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
-                    } else {
+                    if constexpr (CLUSTER == 1) {
+                        if constexpr (!B_MN) {
+                            ptx::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_N / 64; ++j)
-                            ptx::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n_blk * BLOCK_N + j * 64,
-                                             kb * BLOCK_K);
+                            for (int j = 0; j < BLOCK_N / 64; ++j)
+                                ptx::tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n_blk * BLOCK_N + j * 64,
+                                                 kb * BLOCK_K);
+                        }
+                    } else {
+                        // this CTA's slice of the shared B tile, multicast to the whole cluster
+                        constexpr int kSliceRows = BLOCK_N / CLUSTER;
+                        const int n0 = n_blk * BLOCK_N + cta_rank * kSliceRows;
+                        uint8_t* dst = sb + cta_rank * kSliceRows * 128;
+                        if constexpr (!B_MN) {
+                            ptx::tma_load_2d_mcast(dst, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0, kMcastMask);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < kSliceRows / 64; ++j)
+                                ptx::tma_load_2d_mcast(dst + j * 8192, &tmap_b, &full_bar[stage], n0 + j * 64,
+                                                       kb * BLOCK_K, kMcastMask);
+                        }
                     }
                     if (++stage == kStages) {
                         stage = 0;
@@ -224,14 +447,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
                 const int acc = local_tile & 1;
                 const uint32_t acc_phase = (local_tile >> 1) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
+                    if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
                     const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
@@ -246,7 +469,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                  : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
                         ptx::umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    // frees the smem slot (in every CTA that multicasts into it) when these MMAs retire
+                    if constexpr (CLUSTER == 1) ptx::umma_commit(&empty_bar[stage]);
+                    else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -261,37 +486,214 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int half = (warp_idx - kEpiWarp0) >> 2;         // which half of the tile's columns
         constexpr int kColsPerWarp = BLOCK_N / 2;
         int local_tile = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-            const int m_blk = tile % num_m_blocks;
-            const int n_blk = tile / num_m_blocks;
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
+            int m_unit, n_blk;
+            unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+            const int m_blk = m_unit * CLUSTER + cta_rank;
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
+            const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
+            uint4 pre[8];
+            epilogue_prefetch(ep, pre, row0, n0, kColsPerWarp, M, N, lane);
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tc_fence_after_sync();
-            const int row = m_blk * BLOCK_M + quad * 32 + lane;
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-#pragma unroll 1
-            for (int c = 0; c < kColsPerWarp; c += 32) {
-                const int col0 = n_blk * BLOCK_N + half * kColsPerWarp + c;
-                if (col0 >= N) break;  // warp-uniform
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c, r);
-                ptx::tmem_ld_wait();
-                if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0));
-            }
+            epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
+                          kColsPerWarp, M, N, lane);
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) ptx::mbar_arrive_relaxed(&tmem_empty_bar[acc]);
         }
     }
 
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    // no CTA may leave while a peer can still multicast into its shared memory or arrive on its barriers
+    if (CLUSTER > 1) ptx::cluster_sync_all(); else __syncthreads();
     if (warp_idx == 2) {
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a CTA pair (two SMs of one TPC) owns a 256 x BLOCK_N output tile.  Each CTA stages its own
+// 128 rows of A and its own BLOCK_N/2 rows of B; ONE tcgen05.mma issued by the leader drives both tensor cores
+// (M = 256), each SM reading the other half of B through the pair's operand-exchange path.  Per SM this halves the
+// B bytes written by TMA and read by the tensor core: shared-memory traffic drops from 2 x 96 to 2 x 64 B/clk (the
+// single-CTA 128x256 tile is bound by the 128 B/clk shared-memory port, not by the tensor pipe) and the smaller
+// stage (32 KB instead of 48 KB) buys a 6-deep ring.
+//
+// Barrier topology (L = leader = even cluster rank, P = peer):
+//   full[s]       lives in L; armed by L's producer with the bytes of BOTH CTAs; both CTAs' TMA credit it.
+//   empty[s]      one in each CTA; released for both by L's tcgen05.commit (multicast).
+//   tmem_full[a]  one in each CTA; signalled for both by L's commit; each CTA's epilogue drains its own TMEM half.
+//   tmem_empty[a] lives in L; 2 x kNumEpiWarps arrivals (P's epilogue warps arrive remotely).
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int kStages>
+struct SmemLayout2 {
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStagingOffset = kStages * kStageBytes;
+    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * kEpiStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
+    static constexpr int kDynamic = kTotal + 1024;
+};
+
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
+                      int N, int K, int group, EpiParams ep) {
+    using L = SmemLayout2<BLOCK_N, kStages>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int cta_rank = static_cast<int>(ptx::cluster_ctarank());
+    const bool is_leader = cta_rank == 0;
+
+    const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+    const int num_m_units = (num_m_blocks + 1) / 2;
+    const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m_units * num_n_blocks;
+    const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+    const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
+
+    if (warp_idx == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp_idx == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full_bar[s], 1);
+            ptx::mbar_init(&tmem_empty_bar[s], 2 * kNumEpiWarps);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        ptx::tmem_alloc_2sm(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp_idx == 0) {
+        // ===================================== TMA producer (both CTAs) =========================
+        if (lane == 0 && !(ep.debug & 2)) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+                int m_unit, n_blk;
+                unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+                const int m_blk = m_unit * 2 + cta_rank;
+                const int n0 = n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2);
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStageBytes;
+                    uint8_t* sb = sa + L::kABytes;
+                    if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    if constexpr (!A_MN) {
+                        ptx::tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    } else {
+                        ptx::tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], m_blk * BLOCK_M, kb * BLOCK_K);
+                        ptx::tma_load_2d_2sm(sa + 8192, &tmap_a, &full_bar[stage], m_blk * BLOCK_M + 64, kb * BLOCK_K);
+                    }
+                    if constexpr (!B_MN) {
+                        ptx::tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 128; ++j)
+                            ptx::tma_load_2d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local_tile = 0;
+            for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
+                const int acc = local_tile & 1;
+                const uint32_t acc_phase = (local_tile >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                                 : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                        ptx::umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit_2sm(&tmem_full_bar[acc], 0b11);  // both halves of the accumulator are complete
+            }
+        }
+    } else if (warp_idx >= kEpiWarp0) {
+        // ===================================== epilogue (both CTAs, own 128 rows) ===============
+        const int quad = warp_idx & 3;
+        const int half = (warp_idx - kEpiWarp0) >> 2;
+        constexpr int kColsPerWarp = BLOCK_N / 2;
+        int local_tile = 0;
+        for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
+            int m_unit, n_blk;
+            unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+            const int m_blk = m_unit * 2 + cta_rank;
+            const int acc = local_tile & 1;
+            const uint32_t acc_phase = (local_tile >> 1) & 1;
+            const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
+            uint4 pre[8];
+            epilogue_prefetch(ep, pre, row0, n0, kColsPerWarp, M, N, lane);
+            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
+            epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
+                          kColsPerWarp, M, N, lane);
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // the leader's barrier
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync_all();
+    if (warp_idx == 2) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
     }
 }
 
@@ -330,43 +732,113 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer
     return VLK_OK;
 }
 
-template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN, int CLUSTER>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int sms,
            cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N, kStages>;
-    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, kStages, A_MN, B_MN, CLUSTER>;
     static bool configured = false;  // per template instantiation
     if (!configured) {
         VLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
         configured = true;
     }
-    const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
-    const int grid = tiles < sms ? tiles : sms;
-    kern<<<grid, kNumThreads, L::kDynamic, stream>>>(ta, tb, M, N, K, ep);
+    const int m_units = ((M + BLOCK_M - 1) / BLOCK_M + CLUSTER - 1) / CLUSTER;
+    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int max_clusters = sms / CLUSTER;
+    const int grid = (units < max_clusters ? units : max_clusters) * CLUSTER;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L::kDynamic;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // band height: balance distinct A tiles (128 rows each per CTA) against distinct B tiles (BLOCK_N rows) per wave
+    int group = 16 / CLUSTER;
+    if (const char* f = getenv("VLK_GEMM_GROUP")) {
+        const int v = atoi(f);
+        if (v > 0) group = v;
+    }
+    if (group > m_units) group = m_units;
+    VLK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group, ep));
     VLK_CHECK_LAUNCH("vlk_gemm_bf16");
+    return VLK_OK;
+}
+
+template <int BLOCK_N, int kStages, bool A_MN, bool B_MN>
+int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int sms,
+                cudaStream_t stream) {
+    using L = SmemLayout2<BLOCK_N, kStages>;
+    auto kern = gemm_bf16_2cta_kernel<BLOCK_N, kStages, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        VLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+        configured = true;
+    }
+    const int m_units = ((M + BLOCK_M - 1) / BLOCK_M + 1) / 2;
+    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int max_clusters = sms / 2;
+    const int grid = (units < max_clusters ? units : max_clusters) * 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = L::kDynamic;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int group = 8;
+    if (const char* f = getenv("VLK_GEMM_GROUP")) {
+        const int v = atoi(f);
+        if (v > 0) group = v;
+    }
+    if (group > m_units) group = m_units;
+    VLK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group, ep));
+    VLK_CHECK_LAUNCH("vlk_gemm_bf16(2cta)");
     return VLK_OK;
 }
 
 // Relative cost of finishing the problem with a given BLOCK_N: waves x per-tile time.  A 128xBN tile needs
 // max(BN/2 tensor cycles, (128+BN)/4 smem-read cycles) per 16-deep k-step (B300_MICROARCH: floor = M*N/256,
 // smem crossbar 128 B/clk).
-double tile_cost(int M, int N, int bn, int sms) {
-    const long tiles = static_cast<long>((M + BLOCK_M - 1) / BLOCK_M) * ((N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    const double per_tile = fmax(bn / 2.0, (128.0 + bn) / 4.0) + 6.0;
+double tile_cost(int M, int N, int bn, int cluster, int sms) {
+    const long m_units = ((M + BLOCK_M - 1) / BLOCK_M + cluster - 1) / cluster;
+    const long units = m_units * ((N + bn - 1) / bn);
+    const long slots = sms / cluster;
+    const long waves = (units + slots - 1) / slots;
+    // per k-step of 16: tensor cycles bn/2, smem-read cycles (128+bn)/4, L2 delivery (128 + bn/cluster) rows of
+    // 32 B at ~45 B/clk/SM
+    const double per_tile = fmax(fmax(bn / 2.0, (128.0 + bn) / 4.0), (128.0 + bn / cluster) * 32.0 / 45.0) + 6.0;
     return waves * per_tile;
 }
 
 template <bool A_MN, bool B_MN>
-int dispatch(const CUtensorMap* ta, const CUtensorMap* tb_by_bn /*[3]: 256,128,64*/, int M, int N, int K,
-             const EpiParams& ep, int sms, int bn, cudaStream_t stream) {
+int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int sms, int bn,
+             int cluster, cudaStream_t stream) {
+    if (cluster == 3) {  // cta_group::2 pair
+        if (bn == 256) return launch_2cta<256, 5, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
+        return launch_2cta<128, 6, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
+    }
+    if (cluster == 2) {
+        if (bn == 256) return launch<256, 3, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, sms, stream);
+        return launch<128, 5, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, sms, stream);
+    }
     switch (bn) {
         case 256:
-            return launch<256, 4, A_MN, B_MN>(*ta, tb_by_bn[0], M, N, K, ep, sms, stream);
+            return launch<256, 3, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
         case 128:
-            return launch<128, 6, A_MN, B_MN>(*ta, tb_by_bn[1], M, N, K, ep, sms, stream);
+            return launch<128, 5, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
         default:
-            return launch<64, 8, A_MN, B_MN>(*ta, tb_by_bn[2], M, N, K, ep, sms, stream);
+            return launch<64, 6, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
     }
 }
 
@@ -412,39 +884,41 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     ep.dact = dact;
     ep.out_fp32 = out_fp32;
     ep.alpha = alpha;
+    ep.debug = 0;
+    if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
 
-    // tile width: cheapest of 256 / 128 / 64 under the wave-quantisation model
-    int bn = 256;
-    double best = tile_cost(M, N, 256, sms);
-    for (int cand : {128, 64}) {
-        double c = tile_cost(M, N, cand, sms);
-        if (c < best * 0.999) {
-            best = c;
-            bn = cand;
-        }
-    }
+    // Tile selection (measured on B200, profiles/r01_gemm_sweep*.log): the 256-wide tile wins on every shape of
+    // this path (fewer, longer tiles amortise the epilogue; N = 768/1024/2304/3072/4096/50304 all tile well), and
+    // the cta_group::2 pair wins or ties whenever there are at least two 128-row blocks.
+    int bn = N >= 192 ? 256 : (N >= 96 ? 128 : 64);
+    int cluster = (M > BLOCK_M && bn >= 128 && sms % 2 == 0) ? 3 : 1;
+    (void)tile_cost;
     if (const char* f = getenv("VLK_GEMM_BN")) {
         int v = atoi(f);
         if (v == 256 || v == 128 || v == 64) bn = v;
+        if (bn == 64) cluster = 1;
+    }
+    if (const char* f = getenv("VLK_GEMM_CLUSTER")) {  // 1 = single CTA, 2 = multicast pair, 3 = cta_group::2 pair
+        int v = atoi(f);
+        if (v == 1 || ((v == 2 || v == 3) && bn >= 128 && sms % 2 == 0)) cluster = v;
     }
 
-    CUtensorMap ta, tb[3];
+    CUtensorMap ta, tb;
     int rc;
     if (!transA)
         rc = make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M);
     else
         rc = make_tmap(&ta, A, M, K, lda, 64, BLOCK_K);
     if (rc) return rc;
-    const int idx = bn == 256 ? 0 : (bn == 128 ? 1 : 2);
     if (!transB)
-        rc = make_tmap(&tb[idx], B, K, N, ldb, BLOCK_K, bn);
+        rc = make_tmap(&tb, B, K, N, ldb, BLOCK_K, bn / (cluster >= 2 ? 2 : 1));  // one box = this CTA's slice of B
     else
-        rc = make_tmap(&tb[idx], B, N, K, ldb, 64, BLOCK_K);
+        rc = make_tmap(&tb, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (!transA && !transB) return dispatch<false, false>(&ta, tb, M, N, K, ep, sms, bn, s);
-    if (!transA && transB) return dispatch<false, true>(&ta, tb, M, N, K, ep, sms, bn, s);
-    if (transA && !transB) return dispatch<true, false>(&ta, tb, M, N, K, ep, sms, bn, s);
-    return dispatch<true, true>(&ta, tb, M, N, K, ep, sms, bn, s);
+    if (!transA && !transB) return dispatch<false, false>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
+    if (!transA && transB) return dispatch<false, true>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
+    if (transA && !transB) return dispatch<true, false>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
+    return dispatch<true, true>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
 }

@@ -7,20 +7,26 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [
-    # M, N, K, transA, transB, bn
-    (128, 256, 64, 0, 0, 256), (128, 128, 64, 0, 0, 128), (128, 64, 64, 0, 0, 64),
-    (128, 256, 256, 0, 0, 256), (384, 512, 768, 0, 0, 256), (4096, 768, 768, 0, 0, 0),
-    (16448, 1024, 1024, 0, 0, 0), (77, 264, 72, 0, 0, 0),
-    (128, 128, 64, 0, 1, 128), (128, 128, 64, 1, 0, 128), (128, 128, 64, 1, 1, 128),
-    (768, 768, 2112, 1, 1, 0), (4096, 768, 2304, 0, 1, 0), (1000, 256, 512, 1, 0, 256),
+    # M, N, K, transA, transB, bn[, cluster]   (cluster 3 = cta_group::2 pair)
+    (256, 256, 64, 0, 0, 256, 3), (256, 256, 256, 0, 0, 256, 3), (256, 128, 128, 0, 0, 128, 3),
+    (512, 512, 768, 0, 0, 256, 3), (300, 264, 72, 0, 0, 128, 3), (256, 256, 128, 0, 1, 256, 3),
+    (256, 128, 128, 1, 0, 128, 3), (768, 768, 2112, 1, 1, 128, 3), (4096, 768, 2304, 0, 1, 256, 3),
+    (16448, 1024, 1024, 0, 0, 256, 3), (16448, 4096, 1024, 0, 0, 256, 3), (16448, 4096, 1024, 0, 0, 128, 3),
+    (16448, 3072, 1024, 0, 0, 256, 3), (16448, 1024, 4096, 0, 0, 256, 3),
+    (4096, 2304, 768, 0, 0, 256, 3), (4096, 3072, 768, 0, 0, 256, 3), (4096, 768, 3072, 0, 0, 128, 3),
+    (4096, 768, 3072, 0, 0, 256, 3), (4096, 768, 768, 0, 0, 128, 3), (512, 50304, 768, 0, 0, 256, 3),
+    (512, 768, 50304, 0, 1, 128, 3),
 ]
 
 
 def run_case(i):
     import torch
-    M, N, K, ta, tb, bn = CASES[i]
+    M, N, K, ta, tb, bn = CASES[i][:6]
+    cl = CASES[i][6] if len(CASES[i]) > 6 else 0
     if bn:
         os.environ["VLK_GEMM_BN"] = str(bn)
+    if cl:
+        os.environ["VLK_GEMM_CLUSTER"] = str(cl)
     lib = ctypes.CDLL(os.path.join(ROOT, "gpt2-vision-language_b200", "libvlk.so"))
     lib.vlk_last_error_string.restype = ctypes.c_char_p
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
@@ -47,12 +53,12 @@ def run_case(i):
         lib.vlk_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, a.stride(0), b.stride(0), N, ta, tb,
                           0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
     s.record()
-    for _ in range(10):
+    for _ in range(20):
         lib.vlk_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, a.stride(0), b.stride(0), N, ta, tb,
                           0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
     e.record()
     torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / 10
+    ms = s.elapsed_time(e) / 20
     print(f"case {i} {CASES[i]}: max_abs_err={err:.4f} rel={rel:.2e} {'OK' if rel < 2e-2 else 'MISMATCH'} "
           f"{ms*1e3:.1f} us {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     return 0 if rel < 2e-2 else 2
@@ -64,7 +70,7 @@ if __name__ == "__main__":
     bad = 0
     for i in range(len(CASES)):
         try:
-            r = subprocess.run([sys.executable, __file__, str(i)], timeout=120)
+            r = subprocess.run([sys.executable, __file__, str(i)], timeout=90)
             if r.returncode != 0:
                 bad += 1
                 print(f"case {i}: exit {r.returncode}", flush=True)
