@@ -156,8 +156,6 @@ def build_gpu_problem(torch, args, dev, rank):
         lm = gpt2.GPT_previous(gpt2.GPTConfig(vocab_size=50304))
         mod = gpt2_linear if args.workload == "linear" else gpt2_q_former
         model = mod.GPT_Caption(enc_dim=768, lm=lm, m_vis_tokens=32)
-        if args.workload == "qformer":
-            model.bridge.eval()                 # dropout-free Q-Former (see DESIGN.md "Known gaps")
     model = model.to(dev).to(torch.bfloat16)
     clip_sd = ClipVisionTower.random_state_dict(1337, device=dev)
     clip = ClipVisionTower.from_state_dict(clip_sd, device=dev)

@@ -27,11 +27,13 @@ SIGNATURES = {
     "vlk_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_int, c_int, c_void_p],
     "vlk_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float, c_void_p],
+                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float,
+                     c_float, c_void_p, ctypes.c_uint, c_void_p],
     "vlk_attn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_int, c_int, c_int, c_int,
                      c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int,
-                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float, c_void_p, c_void_p],
+                     c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float, c_void_p,
+                     c_float, c_void_p, ctypes.c_uint, c_void_p],
     "vlk_pool33_l2norm": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_embed_concat_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              c_void_p],
@@ -47,6 +49,7 @@ SIGNATURES = {
     "vlk_add_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "vlk_cast_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "vlk_cast_bf16_to_f32": [c_void_p, c_void_p, c_ll, c_void_p],
+    "vlk_dropout_add_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_void_p, ctypes.c_uint, c_void_p],
     "vlk_gate_grad": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "vlk_argmax_rows": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }

@@ -337,12 +337,98 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// forward for a handful of query rows (the 257th CLIP token left over after the 128-row tensor-core blocks):
+// one WARP per (batch, head, row).  Lanes stride the keys for the scores (each K row is one 128-byte line),
+// softmax by warp shuffles, then each lane owns two output dims and walks the keys with coalesced V reads.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFewMaxKeys = 288;  // 9 keys per lane
+
+__global__ void __launch_bounds__(128)
+attn_fwd_fewrows_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
+                        bf16* __restrict__ o, float* __restrict__ lse, int B, int H, int Tq, int Tk, Addr qa, Addr ka,
+                        Addr va, Addr oa, int causal, float scale, int q_row0) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int nrows = Tq - q_row0;
+    if (w >= B * H * nrows) return;
+    const int qi = q_row0 + w % nrows;
+    const int h = (w / nrows) % H, b = w / (nrows * H);
+    const bf16* qrow = q + b * qa.bs + static_cast<size_t>(qi) * qa.rs + h * D;
+    const bf16* kb = k + b * ka.bs + h * D;
+    const bf16* vb = v + b * va.bs + h * D;
+    const int lim = causal ? min(Tk, qi + (Tk - Tq) + 1) : Tk;
+    float qf[D];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float t[8];
+        unpack8(ldg16(qrow + c * 8), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qf[c * 8 + i] = t[i] * scale;
+    }
+    float s[kFewMaxKeys / 32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
+        const int key = j * 32 + lane;
+        s[j] = -INFINITY;
+        if (key < lim) {
+            const bf16* kr = kb + static_cast<size_t>(key) * ka.rs;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float t[8];
+                unpack8(ldg16(kr + c * 8), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(qf[c * 8 + i], t[i], acc);
+            }
+            s[j] = acc;
+            m = fmaxf(m, acc);
+        }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
+        s[j] = (j * 32 + lane < lim) ? __expf(s[j] - m) : 0.f;
+        sum += s[j];
+    }
+    sum = warp_sum(sum);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
+        const int base = j * 32;
+        if (base >= lim) break;
+        const int n = min(32, lim - base);
+        for (int t = 0; t < n; ++t) {
+            const float pj = __shfl_sync(0xffffffffu, s[j], t);
+            const float2 v2 = __bfloat1622float2(
+                reinterpret_cast<const bf162*>(vb + static_cast<size_t>(base + t) * va.rs)[lane]);
+            a0 = fmaf(pj, v2.x, a0);
+            a1 = fmaf(pj, v2.y, a1);
+        }
+    }
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    bf16* orow = o + b * oa.bs + static_cast<size_t>(qi) * oa.rs + h * D;
+    reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(a0 * inv, a1 * inv);
+    if (lse != nullptr && lane == 0) lse[(static_cast<size_t>(b) * H + h) * Tq + qi] = m + __logf(sum);
+}
+
 }  // namespace
 
 int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
                   int o_rs, int causal, float scale, cudaStream_t stream, int q_row0) {
     // rows [q_row0, Tq) of every (batch, head)
+    if (Tq - q_row0 <= 8 && Tk <= kFewMaxKeys) {
+        const int warps = B * H * (Tq - q_row0);
+        attn_fwd_fewrows_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(
+            static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
+            static_cast<bf16*>(o), lse, B, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs},
+            Addr{o_bs, o_rs}, causal, scale, q_row0);
+        VLK_CHECK_LAUNCH("vlk_attn_fwd(fewrows)");
+        return VLK_OK;
+    }
     const dim3 grid((Tq - q_row0 + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
     attn_fwd_simt_kernel<<<grid, kWarps * 32, 0, stream>>>(
         static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v), static_cast<bf16*>(o),
@@ -355,8 +441,8 @@ bool attn_small_applicable(int Tq, int Tk);
 int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
                    int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
-                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
-                   cudaStream_t stream);
+                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
+                   const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
 
 }  // namespace vlk
 
@@ -366,7 +452,12 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
                             const float* lse, void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk,
                             long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
                             long long o_bs, int o_rs, long long dq_bs, int dq_rs, long long dk_bs, int dk_rs,
-                            long long dv_bs, int dv_rs, int causal, float scale, float* delta, void* stream) {
+                            long long dv_bs, int dv_rs, int causal, float scale, float* delta, float dropout_p,
+                            const unsigned long long* seed_state, unsigned int stream_id, void* stream) {
+    VLK_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed_state), VLK_ERR_INVALID_ARG,
+                "vlk_attn_bwd: dropout_p=%f needs a seed state", dropout_p);
+    VLK_REQUIRE(dropout_p == 0.f || attn_small_applicable(Tq, Tk), VLK_ERR_UNSUPPORTED,
+                "vlk_attn_bwd: attention dropout is only implemented for Tq, Tk <= 64 (the Q-Former shapes)");
     VLK_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && delta, VLK_ERR_INVALID_ARG,
                 "vlk_attn_bwd: null pointer");
     VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_bwd: B=%d H=%d Tq=%d Tk=%d", B, H,
@@ -379,9 +470,10 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {
         const char* force = getenv("VLK_ATTN_IMPL");
-        if (attn_small_applicable(Tq, Tk) && !(force && strcmp(force, "simt") == 0))
+        if (attn_small_applicable(Tq, Tk) && (dropout_p > 0.f || !(force && strcmp(force, "simt") == 0)))
             return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
-                                  o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, s);
+                                  o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
+                                  seed_state, stream_id, s);
     }
     float* scratch = delta;
     const dim3 gq((Tq + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);

@@ -96,7 +96,8 @@ __device__ __forceinline__ void store_rows_bf16(bf16* __restrict__ dst, int rs, 
 __global__ void __launch_bounds__(kThreads)
 attn_small_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                       bf16* __restrict__ o, float* __restrict__ lse, int H, int Tq, int Tk, Addr qa, Addr ka,
-                      Addr va, Addr oa, int causal, float scale) {
+                      Addr va, Addr oa, int causal, float scale, float dropout_p,
+                      const unsigned long long* __restrict__ seed_state, uint32_t stream_id) {
     extern __shared__ __align__(16) float sm[];
     float* Qt = sm;
     float* Kt = sm + T * D;
@@ -132,6 +133,16 @@ attn_small_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
         rinv[i] = sum > 0.f ? 1.0f / sum : 0.f;
         if (lse != nullptr && tx == 0 && qi < Tq) lse[(static_cast<size_t>(b) * H + h) * Tq + qi] = m + __logf(sum);
     }
+    if (dropout_p > 0.f) {  // dropout on the (normalised) probabilities, as nn.MultiheadAttention does
+        const DropoutKey dk = make_dropout_key(seed_state, stream_id, dropout_p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mk[4];
+            dropout_scales4(dk, (static_cast<unsigned long long>(blockIdx.x) * T + 4 * ty + i) * (T / 4) + tx, mk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] *= mk[j];
+        }
+    }
     // Pt[j][i]
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -156,7 +167,8 @@ __global__ void __launch_bounds__(kThreads)
 attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                       const bf16* __restrict__ o, const bf16* __restrict__ d_o, const float* __restrict__ lse,
                       bf16* __restrict__ dq, bf16* __restrict__ dk, bf16* __restrict__ dv, int H, int Tq, int Tk,
-                      Addr qa, Addr ka, Addr va, Addr oa, Addr dqa, Addr dka, Addr dva, int causal, float scale) {
+                      Addr qa, Addr ka, Addr va, Addr oa, Addr dqa, Addr dka, Addr dva, int causal, float scale,
+                      float dropout_p, const unsigned long long* __restrict__ seed_state, uint32_t stream_id) {
     extern __shared__ __align__(16) float sm[];
     float* A0 = sm;
     float* A1 = sm + T * D;
@@ -208,16 +220,21 @@ attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
     mm_tt(A0, A1, ty, tx, D, s);    // S[i][j] (already scaled)
     mm_tt(A2, A3, ty, tx, D, dp);   // dP[i][j] = dO_i . V_j
     const int shift = Tk - Tq;
+    DropoutKey dkey;
+    if (dropout_p > 0.f) dkey = make_dropout_key(seed_state, stream_id, dropout_p);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int qi = 4 * ty + i;
         const int lim = (qi < Tq) ? (causal ? min(Tk, qi + shift + 1) : Tk) : 0;
         const float l = sLse[qi], dl = sDelta[qi];
+        float mk[4] = {1.f, 1.f, 1.f, 1.f};
+        if (dropout_p > 0.f)  // the forward's mask, regenerated from the same counters
+            dropout_scales4(dkey, (static_cast<unsigned long long>(blockIdx.x) * T + qi) * (T / 4) + tx, mk);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float p = (4 * tx + j < lim) ? __expf(s[i][j] - l) : 0.f;
-            s[i][j] = p;
-            dp[i][j] = p * (dp[i][j] - dl);
+            s[i][j] = p * mk[j];                       // dropped probabilities feed dV
+            dp[i][j] = p * (dp[i][j] * mk[j] - dl);    // dS = P o (mask o dP_drop - delta)
         }
     }
     __syncthreads();  // everyone is done reading A0..A3
@@ -253,7 +270,8 @@ bool attn_small_applicable(int Tq, int Tk) { return Tq <= T && Tk <= T; }
 
 int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                    long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, cudaStream_t stream) {
+                   int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
+                   unsigned int stream_id, cudaStream_t stream) {
     constexpr int smem = 4 * T * D * sizeof(float);
     static bool configured = false;
     if (!configured) {
@@ -262,7 +280,8 @@ int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* 
     }
     attn_small_fwd_kernel<<<B * H, kThreads, smem, stream>>>(
         static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v), static_cast<bf16*>(o),
-        lse, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, causal, scale);
+        lse, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, causal, scale,
+        dropout_p, seed_state, stream_id);
     VLK_CHECK_LAUNCH("vlk_attn_fwd(small)");
     return VLK_OK;
 }
@@ -270,8 +289,8 @@ int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* 
 int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
                    int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
-                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
-                   cudaStream_t stream) {
+                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
+                   const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream) {
     constexpr int smem = 7 * T * D * sizeof(float);
     static bool configured = false;
     if (!configured) {
@@ -282,7 +301,7 @@ int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, c
         static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
         static_cast<const bf16*>(o), static_cast<const bf16*>(d_o), lse, static_cast<bf16*>(dq), static_cast<bf16*>(dk),
         static_cast<bf16*>(dv), H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs},
-        Addr{dq_bs, dq_rs}, Addr{dk_bs, dk_rs}, Addr{dv_bs, dv_rs}, causal, scale);
+        Addr{dq_bs, dq_rs}, Addr{dk_bs, dk_rs}, Addr{dv_bs, dv_rs}, causal, scale, dropout_p, seed_state, stream_id);
     VLK_CHECK_LAUNCH("vlk_attn_bwd(small)");
     return VLK_OK;
 }

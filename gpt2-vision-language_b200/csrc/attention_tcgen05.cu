@@ -27,7 +27,18 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
 bool attn_small_applicable(int Tq, int Tk);
 int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                    long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, cudaStream_t stream);
+                   int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
+                   unsigned int stream_id, cudaStream_t stream);
+
+// bring-up instrumentation: per-phase %globaltimer stamps of the first CTAs (read back by vlk_debug_dump)
+__device__ long long g_attn_dbg[64 * 16];
+__device__ __forceinline__ void dbg_stamp(int enabled, int slot) {
+    if (enabled && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z < 32 && blockIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_attn_dbg[blockIdx.z * 16 + slot] = t;
+    }
+}
 
 namespace {
 
@@ -225,6 +236,267 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: probabilities stay in TENSOR MEMORY.  After the row max, each thread overwrites its own S row in place
+// with bf16 P (two values per 32-bit column, tcgen05.st) and O = P V runs with A read from TMEM.  That removes the
+// 80 KB shared-memory P tile: a CTA needs 84 KB of smem and 256 TMEM columns, so TWO CTAs fit per SM and one
+// CTA's softmax overlaps the other's loads and MMAs.  Keys beyond 256 (CLIP has 257) are not worth a second
+// 256-column accumulator: their scores and their P.V contribution (<= 16 keys) are computed on the CUDA cores.
+//   TMEM columns: S fp32 [0,256) -> P bf16x2 [0,128) in place; O fp32 [128,192) (dead S columns).
+// ------------------------------------------------------------------------------------------------
+constexpr int k2OffQ = 0;                  // 16 KB
+constexpr int k2OffK = 16 * 1024;          // 32 KB  (256 keys)
+constexpr int k2OffKx = 48 * 1024;         //  2 KB  (keys 256..271)
+constexpr int k2OffV = 50 * 1024;          // 32 KB
+constexpr int k2OffVx = 82 * 1024;         //  2 KB
+constexpr int k2OffBar = 84 * 1024;
+constexpr int k2SmemBytes = k2OffBar + 64 + 1024;
+constexpr uint32_t k2TmemCols = 256;
+constexpr uint32_t k2TmemO = 128;
+
+struct Fwd2Params {
+    bf16* o;
+    float* lse;
+    long long o_bs;
+    int o_rs;
+    int H, Tq, Tk, n_main, n_extra, causal;
+    float scale_log2e, scale;
+    int debug;
+};
+
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// dot of this thread's (swizzled, K-major) Q row with extra-key row e; both 64 bf16
+__device__ __forceinline__ float dot_q_kx(const uint8_t* qrow_base, int qr7, const uint8_t* kx, int e) {
+    const uint8_t* krow = kx + (e >> 3) * 1024 + (e & 7) * 128;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(qrow_base + ((j ^ qr7) << 4)), a);
+        unpack8(*reinterpret_cast<const uint4*>(krow + ((j ^ (e & 7)) << 4)), b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                           const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kx,
+                           const __grid_constant__ CUtensorMap tmap_vx, Fwd2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + k2OffBar);
+    uint64_t* bar_v = bar_qk + 1;
+    uint64_t* bar_s = bar_qk + 2;
+    uint64_t* bar_o = bar_qk + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int n_main = p.n_main, n_extra = p.n_extra;
+    dbg_stamp(p.debug, 0);
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        ptx::mbar_init(bar_qk, 1);
+        ptx::mbar_init(bar_v, 1);
+        ptx::mbar_init(bar_s, 1);
+        ptx::mbar_init(bar_o, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, k2TmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    dbg_stamp(p.debug, 1);
+
+    if (threadIdx.x == 0) {
+        const uint32_t kv_bytes = static_cast<uint32_t>(n_main) * 128u + (n_extra > 0 ? 2048u : 0u);
+        ptx::mbar_arrive_expect_tx(bar_qk, kQBytes + kv_bytes);
+        ptx::tma_load_3d(smem + k2OffQ, &tmap_q, bar_qk, h * 64, q0, b);
+        ptx::tma_load_3d(smem + k2OffK, &tmap_k, bar_qk, h * 64, 0, b);
+        if (n_extra > 0) ptx::tma_load_3d(smem + k2OffKx, &tmap_kx, bar_qk, h * 64, 256, b);
+        ptx::mbar_arrive_expect_tx(bar_v, kv_bytes);
+        ptx::tma_load_3d(smem + k2OffV, &tmap_v, bar_v, h * 64, 0, b);
+        if (n_extra > 0) ptx::tma_load_3d(smem + k2OffVx, &tmap_vx, bar_v, h * 64, 256, b);
+
+        ptx::mbar_wait(bar_qk, 0);
+        dbg_stamp(p.debug, 2);
+        ptx::tc_fence_after_sync();
+        const uint32_t sq = ptx::smem_u32(smem + k2OffQ), sk = ptx::smem_u32(smem + k2OffK);
+        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, n_main, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                              ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc, k != 0);
+        ptx::umma_commit(bar_s);
+    }
+
+    const int row = threadIdx.x;
+    const int qi = q0 + row;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    int lim = p.Tk;
+    if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
+    if (lim < 1) lim = 1;
+    const uint8_t* qrow = smem + k2OffQ + (row >> 3) * 1024 + (row & 7) * 128;
+    const int qr7 = row & 7;
+
+    // scores of the extra keys (CUDA cores), needed for the row max
+    ptx::mbar_wait(bar_qk, 0);  // Q / K / Kx are in shared memory
+    float sx[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sx[e] = (e < n_extra && 256 + e < lim) ? dot_q_kx(qrow, qr7, smem + k2OffKx, e) : -INFINITY;
+
+    dbg_stamp(p.debug, 3);
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after_sync();
+    dbg_stamp(p.debug, 4);
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) m = fmaxf(m, sx[e]);
+    // Columns below `full` need no masking (every key visible to this row): the common, non-causal case runs the
+    // predicate-free loops; only the boundary chunk pays for the per-element compares.
+    // (warp-uniform on purpose: the tcgen05.ld/st below are .sync.aligned, so every lane must run the same trip
+    // counts — with a causal mask `lim` differs per row and the smallest one in the warp decides.)
+    const int full = min(__reduce_min_sync(0xffffffffu, lim), n_main) & ~31;
+    for (int c = 0; c < full; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(trow + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+    }
+    for (int c = full; c < n_main; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(trow + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
+    }
+    const float mb = m * p.scale_log2e;
+    float sum = 0.f;
+    dbg_stamp(p.debug, 5);
+    for (int c = 0; c < full; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(trow + c, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
+            const float e1 = ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
+            const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+            const float2 back = __bfloat1622float2(h2);  // sum what the tensor core will actually multiply
+            sum += back.x + back.y;
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        // P columns [c/2, c/2+16) overwrite S columns this thread has already consumed
+        ptx::tmem_st_32x32b_x16(trow + (c >> 1), pk);
+    }
+    for (int c = full; c < n_main; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(trow + c, r);
+        ptx::tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float e0 = (c + 2 * i < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb)) : 0.f;
+            const float e1 =
+                (c + 2 * i + 1 < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb)) : 0.f;
+            const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+            const float2 back = __bfloat1622float2(h2);
+            sum += back.x + back.y;
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        ptx::tmem_st_32x32b_x8(trow + (c >> 1), pk);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        sx[e] = (e < n_extra && 256 + e < lim) ? ex2_fast(fmaf(sx[e], p.scale_log2e, -mb)) : 0.f;
+        sum += sx[e];
+    }
+    dbg_stamp(p.debug, 6);
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    dbg_stamp(p.debug, 7);
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_wait(bar_v, 0);
+        ptx::tc_fence_after_sync();
+        const uint32_t sv = ptx::smem_u32(smem + k2OffV);
+        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (MN-major)
+        const int ksteps = n_main / 16;
+        for (int k = 0; k < ksteps; ++k)
+            ptx::umma_bf16_ts(tmem + k2TmemO, tmem + k * 8, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc,
+                              k != 0);
+        ptx::umma_commit(bar_o);
+    }
+    ptx::mbar_wait(bar_v, 0);  // Vx visible to every thread
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after_sync();
+    dbg_stamp(p.debug, 8);
+    const float inv = 1.0f / sum;
+    bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(trow + k2TmemO + c, r);
+        ptx::tmem_ld_wait();
+        float t0[8], t1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            t0[i] = __uint_as_float(r[i]);
+            t1[i] = __uint_as_float(r[8 + i]);
+        }
+        for (int e = 0; e < n_extra; ++e) {  // rank-1 updates from the extra keys
+            const uint8_t* vrow = smem + k2OffVx + (e >> 3) * 1024 + (e & 7) * 128;
+            float v0[8], v1[8];
+            unpack8(*reinterpret_cast<const uint4*>(vrow + ((((c >> 3)) ^ (e & 7)) << 4)), v0);
+            unpack8(*reinterpret_cast<const uint4*>(vrow + ((((c >> 3) + 1) ^ (e & 7)) << 4)), v1);
+            float pe = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pe = (j == e) ? sx[j] : pe;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                t0[i] = fmaf(pe, v0[i], t0[i]);
+                t1[i] = fmaf(pe, v1[i], t1[i]);
+            }
+        }
+        if (qi < p.Tq) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                t0[i] *= inv;
+                t1[i] *= inv;
+            }
+            stg16(orow + c, pack8(t0));
+            stg16(orow + c + 8, pack8(t1));
+        }
+    }
+    if (qi < p.Tq && p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
+    dbg_stamp(p.debug, 9);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, k2TmemCols);
+    }
+    dbg_stamp(p.debug, 10);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -263,8 +535,13 @@ using namespace vlk;
 
 extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq,
                             int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
-                            long long o_bs, int o_rs, int causal, float scale, void* stream) {
+                            long long o_bs, int o_rs, int causal, float scale, float dropout_p,
+                            const unsigned long long* seed_state, unsigned int stream_id, void* stream) {
     VLK_REQUIRE(q && k && v && o, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: null pointer");
+    VLK_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed_state), VLK_ERR_INVALID_ARG,
+                "vlk_attn_fwd: dropout_p=%f needs a seed state", dropout_p);
+    VLK_REQUIRE(dropout_p == 0.f || attn_small_applicable(Tq, Tk), VLK_ERR_UNSUPPORTED,
+                "vlk_attn_fwd: attention dropout is only implemented for Tq, Tk <= 64 (the Q-Former shapes)");
     VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: B=%d H=%d Tq=%d Tk=%d", B, H,
                 Tq, Tk);
     VLK_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
@@ -274,9 +551,9 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
                 "vlk_attn_fwd: 16B alignment");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const char* force = getenv("VLK_ATTN_IMPL");
-    if (attn_small_applicable(Tq, Tk) && !(force && strcmp(force, "simt") == 0))
+    if (attn_small_applicable(Tq, Tk) && (dropout_p > 0.f || !(force && strcmp(force, "simt") == 0)))
         return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                              scale, s);
+                              scale, dropout_p, seed_state, stream_id, s);
     const bool want_tc = force ? (strcmp(force, "tcgen05") == 0) : (Tk > 64);
     if (!want_tc || Tk > kMaxKeys || Tq < 64 || (force && strcmp(force, "simt") == 0))
         return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
@@ -288,6 +565,46 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (tail > 32) {
         tc_rows = Tq;
         tail = 0;
+    }
+    if (!(force && strcmp(force, "tcgen05v1") == 0)) {
+        static bool configured2 = false;
+        if (!configured2) {
+            VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          k2SmemBytes));
+            configured2 = true;
+        }
+        Fwd2Params p2;
+        p2.o = static_cast<bf16*>(o);
+        p2.lse = lse;
+        p2.o_bs = o_bs;
+        p2.o_rs = o_rs;
+        p2.H = H;
+        p2.Tq = Tq;
+        p2.Tk = Tk;
+        p2.n_main = Tk >= 256 ? 256 : (Tk + 15) / 16 * 16;
+        p2.n_extra = Tk > 256 ? Tk - 256 : 0;
+        p2.causal = causal;
+        p2.scale = scale;
+        p2.scale_log2e = scale * 1.4426950408889634f;
+        p2.debug = getenv("VLK_ATTN_DEBUG") != nullptr;
+        CUtensorMap tq, tk, tv, tkx, tvx;
+        int rc = make_tmap3(&tq, q, H * 64, Tq, B, q_rs, q_bs, 128);
+        if (rc) return rc;
+        rc = make_tmap3(&tk, k, H * 64, Tk, B, k_rs, k_bs, p2.n_main);
+        if (rc) return rc;
+        rc = make_tmap3(&tv, v, H * 64, Tk, B, v_rs, v_bs, p2.n_main);
+        if (rc) return rc;
+        rc = make_tmap3(&tkx, k, H * 64, Tk, B, k_rs, k_bs, 16);
+        if (rc) return rc;
+        rc = make_tmap3(&tvx, v, H * 64, Tk, B, v_rs, v_bs, 16);
+        if (rc) return rc;
+        const dim3 grid2((tc_rows + 127) / 128, H, B);
+        attn_fwd_tcgen05_v2_kernel<<<grid2, 128, k2SmemBytes, s>>>(tq, tk, tv, tkx, tvx, p2);
+        VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v2)");
+        if (tail > 0)
+            return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                                 scale, s, tc_rows);
+        return VLK_OK;
     }
     static bool configured = false;
     if (!configured) {
@@ -321,4 +638,11 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
         return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                              scale, s, tc_rows);
     return VLK_OK;
+}
+
+// bring-up only (not part of include/vlk.h): copy the attention phase stamps to the host
+extern "C" int vlk_debug_dump(long long* host_out, int n) {
+    if (n > 64 * 16) n = 64 * 16;
+    cudaError_t e = cudaMemcpyFromSymbol(host_out, vlk::g_attn_dbg, sizeof(long long) * n);
+    return static_cast<int>(e);
 }

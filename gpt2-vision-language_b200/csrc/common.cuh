@@ -76,6 +76,54 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// Counter-based RNG for dropout: Philox-4x32-10 (Salmon et al. 2011), the generator torch's CUDA dropout uses.
+// Keyed by a device-resident (seed, step) pair so that a captured CUDA graph draws fresh masks on every replay,
+// and by a per-call-site stream id so forward and backward of one site regenerate the SAME mask.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+struct DropoutKey {
+    uint2 key;        // seed (low, high)
+    uint32_t stream;  // call-site id
+    uint32_t step;    // device step counter
+    uint32_t thresh;  // drop if rand < thresh
+    float inv_keep;   // 1 / (1 - p)
+};
+__device__ __forceinline__ DropoutKey make_dropout_key(const unsigned long long* seed_state, uint32_t stream, float p) {
+    DropoutKey d;
+    const unsigned long long seed = seed_state[0];
+    d.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    d.stream = stream;
+    d.step = static_cast<uint32_t>(seed_state[1]);
+    d.thresh = static_cast<uint32_t>(fminf(p, 0.999999f) * 4294967296.0f);
+    d.inv_keep = 1.0f / (1.0f - p);
+    return d;
+}
+// four keep-scales (0 or 1/(1-p)) for elements 4*group .. 4*group+3
+__device__ __forceinline__ void dropout_scales4(const DropoutKey& d, unsigned long long group, float (&m)[4]) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32), d.stream,
+                                             d.step), d.key);
+    m[0] = r.x >= d.thresh ? d.inv_keep : 0.f;
+    m[1] = r.y >= d.thresh ? d.inv_keep : 0.f;
+    m[2] = r.z >= d.thresh ? d.inv_keep : 0.f;
+    m[3] = r.w >= d.thresh ? d.inv_keep : 0.f;
+}
+// single element (small attention tiles): element index -> its scale
+__device__ __forceinline__ float dropout_scale1(const DropoutKey& d, unsigned long long idx) {
+    float m[4];
+    dropout_scales4(d, idx >> 2, m);
+    const int s = static_cast<int>(idx & 3);
+    return s == 0 ? m[0] : (s == 1 ? m[1] : (s == 2 ? m[2] : m[3]));
+}
+
 // The three GELU flavours on the path: tanh (GPT-2), erf (Q-Former), quick (CLIP).
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;

@@ -301,6 +301,32 @@ __global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ lo
     }
 }
 
+// y = residual + x * keep / (1 - p)   (residual may be NULL); 8 elements per thread, two Philox draws
+__global__ void dropout_add_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual,
+                                   bf16* __restrict__ y, long long n8, float p,
+                                   const unsigned long long* __restrict__ seed_state, uint32_t stream) {
+    const DropoutKey dk = make_dropout_key(seed_state, stream, p);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float a[8], m0[4], m1[4];
+        unpack8(ldg16(x + i * 8), a);
+        dropout_scales4(dk, static_cast<unsigned long long>(i) * 2, m0);
+        dropout_scales4(dk, static_cast<unsigned long long>(i) * 2 + 1, m1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] *= m0[k];
+            a[4 + k] *= m1[k];
+        }
+        if (residual != nullptr) {
+            float r[8];
+            unpack8(ldg16(residual + i * 8), r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += r[k];
+        }
+        stg16(y + i * 8, pack8(a));
+    }
+}
+
 inline int grid_for(long long work_items, int threads, int sms) {
     long long b = (work_items + threads - 1) / threads;
     long long cap = static_cast<long long>(sms) * 16;
@@ -441,5 +467,18 @@ extern "C" int vlk_argmax_rows(const void* logits, long long* out, int rows, int
                 "vlk_argmax_rows: rows=%d V=%d ld=%d", rows, V, ld);
     argmax_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(logits), out, V, ld);
     VLK_CHECK_LAUNCH("vlk_argmax_rows");
+    return VLK_OK;
+}
+
+extern "C" int vlk_dropout_add_bf16(const void* x, const void* residual, void* y, long long n, float p,
+                                    const unsigned long long* seed_state, unsigned int stream_id, void* stream) {
+    VLK_REQUIRE(x && y && seed_state && n > 0 && n % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_dropout_add_bf16: n=%lld", n);
+    VLK_REQUIRE(p >= 0.f && p < 1.f, VLK_ERR_INVALID_ARG, "vlk_dropout_add_bf16: p=%f", p);
+    const int sms = device_sm_count();
+    VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_dropout_add_bf16: no sm_100 device");
+    dropout_add_kernel<<<grid_for(n / 8, 256, sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), static_cast<const bf16*>(residual), static_cast<bf16*>(y), n / 8, p, seed_state,
+        stream_id);
+    VLK_CHECK_LAUNCH("vlk_dropout_add_bf16");
     return VLK_OK;
 }

@@ -310,7 +310,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
             }
             __syncwarp();
             stage_store_tile(stage_out, sweep == 0 ? ep.aux_out : reinterpret_cast<bf16*>(ep.D),
-                             sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
+                                 sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
             __syncwarp();
         }
     }

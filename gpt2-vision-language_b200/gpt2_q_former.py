@@ -25,30 +25,38 @@ class QFormerLayer(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(d, 4 * d), nn.GELU(), nn.Linear(4 * d, d))
         self.drop = nn.Dropout(drop)
 
-    def _check_dropout(self):
-        if self.training and (self.drop.p > 0 or self.self_attn.dropout > 0 or self.cross_attn.dropout > 0):
-            raise NotImplementedError(
-                "Q-Former dropout (p>0 in train mode) is not yet available on the B200 path: build the bridge "
-                "with drop=0.0 or call .eval() on it (the reference's eval-mode math is reproduced exactly)")
-
     def forward(self, q, v):
-        self._check_dropout()
         d = q.shape[-1]
         sa, ca = self.self_attn, self.cross_attn
+        # dropout is live only in train mode (nn.Dropout / nn.MultiheadAttention semantics): 3 residual branches
+        # + the attention probabilities of both attentions, masks from the Philox state of ops.DropoutState
+        p_res = self.drop.p if self.training else 0.0
+        p_sa = sa.dropout if self.training else 0.0
+        p_ca = ca.dropout if self.training else 0.0
+        rng = ops.DropoutState.default(q.device) if (p_res > 0 or p_sa > 0 or p_ca > 0) else None
+
+        def branch(out, w, b, res):          # res + dropout(out @ w^T + b)
+            if p_res > 0:
+                return ops.dropout_add(ops.linear(out, w, b), res, p_res, rng)
+            return ops.linear(out, w, b, res)
+
         h = ops.layernorm(q, self.ln1.weight, self.ln1.bias, self.ln1.eps)
         qkv = ops.linear(h, sa.in_proj_weight, sa.in_proj_bias)
-        a = ops.self_attention(qkv, self.n_heads, False)
-        q = ops.linear(a, sa.out_proj.weight, sa.out_proj.bias, q)
+        a = ops.self_attention(qkv, self.n_heads, False, p_sa, rng)
+        q = branch(a, sa.out_proj.weight, sa.out_proj.bias, q)
 
         hq = ops.layernorm(q, self.ln2_q.weight, self.ln2_q.bias, self.ln2_q.eps)
         hv = ops.layernorm(v, self.ln2_v.weight, self.ln2_v.bias, self.ln2_v.eps)
         qq = ops.linear(hq, ca.in_proj_weight[:d], ca.in_proj_bias[:d])
         kv = ops.linear(hv, ca.in_proj_weight[d:], ca.in_proj_bias[d:])
-        a = ops.cross_attention(qq, kv, self.n_heads)
-        q = ops.linear(a, ca.out_proj.weight, ca.out_proj.bias, q)
+        a = ops.cross_attention(qq, kv, self.n_heads, p_ca, rng)
+        q = branch(a, ca.out_proj.weight, ca.out_proj.bias, q)
 
         h = ops.layernorm(q, self.ln3.weight, self.ln3.bias, self.ln3.eps)
         fc, proj = self.mlp[0], self.mlp[2]
+        if p_res > 0:
+            m = ops.mlp(h, fc.weight, fc.bias, proj.weight, proj.bias, None, "gelu_erf")
+            return ops.dropout_add(m, q, p_res, rng)
         return ops.mlp(h, fc.weight, fc.bias, proj.weight, proj.bias, q, "gelu_erf")
 
 

@@ -143,7 +143,38 @@ def _bt_strides(t):
     return t.stride(0), t.stride(1)
 
 
-def attention_fwd(q, k, v, n_head, causal, scale=None, need_lse=True):
+class DropoutState:
+    """Device-resident Philox key for the dropout kernels: int64 [seed, step].
+
+    Every dropout call site draws a fresh ``stream id`` from a host counter (so eager calls never repeat a mask)
+    and the device ``step`` is bumped by ``advance()`` once per optimizer step — that is what makes masks change
+    between replays of a captured CUDA graph, where the stream ids are baked in.  Forward and backward of one site
+    use the same (seed, step, stream id) triple and therefore regenerate the same mask."""
+
+    _per_device = {}
+
+    def __init__(self, device, seed=None):
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self._next = 0
+
+    def new_stream(self):
+        self._next = (self._next + 1) & 0x7FFFFFFF
+        return self._next
+
+    def advance(self):
+        self.state[1:2] += 1
+
+    @classmethod
+    def default(cls, device):
+        key = str(device)
+        if key not in cls._per_device:
+            cls._per_device[key] = cls(device)
+        return cls._per_device[key]
+
+
+def attention_fwd(q, k, v, n_head, causal, scale=None, need_lse=True, dropout_p=0.0, rng=None, stream_id=0):
     """q: [B,Tq,H*64] view, k/v: [B,Tk,H*64] views (slices of packed projections are fine). Returns o [B,Tq,H*64], lse."""
     _need_cuda(q, k, v)
     B, Tq, W = q.shape
@@ -154,12 +185,13 @@ def attention_fwd(q, k, v, n_head, causal, scale=None, need_lse=True):
     lse = torch.empty((B, n_head, Tq), device=q.device, dtype=torch.float32) if need_lse else None
     (qb, qr), (kb, kr), (vb, vr), (ob, orr) = _bt_strides(q), _bt_strides(k), _bt_strides(v), _bt_strides(o)
     check(_lib.load().vlk_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), _p(lse), B, n_head, Tq,
-                                   Tk, qb, qr, kb, kr, vb, vr, ob, orr, int(causal), float(scale), _stream()),
+                                   Tk, qb, qr, kb, kr, vb, vr, ob, orr, int(causal), float(scale), float(dropout_p),
+                                   rng.state.data_ptr() if rng is not None else 0, int(stream_id), _stream()),
           "vlk_attn_fwd")
     return o, lse
 
 
-def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n_head, causal, scale=None):
+def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n_head, causal, scale=None, dropout_p=0.0, rng=None, stream_id=0):
     """Writes dq/dk/dv (pre-allocated views with the primal shapes)."""
     B, Tq, W = q.shape
     Tk = k.shape[1]
@@ -174,7 +206,21 @@ def attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, n_head, causal, scale=None):
     check(_lib.load().vlk_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                    lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, n_head, Tq, Tk,
                                    qb, qr, kb, kr, vb, vr, ob, orr, dqb, dqr, dkb, dkr, dvb, dvr, int(causal),
-                                   float(scale), delta.data_ptr(), _stream()), "vlk_attn_bwd")
+                                   float(scale), delta.data_ptr(), float(dropout_p),
+                                   rng.state.data_ptr() if rng is not None else 0, int(stream_id), _stream()),
+          "vlk_attn_bwd")
+
+
+def dropout_add_raw(x, residual, p, rng, stream_id):
+    """y = residual + x * keep/(1-p) (residual may be None); mask = Philox(rng.state, stream_id)."""
+    _need_cuda(x)
+    x = _bf16c(x).contiguous()
+    if residual is not None:
+        residual = _bf16c(residual).contiguous()
+    y = torch.empty_like(x)
+    check(_lib.load().vlk_dropout_add_bf16(x.data_ptr(), _p(residual), y.data_ptr(), x.numel(), float(p),
+                                           rng.state.data_ptr(), int(stream_id), _stream()), "vlk_dropout_add_bf16")
+    return y
 
 
 def pool33(tokens, normalize=True):
@@ -371,15 +417,17 @@ class SelfAttnFn(torch.autograd.Function):
     nn.MultiheadAttention in_proj with q=k=v).  The gradient is written straight into a packed [B,T,3C] buffer."""
 
     @staticmethod
-    def forward(ctx, qkv, n_head, causal):
+    def forward(ctx, qkv, n_head, causal, dropout_p=0.0, rng=None, stream_id=0):
         qkv = _bf16c(qkv)
         C = qkv.shape[-1] // 3
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         need_bwd = ctx.needs_input_grad[0]
-        o, lse = attention_fwd(q, k, v, n_head, causal, need_lse=need_bwd)
+        o, lse = attention_fwd(q, k, v, n_head, causal, need_lse=need_bwd, dropout_p=dropout_p, rng=rng,
+                               stream_id=stream_id)
         if need_bwd:
             ctx.save_for_backward(qkv, o, lse)
         ctx.n_head, ctx.causal = n_head, causal
+        ctx.drop = (dropout_p, rng, stream_id)
         return o
 
     @staticmethod
@@ -387,13 +435,16 @@ class SelfAttnFn(torch.autograd.Function):
         qkv, o, lse = ctx.saved_tensors
         C = qkv.shape[-1] // 3
         dqkv = torch.empty_like(qkv)
+        p, rng, sid = ctx.drop
         attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, d_o, lse, dqkv[..., :C],
-                      dqkv[..., C:2 * C], dqkv[..., 2 * C:], ctx.n_head, ctx.causal)
-        return dqkv, None, None
+                      dqkv[..., C:2 * C], dqkv[..., 2 * C:], ctx.n_head, ctx.causal, dropout_p=p, rng=rng,
+                      stream_id=sid)
+        return dqkv, None, None, None, None, None
 
 
-def self_attention(qkv, n_head, causal):
-    return SelfAttnFn.apply(qkv, n_head, causal)
+def self_attention(qkv, n_head, causal, dropout_p=0.0, rng=None):
+    sid = rng.new_stream() if (dropout_p > 0 and rng is not None) else 0
+    return SelfAttnFn.apply(qkv, n_head, causal, dropout_p, rng, sid)
 
 
 class CrossAttnFn(torch.autograd.Function):
@@ -401,14 +452,16 @@ class CrossAttnFn(torch.autograd.Function):
     nn.MultiheadAttention of the Q-Former, gpt2_q_former/model.py:140).  Non-causal."""
 
     @staticmethod
-    def forward(ctx, q, kv, n_head):
+    def forward(ctx, q, kv, n_head, dropout_p=0.0, rng=None, stream_id=0):
         q, kv = _bf16c(q), _bf16c(kv)
         C = q.shape[-1]
         need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        o, lse = attention_fwd(q, kv[..., :C], kv[..., C:], n_head, False, need_lse=need_bwd)
+        o, lse = attention_fwd(q, kv[..., :C], kv[..., C:], n_head, False, need_lse=need_bwd, dropout_p=dropout_p,
+                               rng=rng, stream_id=stream_id)
         if need_bwd:
             ctx.save_for_backward(q, kv, o, lse)
         ctx.n_head = n_head
+        ctx.drop = (dropout_p, rng, stream_id)
         return o
 
     @staticmethod
@@ -416,12 +469,34 @@ class CrossAttnFn(torch.autograd.Function):
         q, kv, o, lse = ctx.saved_tensors
         C = q.shape[-1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
-        attention_bwd(q, kv[..., :C], kv[..., C:], o, d_o, lse, dq, dkv[..., :C], dkv[..., C:], ctx.n_head, False)
-        return dq, dkv, None
+        p, rng, sid = ctx.drop
+        attention_bwd(q, kv[..., :C], kv[..., C:], o, d_o, lse, dq, dkv[..., :C], dkv[..., C:], ctx.n_head, False,
+                      dropout_p=p, rng=rng, stream_id=sid)
+        return dq, dkv, None, None, None, None
 
 
-def cross_attention(q, kv, n_head):
-    return CrossAttnFn.apply(q, kv, n_head)
+def cross_attention(q, kv, n_head, dropout_p=0.0, rng=None):
+    sid = rng.new_stream() if (dropout_p > 0 and rng is not None) else 0
+    return CrossAttnFn.apply(q, kv, n_head, dropout_p, rng, sid)
+
+
+class DropoutAddFn(torch.autograd.Function):
+    """residual + dropout(x): nn.Dropout on a residual branch (gpt2_q_former/model.py:136,141,144)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, p, rng, stream_id):
+        ctx.args = (p, rng, stream_id)
+        return dropout_add_raw(x, residual, p, rng, stream_id).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, rng, sid = ctx.args
+        dx = dropout_add_raw(dy, None, p, rng, sid).view(dy.shape) if ctx.needs_input_grad[0] else None
+        return dx, dy if ctx.needs_input_grad[1] else None, None, None, None
+
+
+def dropout_add(x, residual, p, rng):
+    return DropoutAddFn.apply(x, residual, p, rng, rng.new_stream())
 
 
 class GatedProjFn(torch.autograd.Function):

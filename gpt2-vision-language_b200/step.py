@@ -55,6 +55,9 @@ class CaptionTrainStep:
             self.loss.div_(dist.get_world_size(self.group))
         self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
         self.opt.step()
+        if self.kind == "qformer":
+            # fresh dropout masks next step, also under CUDA-graph replay (the Philox step counter lives on device)
+            ops.DropoutState.default(self.dev).advance()
 
     def set_lr(self, lr):
         for g in self.opt.param_groups:

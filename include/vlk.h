@@ -90,15 +90,20 @@ int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const fl
  * packed c_attn / kv_proj / in_proj outputs are consumed in place with no head transpose.
  * lse (fp32 [B,H,Tq], natural log) is written when non-NULL and is required by the backward.
  * bwd computes dQ, dK, dV (same addressing as their primals; written, not accumulated).
+ * dropout_p > 0 drops attention probabilities (nn.MultiheadAttention(dropout=0.1), gpt2_q_former/model.py:119,123);
+ * implemented for Tq, Tk <= 64 only.  Masks come from Philox-4x32-10 keyed by seed_state = device {seed, step}
+ * and the call-site stream_id; the backward regenerates the forward's mask from the same triple.
  */
 int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                  long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                 int o_rs, int causal, float scale, void* stream);
+                 int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
+                 unsigned int stream_id, void* stream);
 int vlk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                  void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs,
                  long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs,
                  int dq_rs, long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale,
-                 float* delta_scratch /* fp32 [B*H*Tq], overwritten */, void* stream);
+                 float* delta_scratch /* fp32 [B*H*Tq], overwritten */, float dropout_p,
+                 const unsigned long long* seed_state, unsigned int stream_id, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * 257 -> 33 token pooling: keep CLS, average the 16x16 patch grid into 4 rows x 8 cols of bins
@@ -174,6 +179,11 @@ int vlk_add_bf16(const void* a, const void* b, void* y, long long n, void* strea
 /* dst(bf16) <- src(fp32) and back */
 int vlk_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int vlk_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
+/* y = residual + x * keep / (1 - p) with the Philox mask of (seed_state, stream_id); residual may be NULL.
+ * nn.Dropout on the three residual branches of QFormerLayer (gpt2_q_former/model.py:131,136,141,144); the
+ * backward is the same call on dy with residual = NULL. n % 8 == 0. */
+int vlk_dropout_add_bf16(const void* x, const void* residual, void* y, long long n, float p,
+                         const unsigned long long* seed_state, unsigned int stream_id, void* stream);
 /* gate gradient for the x-attn block (gpt2_cross-att/model.py:101):
  * out[0] += (1 - tanh(gate)^2) * sum(dy * y)  over n elements. */
 int vlk_gate_grad(const void* dy, const void* y, const float* gate, float* out, long long n, void* stream);
