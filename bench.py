@@ -23,6 +23,8 @@ if ROOT not in sys.path:
 # Algorithmic FLOPs per step at B=64: 2MNK per GEMM, 4*Tq*Tk*d per attention head,
 # dgrad-only backward through frozen weights.
 ALGO_TFLOP_PER_STEP_B64 = {"linear": 12.28, "qformer": 12.49, "xattn": 11.74}
+PRETRAIN_GFLOP_PER_TOKEN = 0.8075      # T=1024, fwd + full bwd
+PRETRAIN_TOKENS_PER_STEP = 524288      # 16 x 1024 x 32 micro-batches, split over the ranks (train_gpt2.py:244-248)
 TEXT_LEN = 31
 
 
@@ -164,6 +166,113 @@ def build_gpu_problem(torch, args, dev, rank):
     return model, clip, clip_sd, step
 
 
+def run_pretrain(args, torch, dist, dev, world, rank, local, peaks):
+    """GPT-2 124M pretraining step (BASELINE.json configs[4]): tokens/s, strong scaling over the ranks."""
+    from gpt2_vision_language_b200 import _lib, gpt2
+    from gpt2_vision_language_b200.dp import broadcast_parameters
+    from gpt2_vision_language_b200.step import PretrainStep
+    torch.manual_seed(1337)
+    model = gpt2.GPT(gpt2.GPTConfig(vocab_size=50304)).to(dev).to(torch.bfloat16)
+    broadcast_parameters(model)
+    mb, T = args.micro_batch, 1024
+    accum = max(1, PRETRAIN_TOKENS_PER_STEP // (mb * T * world))
+    step = PretrainStep(model, mb, T, accum, use_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(rank)
+    x_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
+    y_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
+    step.load_tokens(x_h, y_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    c0 = _lib.launch_count()
+    step.run()                      # eager warm-up step, also counts launches
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - c0
+    for _ in range(max(args.warmup, 3)):
+        step.run()
+    clocks, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clocks, local), daemon=True)
+    if rank == 0:
+        th.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step.run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    loss_h = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step.load_tokens(x_h, y_h)
+        loss = step.run()
+        loss_h[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    stop.set()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    th.join(timeout=2)
+    # roofline of the GEMMs: one instrumented eager micro-step
+    from gpt2_vision_language_b200 import ops
+    records, orig = [], ops.gemm
+
+    def timed(a, b, **kw):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ta, tb = kw.get("trans_a", False), kw.get("trans_b", False)
+        M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+        N = b.shape[1] if tb else b.shape[0]
+        ev0.record()
+        out = orig(a, b, **kw)
+        ev1.record()
+        records.append((ev0, ev1, 2.0 * M * N * K))
+        return out
+    ops.gemm = timed
+    try:
+        step.bucket.zero()
+        step._set_slot(0)
+        step._micro()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    tot_ms = sum(a.elapsed_time(b) for a, b, _ in records)
+    tot_fl = sum(f for _, _, f in records)
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    tokens = mb * T * accum * world
+    tflop = PRETRAIN_GFLOP_PER_TOKEN * tokens / 1e3
+    line = {
+        "metric": "gpt2_pretrain_tokens_per_s", "value": tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "GPT-2 124M pretraining step, T=1024, AdamW, clip 1.0, grad accumulation",
+                   "tokens_per_step": tokens, "micro_batch": mb, "seq_len": T, "grad_accum_per_rank": accum,
+                   "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "l2": "no explicit flush: 250 MB of weights + GBs of activations per micro-step >> 126 MB L2"},
+        "algorithmic_tflops": tflop / (ms * 1e-3), "frac_of_bf16_sustained_peak": tflop / (ms * 1e-3) / peak / world,
+        "clocks": summarize_clocks(clocks),
+        "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": "tokens/s",
+                "h2d_bytes_per_step": int(x_h.numel() * 16), "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+        "roofline": {"bound": "tensor", "kernel": "vlk_gemm_bf16 (all launches of one micro-step)",
+                     "launches_per_step": len(records), "achieved": tot_fl / (tot_ms * 1e-3) / 1e12, "peak": peak,
+                     "unit": "TFLOP/s", "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak,
+                     "gemm_ms_per_micro_step": tot_ms, "traffic": None},
+        "cpu_baseline": None, "final_loss": float(loss_h[-1]),
+        "note": "attention at T=1024 runs on the streaming CUDA-core kernels this round (DESIGN.md 7)",
+    }
+    print(json.dumps(line))
+
+
 def gemm_roofline(torch, step, peaks):
     """Instrumented eager pass: CUDA events around every vlk_gemm_bf16 launch of one full step."""
     from gpt2_vision_language_b200 import ops
@@ -184,7 +293,8 @@ def gemm_roofline(torch, step, peaks):
     try:
         for _ in range(2):
             records.clear()
-            step._body()
+            step._fwd_bwd()      # rank-local: no collective here (only rank 0 runs this pass)
+            step._update()
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
@@ -198,6 +308,12 @@ def gemm_roofline(torch, step, peaks):
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained",
             "avg_launch_us": tot_ms * 1e3 / max(n, 1), "gemm_ms_per_step": tot_ms,
             "algorithmic_tflop_in_gemms": tot_fl / 1e12, "frac_of_nominal_2250": achieved / 2250.0, "traffic": None}
+
+
+def stage(msg):
+    if os.environ.get("VLK_BENCH_DEBUG"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')}] {msg}\n")
+        sys.stderr.flush()
 
 
 def run_b200(args):
@@ -219,7 +335,14 @@ def run_b200(args):
     except Exception:
         pass
 
+    if args.workload == "pretrain":
+        run_pretrain(args, torch, dist, dev, world, rank, local, peaks)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    stage("process group up")
     model, clip, clip_sd, step = build_gpu_problem(torch, args, dev, rank)
+    stage("problem built")
     B = args.batch
     pixels_h, x_h, y_h, m_h = synthetic_host_batch(B, seed=rank, torch=torch, pin=True)
     step.load_batch(pixels_h, x_h, y_h, m_h)
@@ -234,11 +357,13 @@ def run_b200(args):
     step._body()
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - c0
+    stage("eager step done")
 
     warm = max(args.warmup, 3)
     for _ in range(warm + (3 if not args.no_graph else 0)):     # +3: two eager warm steps and the capture itself
         step.run()
     barrier()
+    stage("warm-up + capture done")
 
     clocks, stop = [], threading.Event()
     th = threading.Thread(target=sample_clocks, args=(stop, clocks, local), daemon=True)
@@ -254,6 +379,7 @@ def run_b200(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    stage("timed region done")
 
     # ---- end-to-end: pinned host batch -> H2D, step, loss -> D2H, every step ----------------------------
     loss_h = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
@@ -324,7 +450,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="linear", choices=["linear", "qformer", "xattn"])
+    ap.add_argument("--workload", default="linear", choices=["linear", "qformer", "xattn", "pretrain"])
+    ap.add_argument("--micro-batch", type=int, default=16, help="pretrain micro-batch (train_gpt2.py:245: B = 16)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the reference's B is per rank)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

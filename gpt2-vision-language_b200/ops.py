@@ -589,6 +589,7 @@ class LMHeadCEFn(torch.autograd.Function):
     The gradient is produced in the forward pass and scaled by the incoming scalar in backward."""
 
     CHUNK_ROWS = 512
+    CHUNK_ROWS_DW = 4096
 
     @staticmethod
     def forward(ctx, h, weight, labels, row_weight):
@@ -608,7 +609,9 @@ class LMHeadCEFn(torch.autograd.Function):
         write_grad = need_dh or need_dw
         dh = torch.empty_like(h2) if need_dh else None
         dw = None
-        chunk = LMHeadCEFn.CHUNK_ROWS
+        # frozen lm_head (captioning): 512-row chunks keep the chunk's logits L2-resident; trainable lm_head
+        # (pretraining): larger chunks so that dW is rounded to bf16 only a few times per micro-batch
+        chunk = LMHeadCEFn.CHUNK_ROWS if not need_dw else max(LMHeadCEFn.CHUNK_ROWS, LMHeadCEFn.CHUNK_ROWS_DW)
         logits = torch.empty((min(chunk, rows), V), device=dev, dtype=BF16)
         for r0 in range(0, rows, chunk):
             r1 = min(rows, r0 + chunk)

@@ -38,7 +38,10 @@ class CaptionTrainStep:
         self._warm = 0
 
     # -------------------------------------------------------------------------------------------------
-    def _body(self):
+    def _multi(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _fwd_bwd(self):
         feats = self.clip(self.pixels)                                    # [B,257,768]
         z = pool_clip_197_to_33_avg_with_cls(feats)                       # [B,33,768], unit-norm rows
         self.bucket.zero()
@@ -49,15 +52,25 @@ class CaptionTrainStep:
             _, loss = self.model(z, self.x, labels=labels)
         loss.backward()
         self.loss.copy_(loss.detach())
-        self.bucket.all_reduce(self.group)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+
+    def _exchange(self):
+        """The one exchange step of the path: average the flat gradient bucket (and the scalar loss) over ranks."""
+        if self._multi():
+            self.bucket.all_reduce(self.group)
             dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)   # train_gpt2.py:470-471 (AVG)
             self.loss.div_(dist.get_world_size(self.group))
+
+    def _update(self):
         self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
         self.opt.step()
         if self.kind == "qformer":
             # fresh dropout masks next step, also under CUDA-graph replay (the Philox step counter lives on device)
             ops.DropoutState.default(self.dev).advance()
+
+    def _body(self):
+        self._fwd_bwd()
+        self._exchange()
+        self._update()
 
     def set_lr(self, lr):
         for g in self.opt.param_groups:
@@ -71,12 +84,14 @@ class CaptionTrainStep:
         self.mask.copy_(mask, non_blocking=non_blocking)
 
     def run(self):
-        """One optimizer step on the current contents of the static buffers. Returns the (device) loss tensor."""
+        """One optimizer step on the current contents of the static buffers. Returns the (device) loss tensor.
+        Single GPU: the whole step is one CUDA graph.  Data parallel: two graphs (forward+backward, clip+AdamW)
+        with the NCCL all-reduce launched between them on the same stream — collectives stay outside capture."""
         if not self.use_graph:
             self._body()
             return self.loss
         if self.graph is None:
-            # two eager warm-up steps on a side stream (allocator / lazy state), then capture
+            # two eager warm-up steps on a side stream (allocator / lazy state / NCCL communicator), then capture
             if self._warm < 2:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
@@ -85,8 +100,104 @@ class CaptionTrainStep:
                 torch.cuda.current_stream().wait_stream(s)
                 self._warm += 1
                 return self.loss
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
-        self.graph.replay()
+            if self._multi():
+                self.graph = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                with torch.cuda.graph(self.graph[0]):
+                    self._fwd_bwd()
+                with torch.cuda.graph(self.graph[1]):
+                    self._update()
+            else:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+        if isinstance(self.graph, tuple):
+            self.graph[0].replay()
+            self._exchange()
+            self.graph[1].replay()
+        else:
+            self.graph.replay()
+        return self.loss
+
+
+class PretrainStep:
+    """GPT-2 124M pretraining step (source/gpt2/train_gpt2.py:456-478): ``grad_accum`` micro-batches of
+    [micro_batch, seq] tokens -> loss/grad_accum -> backward (gradients accumulate in the flat bucket) -> all-reduce
+    -> clip_grad_norm_(1.0) -> AdamW.  Two CUDA graphs: one micro-step (replayed grad_accum times on static token
+    slots) and one update (all-reduce + clip + AdamW)."""
+
+    def __init__(self, model, micro_batch=16, seq=1024, grad_accum=32, lr=6e-4, weight_decay=0.1, max_norm=1.0,
+                 use_graph=True, group=None):
+        self.model, self.group, self.max_norm, self.use_graph = model, group, max_norm, use_graph
+        self.grad_accum = grad_accum
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.tokens_x = torch.zeros(grad_accum, micro_batch, seq, device=dev, dtype=torch.int64)
+        self.tokens_y = torch.zeros(grad_accum, micro_batch, seq, device=dev, dtype=torch.int64)
+        self.x = torch.zeros(micro_batch, seq, device=dev, dtype=torch.int64)
+        self.y = torch.zeros(micro_batch, seq, device=dev, dtype=torch.int64)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float32)
+        self.norm = torch.zeros((), device=dev, dtype=torch.float32)
+        self.bucket = FlatGradBucket(model.parameters())
+        self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
+        self.g_micro = self.g_update = None
+        self._warm = 0
+
+    def _micro(self):
+        _, loss = self.model(self.x, self.y)
+        (loss / self.grad_accum).backward()
+        self.loss += loss.detach() / self.grad_accum
+
+    def _exchange(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.bucket.all_reduce(self.group)
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
+            self.loss.div_(dist.get_world_size(self.group))
+
+    def _update(self):
+        self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
+        self.opt.step()
+
+    def set_lr(self, lr):
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+
+    def load_tokens(self, x, y, non_blocking=True):
+        """[grad_accum, micro_batch, seq] int64 (host pinned or device)."""
+        self.tokens_x.copy_(x, non_blocking=non_blocking)
+        self.tokens_y.copy_(y, non_blocking=non_blocking)
+
+    def _set_slot(self, i):
+        self.x.copy_(self.tokens_x[i])
+        self.y.copy_(self.tokens_y[i])
+
+    def run(self):
+        """One optimizer step over the grad_accum micro-batches currently in the token buffers."""
+        self.bucket.zero()
+        self.loss.zero_()
+        if not self.use_graph or self._warm < 1:
+            # eager pass (also the warm-up that creates optimizer state and allocator pools), on a side stream
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for i in range(self.grad_accum):
+                    self._set_slot(i)
+                    self._micro()
+                self._exchange()
+                self._update()
+            torch.cuda.current_stream().wait_stream(s)
+            self._warm += 1
+            return self.loss
+        if self.g_micro is None:
+            self._set_slot(0)
+            self.g_micro = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_micro):      # capture only records; nothing below has run yet
+                self._micro()
+            self.g_update = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_update):
+                self._update()
+        for i in range(self.grad_accum):
+            self._set_slot(i)
+            self.g_micro.replay()
+        self._exchange()                       # NCCL stays outside graph capture
+        self.g_update.replay()
         return self.loss

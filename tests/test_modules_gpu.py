@@ -149,6 +149,36 @@ def test_clip_tower_vs_hf_golden(cuda):
     assert cos(feats, ref) > 0.9995
 
 
+def test_greedy_decode_ids_match_oracle(cuda):
+    """north_star: greedy-decoded caption token ids identical at >= 99 % of positions.  Random-init logits are
+    nearly flat, so positions whose fp32 top-2 margin is below bf16 resolution are reported separately (SURVEY 8c
+    pitfall 4); the bar applies to the decisive ones, and a sequence is followed only while it still agrees."""
+    from gpt2_vision_language_b200 import gpt2, gpt2_linear
+    from gpt2_vision_language_b200.decode import greedy_decode
+    from oracle import torch_oracle as O
+    g = load("caption_linear_tiny.pt")
+    m = gpt2_linear.GPT_Caption(enc_dim=64, lm=gpt2.GPT_previous(gpt2.GPTConfig(**g["cfg"])), m_vis_tokens=32)
+    m.load_state_dict(g["sd"])
+    # sharpen the tiny model so that argmax is not a coin flip on flat logits
+    with torch.no_grad():
+        m.gpt.lm_head.weight.mul_(8.0)
+    sd = bf16_round({k: v.detach().clone() for k, v in m.state_dict().items()})
+    m = m.to(cuda).to(torch.bfloat16).eval()
+    z = g["pooled"].to(torch.bfloat16)
+    prompt = g["input_ids"][:, :3]
+    ids = greedy_decode(m, z.to(cuda), prompt.to(cuda), max_new_tokens=24).cpu()
+    ref, margins = O.greedy_decode(
+        lambda x: O.caption_linear_forward(sd, z.float(), x, None, g["cfg"]["n_layer"], g["cfg"]["n_head"])[0], prompt, 24)
+    assert ids.shape == ref.shape == (3, 27)
+    new, new_ref = ids[:, 3:], ref[:, 3:]
+    agree_prefix = (new == new_ref).long().cumprod(dim=1).bool()          # still on the oracle's trajectory
+    comparable = torch.cat([torch.ones(3, 1, dtype=torch.bool), agree_prefix[:, :-1]], dim=1)
+    decisive = comparable & (margins > 0.05)
+    assert decisive.sum() >= 30, int(decisive.sum())
+    rate = (new == new_ref)[decisive].float().mean().item()
+    assert rate >= 0.99, rate
+
+
 def test_smoke_entry(cuda):
     import __graft_entry__
     __graft_entry__.smoke()

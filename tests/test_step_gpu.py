@@ -1,0 +1,115 @@
+"""Step-level parity: a few full optimizer steps on the B200 path vs the fp32 CPU oracle — loss
+trajectory and updated weights.  bf16 parameters/moments on the GPU vs fp32 on the CPU, hence the looser bars
+after the first step."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name), map_location="cpu", weights_only=False)
+
+
+def bf16_round(sd):
+    return {k: v.to(torch.bfloat16).float() if v.is_floating_point() else v for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_caption_linear_steps_end_to_end(cuda, use_graph):
+    """pixels -> tiny CLIP tower -> pool -> linear bridge -> GPT-2 -> CE -> backward -> clip + AdamW, 4 steps."""
+    from gpt2_vision_language_b200 import gpt2, gpt2_linear
+    from gpt2_vision_language_b200.clip import ClipVisionTower
+    from gpt2_vision_language_b200.step import CaptionTrainStep
+    from oracle import torch_oracle as O
+    g, gc = load("caption_linear_tiny.pt"), load("clip_tiny.pt")
+    cfg = g["cfg"]
+    m = gpt2_linear.GPT_Caption(enc_dim=64, lm=gpt2.GPT_previous(gpt2.GPTConfig(**cfg)), m_vis_tokens=32)
+    m.load_state_dict(g["sd"])
+    m = m.to(cuda).to(torch.bfloat16)
+    tower = ClipVisionTower.from_state_dict(gc["sd"], layers=2, heads=2, device=cuda)
+    B, T = 2, 15
+    step = CaptionTrainStep(m, tower, "linear", B, T, lr=1e-2, weight_decay=0.1, use_graph=use_graph)
+    pixels = gc["pixels"].float()
+    x, labels = g["input_ids"][:B], g["labels"][:B]
+    mask = labels != -100
+    y = labels.clamp_min(0)
+    step.load_batch(pixels.to(cuda), x.to(cuda), y.to(cuda), mask.to(cuda))
+    # oracle: fp32 on bf16-rounded initial weights
+    sd = bf16_round(g["sd"])
+    csd = bf16_round(gc["sd"])
+    names = ["bridge.vis_proj.weight", "bridge.vis_proj.bias"]
+    for n in names:
+        sd[n].requires_grad_(True)
+    mom = [torch.zeros_like(sd[n]) for n in names], [torch.zeros_like(sd[n]) for n in names]
+    with torch.no_grad():
+        z = O.pool33(O.clip_features(csd, pixels.to(torch.bfloat16).float(), 2, 2))
+    losses, ref_losses = [], []
+    for it in range(1, 5):
+        losses.append(step.run().item())
+        for n in names:
+            sd[n].grad = None
+        _, loss = O.caption_linear_forward(sd, z, x, labels, cfg["n_layer"], cfg["n_head"])
+        loss.backward()
+        ref_losses.append(loss.item())
+        with torch.no_grad():
+            O.clip_and_adamw([sd[n] for n in names], [sd[n].grad for n in names], mom[0], mom[1], it, 1e-2, [0.1, 0.0])
+    assert abs(losses[0] - ref_losses[0]) / ref_losses[0] < 3e-3, (losses, ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / b < 1.5e-2, (losses, ref_losses)
+    assert losses[-1] < losses[0]                                         # it actually trains
+    w = m.bridge.vis_proj.weight.detach().float().cpu()
+    assert F.cosine_similarity((w - g["sd"]["bridge.vis_proj.weight"]).flatten(),
+                               (sd["bridge.vis_proj.weight"].detach() - g["sd"]["bridge.vis_proj.weight"]).flatten(),
+                               dim=0) > 0.98                              # same update direction after 4 steps
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_gpt2_pretrain_steps_with_grad_accumulation(cuda, use_graph):
+    from gpt2_vision_language_b200 import gpt2
+    from gpt2_vision_language_b200.step import PretrainStep
+    from oracle import torch_oracle as O
+    g = load("gpt2_tiny.pt")
+    cfg = g["cfg"]
+    m = gpt2.GPT(gpt2.GPTConfig(**cfg))
+    m.load_state_dict(g["sd"])
+    m = m.to(cuda).to(torch.bfloat16)
+    accum, mb, T = 2, 3, 24
+    step = PretrainStep(m, micro_batch=mb, seq=T, grad_accum=accum, lr=3e-3, weight_decay=0.1, use_graph=use_graph)
+    gen = torch.Generator().manual_seed(5)
+    xs = torch.randint(0, 256, (accum, mb, T), generator=gen)
+    ys = torch.randint(0, 256, (accum, mb, T), generator=gen)
+    step.load_tokens(xs.to(cuda), ys.to(cuda))
+    sd = bf16_round(g["sd"])
+    names = [n for n, _ in m.named_parameters()]                     # tied wte/lm_head appears once
+    params = {n: sd[n].clone().requires_grad_(True) for n in names}
+    wds = [0.1 if params[n].dim() >= 2 else 0.0 for n in names]
+    mom = [torch.zeros_like(params[n]) for n in names], [torch.zeros_like(params[n]) for n in names]
+
+    def full_sd():
+        d = dict(sd)
+        d.update(params)
+        d["lm_head.weight"] = params["transformer.wte.weight"] if "transformer.wte.weight" in params else params["lm_head.weight"]
+        d["transformer.wte.weight"] = d["lm_head.weight"]
+        return d
+    losses, ref_losses = [], []
+    for it in range(1, 4):
+        losses.append(step.run().item())
+        for p in params.values():
+            p.grad = None
+        tot = 0.0
+        for i in range(accum):
+            _, loss = O.gpt2_forward(full_sd(), xs[i], ys[i], cfg["n_layer"], cfg["n_head"])
+            (loss / accum).backward()
+            tot += loss.item() / accum
+        ref_losses.append(tot)
+        with torch.no_grad():
+            O.clip_and_adamw([params[n] for n in names], [params[n].grad for n in names], mom[0], mom[1], it, 3e-3, wds)
+    assert abs(losses[0] - ref_losses[0]) / ref_losses[0] < 3e-3, (losses, ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / b < 2e-2, (losses, ref_losses)
+    assert losses[-1] < losses[0]
