@@ -1,0 +1,699 @@
+// Streaming (flash) attention on the tcgen05 tensor cores for long sequences (GPT-2 pretraining, T = 1024),
+// forward and backward, head dim 64, causal or not.  Three kernels, all with 128 threads = 128 TMEM lanes:
+//
+//   forward   CTA = 128 queries of one (b,h); loop over 128-key blocks (double-buffered TMA loads):
+//             S = Q K_j^T -> TMEM; thread = query row: running max / sum, P (bf16) written in place over S;
+//             O_j = P V_j (A from TMEM, V as MN-major B) -> TMEM; o_reg = o_reg * corr + O_j in registers.
+//   bwd dK/dV CTA = 128 keys; loop over query blocks.  Everything is computed TRANSPOSED so that the operand that
+//             must come from TMEM is always the A operand:  S^T = K_j Q_i^T and dP^T = V_j dO_i^T (thread = key row,
+//             lse / delta indexed by column), P^T and dS^T (bf16, in place) are then the A operands of
+//             dV_j += P^T dO_i and dK_j += dS^T Q_i.  One smem tile [query x 64] serves both as the K-major B
+//             operand of the first two products and as the MN-major B operand of the last two.
+//   bwd dQ    CTA = 128 queries; loop over key blocks: S = Q_i K_j^T, dP = dO_i V_j^T, dS in place,
+//             dQ_i += dS K_j (K_j as MN-major B).  Recomputing S and dP here (7 instead of 5 block products)
+//             buys a backward without atomics.
+//
+// Scores are kept unscaled in TMEM; probabilities are exp2(s * scale*log2e - lse*log2e) with the forward's lse.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace vlk {
+namespace {
+
+constexpr int BQ = 128;   // query rows per block = TMEM lanes
+constexpr int BK = 128;   // keys per block
+constexpr int kTile = 128 * 128;  // bytes of a 128-row x 64-col bf16 tile
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct Strides {
+    long long bs;
+    int rs;
+};
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct FlashFwdParams {
+    bf16* o;
+    float* lse;
+    Strides os;
+    int H, Tq, Tk, causal;
+    float scale, scale_log2e;
+};
+
+// smem: Q | K0 | V0 | K1 | V1 | barriers
+__global__ void __launch_bounds__(128, 2)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, FlashFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = smem + kTile;  // [buf][K|V]
+    uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
+    uint64_t* bar_kv = bar_q + 1;   // [2]
+    uint64_t* bar_s = bar_q + 3;
+    uint64_t* bar_o = bar_q + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * BQ;
+    const int shift = p.Tk - p.Tq;
+    int nkb = (p.Tk + BK - 1) / BK;
+    if (p.causal) nkb = min(nkb, (q0 + BQ - 1 + shift) / BK + 1);
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        ptx::mbar_init(bar_q, 1);
+        ptx::mbar_init(&bar_kv[0], 1);
+        ptx::mbar_init(&bar_kv[1], 1);
+        ptx::mbar_init(bar_s, 1);
+        ptx::mbar_init(bar_o, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tO = tmem + 128;
+
+    auto load_kv = [&](int j) {
+        uint8_t* dst = sKV + (j & 1) * 2 * kTile;
+        ptx::mbar_arrive_expect_tx(&bar_kv[j & 1], 2 * kTile);
+        ptx::tma_load_3d(dst, &tmap_k, &bar_kv[j & 1], h * 64, j * BK, b);
+        ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[j & 1], h * 64, j * BK, b);
+    };
+    if (threadIdx.x == 0) {
+        ptx::mbar_arrive_expect_tx(bar_q, kTile);
+        ptx::tma_load_3d(sQ, &tmap_q, bar_q, h * 64, q0, b);
+        load_kv(0);
+    }
+
+    const int row = threadIdx.x, qi = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int lim = p.Tk;  // keys [0, lim) visible to this row
+    if (p.causal) lim = min(p.Tk, qi + shift + 1);
+    if (lim < 1) lim = 1;
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+
+    for (int j = 0; j < nkb; ++j) {
+        const uint32_t par = (j >> 1) & 1;
+        if (threadIdx.x == 0) {
+            if (j == 0) ptx::mbar_wait(bar_q, 0);
+            ptx::mbar_wait(&bar_kv[j & 1], par);
+            ptx::tc_fence_after_sync();
+            const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_s);
+            if (j + 1 < nkb) load_kv(j + 1);  // the other buffer was released by the previous iteration's bar_o wait
+        }
+        ptx::mbar_wait(bar_s, j & 1);
+        ptx::tc_fence_after_sync();
+        const int k0 = j * BK;
+        const bool masked = (k0 + BK > __reduce_min_sync(0xffffffffu, lim));  // warp-uniform
+        // ---- row max of this block ----
+        float mj = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < BK; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, r);
+            ptx::tmem_ld_wait();
+            if (!masked) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mj = fmaxf(mj, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (k0 + c + i < lim) mj = fmaxf(mj, __uint_as_float(r[i]));
+            }
+        }
+        const float m_new = fmaxf(m, mj);
+        // rows that see nothing in this block keep their state (m_new may still be -inf for early causal rows)
+        const float mb = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2e;
+        const float corr = (m == -INFINITY) ? 0.f : ex2f(m * p.scale_log2e - mb);
+        float lj = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BK; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, r);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float e0 = ex2f(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
+                float e1 = ex2f(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
+                if (masked) {
+                    if (k0 + c + 2 * i >= lim) e0 = 0.f;
+                    if (k0 + c + 2 * i + 1 >= lim) e1 = 0.f;
+                }
+                lj += e0 + e1;
+                const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            ptx::tmem_st_32x32b_x16(tS + lane_base + (c >> 1), pk);
+        }
+        l = l * corr + lj;
+        m = m_new;
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ptx::tc_fence_after_sync();
+            const uint32_t av = ptx::smem_u32(sKV + (j & 1) * 2 * kTile + kTile);
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+                ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_o);
+        }
+        ptx::mbar_wait(bar_o, j & 1);
+        ptx::tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tO + lane_base + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(r[i]));
+        }
+        ptx::tc_fence_before_sync();  // S / O columns are rewritten by the next iteration's MMAs
+        __syncthreads();
+    }
+    if (qi < p.Tq) {
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        bf16* orow = p.o + b * p.os.bs + static_cast<size_t>(qi) * p.os.rs + h * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = o[c + i] * inv;
+            stg16(orow + c, pack8(t));
+        }
+        if (p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(l);
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, 256);
+    }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// delta[b,h,i] = dO_i . O_i
+__global__ void __launch_bounds__(128)
+flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, int H, int Tq,
+                   Strides os, int total_rows) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= total_rows) return;
+    const int qi = w % Tq, h = (w / Tq) % H, b = w / (Tq * H);
+    const size_t off = b * os.bs + static_cast<size_t>(qi) * os.rs + h * 64;
+    const float2 a = __bfloat1622float2(reinterpret_cast<const bf162*>(o + off)[lane]);
+    const float2 g = __bfloat1622float2(reinterpret_cast<const bf162*>(d_o + off)[lane]);
+    const float s = warp_sum(a.x * g.x + a.y * g.y);
+    if (lane == 0) delta[w] = s;
+}
+
+struct FlashBwdParams {
+    const float* lse;
+    const float* delta;
+    bf16* out0;  // dK (kernel A) or dQ (kernel B)
+    bf16* out1;  // dV (kernel A)
+    Strides s0, s1;
+    int H, Tq, Tk, causal;
+    float scale, scale_log2e;
+};
+
+// ---- kernel A: dK_j, dV_j.  smem: K | V | (Q,dO) x 2 | lse/delta x 2 | barriers ----
+__global__ void __launch_bounds__(128, 1)
+flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                     FlashBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + kTile;
+    uint8_t* sQdO = smem + 2 * kTile;  // [buf][Q|dO]
+    float* sStat = reinterpret_cast<float*>(smem + 6 * kTile);  // [buf][lse(128) | delta(128)]
+    uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + 6 * kTile + 2 * 256 * 4);
+    uint64_t* bar_q = bar_kv + 1;  // [2]
+    uint64_t* bar_s = bar_kv + 3;
+    uint64_t* bar_acc = bar_kv + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int k0 = kb * BK;
+    const int shift = p.Tk - p.Tq;
+    const int nqb = (p.Tq + BQ - 1) / BQ;
+    int qb0 = 0;  // first query block that sees this key block (causal: query i sees key j iff j <= i + shift)
+    if (p.causal) qb0 = max(0, k0 - shift) / BQ;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        ptx::prefetch_tensormap(&tmap_do);
+        ptx::mbar_init(bar_kv, 1);
+        ptx::mbar_init(&bar_q[0], 1);
+        ptx::mbar_init(&bar_q[1], 1);
+        ptx::mbar_init(bar_s, 1);
+        ptx::mbar_init(bar_acc, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+
+    auto load_q = [&](int i) {
+        const int buf = (i - qb0) & 1;
+        uint8_t* dst = sQdO + buf * 2 * kTile;
+        ptx::mbar_arrive_expect_tx(&bar_q[buf], 2 * kTile);
+        ptx::tma_load_3d(dst, &tmap_q, &bar_q[buf], h * 64, i * BQ, b);
+        ptx::tma_load_3d(dst + kTile, &tmap_do, &bar_q[buf], h * 64, i * BQ, b);
+    };
+    if (threadIdx.x == 0) {
+        ptx::mbar_arrive_expect_tx(bar_kv, 2 * kTile);
+        ptx::tma_load_3d(sK, &tmap_k, bar_kv, h * 64, k0, b);
+        ptx::tma_load_3d(sV, &tmap_v, bar_kv, h * 64, k0, b);
+        if (qb0 < nqb) load_q(qb0);
+    }
+    const int row = threadIdx.x, kj = k0 + row;  // this thread's key
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.Tq;
+
+    for (int i = qb0; i < nqb; ++i) {
+        const int it = i - qb0, buf = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        const int qs = i * BQ;
+        // per-column statistics of this query block (pre-multiplied by log2e for exp2)
+        float* st = sStat + buf * 256;
+        {
+            const int qi = qs + row;
+            st[row] = qi < p.Tq ? p.lse[stat_base + qi] * 1.4426950408889634f : INFINITY;  // p -> 0 for padded rows
+            st[128 + row] = qi < p.Tq ? p.delta[stat_base + qi] : 0.f;
+        }
+        if (threadIdx.x == 0) {
+            if (it == 0) ptx::mbar_wait(bar_kv, 0);
+            ptx::mbar_wait(&bar_q[buf], par);
+            ptx::tc_fence_after_sync();
+            const uint32_t ak = ptx::smem_u32(sK), av = ptx::smem_u32(sV);
+            const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQ, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
+                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(bq + k * 32, 16, 1024), idesc, k != 0);
+                ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(bdo + k * 32, 16, 1024), idesc, k != 0);
+            }
+            ptx::umma_commit(bar_s);
+            if (i + 1 < nqb) load_q(i + 1);  // other buffer: its last readers (dV/dK MMAs) were waited on via bar_acc
+        }
+        __syncthreads();  // sStat visible
+        ptx::mbar_wait(bar_s, it & 1);
+        ptx::tc_fence_after_sync();
+        const bool diag = p.causal && (qs < kj + 128 - shift);  // some (key, query) pairs of this block are masked
+#pragma unroll 1
+        for (int c = 0; c < BQ; c += 32) {
+            uint32_t rs[32], rp[32];
+            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, rs);
+            ptx::tmem_ld_32x32b_x32(tDP + lane_base + c, rp);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16], dk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                float pv[2], dv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int col = c + 2 * t + u;  // query index within the block
+                    float pr = ex2f(fmaf(__uint_as_float(rs[2 * t + u]), p.scale_log2e, -st[col]));
+                    if (diag && (qs + col + shift < kj)) pr = 0.f;   // causal: query sees key iff key <= query + shift
+                    if (kj >= p.Tk) pr = 0.f;
+                    pv[u] = pr;
+                    dv[u] = pr * (__uint_as_float(rp[2 * t + u]) - st[128 + col]);
+                }
+                const bf162 hp = __floats2bfloat162_rn(pv[0], pv[1]);
+                const bf162 hd = __floats2bfloat162_rn(dv[0], dv[1]);
+                pk[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+            }
+            ptx::tmem_st_32x32b_x16(tS + lane_base + (c >> 1), pk);    // P^T in place
+            ptx::tmem_st_32x32b_x16(tDP + lane_base + (c >> 1), dk);   // dS^T in place
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ptx::tc_fence_after_sync();
+            const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
+#pragma unroll
+            for (int k = 0; k < BQ / 16; ++k) {
+                ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc,
+                                  (it | k) != 0);
+                ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc,
+                                  (it | k) != 0);
+            }
+            ptx::umma_commit(bar_acc);
+        }
+        // the accumulating MMAs read P^T / dS^T and this Q/dO buffer: wait before either is overwritten
+        ptx::mbar_wait(bar_acc, it & 1);
+        ptx::tc_fence_after_sync();
+    }
+    // ---- write dK (scaled) and dV ----
+    if (qb0 < nqb) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t tacc = which == 0 ? tDK : tDV;
+            bf16* dst = (which == 0 ? p.out0 : p.out1);
+            const Strides ss = which == 0 ? p.s0 : p.s1;
+            const float mul = which == 0 ? p.scale : 1.0f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tacc + lane_base + c, r);
+                ptx::tmem_ld_wait();
+                if (kj < p.Tk) {
+                    bf16* orow = dst + b * ss.bs + static_cast<size_t>(kj) * ss.rs + h * 64 + c;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = __uint_as_float(r[q * 8 + u]) * mul;
+                        stg16(orow + q * 8, pack8(t));
+                    }
+                }
+            }
+        }
+    } else if (kj < p.Tk) {  // no query sees this key block: zero gradients
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        bf16* r0 = p.out0 + b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs + h * 64;
+        bf16* r1 = p.out1 + b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs + h * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+            stg16(r0 + c, z);
+            stg16(r1 + c, z);
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, 512);
+    }
+}
+
+// ---- kernel B: dQ_i.  smem: Q | dO | (K,V) x 2 | barriers ----
+__global__ void __launch_bounds__(128, 1)
+flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                    FlashBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sdO = smem + kTile;
+    uint8_t* sKV = smem + 2 * kTile;  // [buf][K|V]
+    uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 6 * kTile);
+    uint64_t* bar_kv = bar_q + 1;  // [2]
+    uint64_t* bar_s = bar_q + 3;
+    uint64_t* bar_acc = bar_q + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = qb * BQ;
+    const int shift = p.Tk - p.Tq;
+    int nkb = (p.Tk + BK - 1) / BK;
+    if (p.causal) nkb = min(nkb, (q0 + BQ - 1 + shift) / BK + 1);
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        ptx::prefetch_tensormap(&tmap_do);
+        ptx::mbar_init(bar_q, 1);
+        ptx::mbar_init(&bar_kv[0], 1);
+        ptx::mbar_init(&bar_kv[1], 1);
+        ptx::mbar_init(bar_s, 1);
+        ptx::mbar_init(bar_acc, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+
+    auto load_kv = [&](int j) {
+        uint8_t* dst = sKV + (j & 1) * 2 * kTile;
+        ptx::mbar_arrive_expect_tx(&bar_kv[j & 1], 2 * kTile);
+        ptx::tma_load_3d(dst, &tmap_k, &bar_kv[j & 1], h * 64, j * BK, b);
+        ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[j & 1], h * 64, j * BK, b);
+    };
+    if (threadIdx.x == 0) {
+        ptx::mbar_arrive_expect_tx(bar_q, 2 * kTile);
+        ptx::tma_load_3d(sQ, &tmap_q, bar_q, h * 64, q0, b);
+        ptx::tma_load_3d(sdO, &tmap_do, bar_q, h * 64, q0, b);
+        load_kv(0);
+    }
+    const int row = threadIdx.x, qi = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    int lim = p.Tk;
+    if (p.causal) lim = min(p.Tk, qi + shift + 1);
+    const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.Tq + qi;
+    const float lse2 = qi < p.Tq ? p.lse[stat] * 1.4426950408889634f : INFINITY;
+    const float dlt = qi < p.Tq ? p.delta[stat] : 0.f;
+
+    for (int j = 0; j < nkb; ++j) {
+        const uint32_t par = (j >> 1) & 1;
+        if (threadIdx.x == 0) {
+            if (j == 0) ptx::mbar_wait(bar_q, 0);
+            ptx::mbar_wait(&bar_kv[j & 1], par);
+            ptx::tc_fence_after_sync();
+            const uint32_t aq = ptx::smem_u32(sQ), ado = ptx::smem_u32(sdO);
+            const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile), bv = bk + kTile;
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
+                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc, k != 0);
+                ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(bv + k * 32, 16, 1024), idesc, k != 0);
+            }
+            ptx::umma_commit(bar_s);
+            if (j + 1 < nkb) load_kv(j + 1);
+        }
+        ptx::mbar_wait(bar_s, j & 1);
+        ptx::tc_fence_after_sync();
+        const int k0 = j * BK;
+#pragma unroll 1
+        for (int c = 0; c < BK; c += 32) {
+            uint32_t rs[32], rp[32];
+            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, rs);
+            ptx::tmem_ld_32x32b_x32(tDP + lane_base + c, rp);
+            ptx::tmem_ld_wait();
+            uint32_t dk[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                float dv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float pr = ex2f(fmaf(__uint_as_float(rs[2 * t + u]), p.scale_log2e, -lse2));
+                    if (k0 + c + 2 * t + u >= lim) pr = 0.f;
+                    dv[u] = pr * (__uint_as_float(rp[2 * t + u]) - dlt);
+                }
+                const bf162 hd = __floats2bfloat162_rn(dv[0], dv[1]);
+                dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+            }
+            ptx::tmem_st_32x32b_x16(tDP + lane_base + (c >> 1), dk);  // dS in place
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ptx::tc_fence_after_sync();
+            const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K_j read MN-major: N = d, K = keys
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+                ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc,
+                                  (j | k) != 0);
+            ptx::umma_commit(bar_acc);
+        }
+        ptx::mbar_wait(bar_acc, j & 1);
+        ptx::tc_fence_after_sync();
+    }
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tDQ + lane_base + c, r);
+        ptx::tmem_ld_wait();
+        if (qi < p.Tq) {
+            bf16* orow = p.out0 + b * p.s0.bs + static_cast<size_t>(qi) * p.s0.rs + h * 64 + c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = __uint_as_float(r[q * 8 + u]) * p.scale;
+                stg16(orow + q * 8, pack8(t));
+            }
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, 512);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn2() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// [B, T, W] bf16 view -> box 64 x 128 x 1, 128B swizzle, zero fill
+int tmap_rows128(CUtensorMap* map, const void* base, int W, int T, int B, int rs, long long bs) {
+    EncodeTiledFn fn = encode_fn2();
+    VLK_REQUIRE(fn != nullptr, VLK_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLK_REQUIRE(r == CUDA_SUCCESS, VLK_ERR_DRIVER, "cuTensorMapEncodeTiled(flash) failed with CUresult %d", (int)r);
+    return VLK_OK;
+}
+
+constexpr int kFwdSmem = 5 * kTile + 128 + 1024;
+constexpr int kBwdSmem = 6 * kTile + 2 * 256 * 4 + 128 + 1024;
+
+}  // namespace
+
+int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                   int o_rs, int causal, float scale, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        VLK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        configured = true;
+    }
+    CUtensorMap tq, tk, tv;
+    int rc = tmap_rows128(&tq, q, H * 64, Tq, B, q_rs, q_bs);
+    if (rc) return rc;
+    rc = tmap_rows128(&tk, k, H * 64, Tk, B, k_rs, k_bs);
+    if (rc) return rc;
+    rc = tmap_rows128(&tv, v, H * 64, Tk, B, v_rs, v_bs);
+    if (rc) return rc;
+    FlashFwdParams p;
+    p.o = static_cast<bf16*>(o);
+    p.lse = lse;
+    p.os = Strides{o_bs, o_rs};
+    p.H = H;
+    p.Tq = Tq;
+    p.Tk = Tk;
+    p.causal = causal;
+    p.scale = scale;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    flash_fwd_kernel<<<dim3((Tq + BQ - 1) / BQ, H, B), 128, kFwdSmem, stream>>>(tq, tk, tv, p);
+    VLK_CHECK_LAUNCH("vlk_attn_fwd(flash)");
+    return VLK_OK;
+}
+
+int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                   void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
+                   int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
+                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float* delta,
+                   cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        configured = true;
+    }
+    const int rows = B * H * Tq;
+    flash_delta_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(static_cast<const bf16*>(o), static_cast<const bf16*>(d_o),
+                                                          delta, H, Tq, Strides{o_bs, o_rs}, rows);
+    VLK_CHECK_LAUNCH("vlk_attn_bwd(delta)");
+    CUtensorMap tq, tk, tv, tdo;
+    int rc = tmap_rows128(&tq, q, H * 64, Tq, B, q_rs, q_bs);
+    if (rc) return rc;
+    rc = tmap_rows128(&tk, k, H * 64, Tk, B, k_rs, k_bs);
+    if (rc) return rc;
+    rc = tmap_rows128(&tv, v, H * 64, Tk, B, v_rs, v_bs);
+    if (rc) return rc;
+    rc = tmap_rows128(&tdo, d_o, H * 64, Tq, B, o_rs, o_bs);
+    if (rc) return rc;
+    FlashBwdParams p;
+    p.lse = lse;
+    p.delta = delta;
+    p.H = H;
+    p.Tq = Tq;
+    p.Tk = Tk;
+    p.causal = causal;
+    p.scale = scale;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.out0 = static_cast<bf16*>(dk);
+    p.out1 = static_cast<bf16*>(dv);
+    p.s0 = Strides{dk_bs, dk_rs};
+    p.s1 = Strides{dv_bs, dv_rs};
+    flash_bwd_dkv_kernel<<<dim3((Tk + BK - 1) / BK, H, B), 128, kBwdSmem, stream>>>(tq, tk, tv, tdo, p);
+    VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dkv)");
+    p.out0 = static_cast<bf16*>(dq);
+    p.out1 = nullptr;
+    p.s0 = Strides{dq_bs, dq_rs};
+    flash_bwd_dq_kernel<<<dim3((Tq + BQ - 1) / BQ, H, B), 128, kBwdSmem, stream>>>(tq, tk, tv, tdo, p);
+    VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dq)");
+    return VLK_OK;
+}
+
+}  // namespace vlk

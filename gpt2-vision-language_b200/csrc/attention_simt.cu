@@ -444,6 +444,12 @@ int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, c
                    long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
                    const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
 
+int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                   void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
+                   int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
+                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float* delta,
+                   cudaStream_t stream);
+
 }  // namespace vlk
 
 using namespace vlk;
@@ -474,6 +480,16 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
             return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
                                   o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
                                   seed_state, stream_id, s);
+    }
+    {
+        // everything longer than the one-CTA-per-head tile runs on the tensor cores (streaming tcgen05 backward)
+        const char* force = getenv("VLK_ATTN_IMPL");
+        const bool aligned = q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && dq_rs % 8 == 0 &&
+                             dk_rs % 8 == 0 && dv_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 &&
+                             o_bs % 8 == 0;
+        if (aligned && !(force && strcmp(force, "simt") == 0))
+            return attn_flash_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs,
+                                  o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, delta, s);
     }
     float* scratch = delta;
     const dim3 gq((Tq + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);

@@ -30,6 +30,10 @@ int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* 
                    int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
                    unsigned int stream_id, cudaStream_t stream);
 
+int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                   int o_rs, int causal, float scale, cudaStream_t stream);
+
 // bring-up instrumentation: per-phase %globaltimer stamps of the first CTAs (read back by vlk_debug_dump)
 __device__ long long g_attn_dbg[64 * 16];
 __device__ __forceinline__ void dbg_stamp(int enabled, int slot) {
@@ -285,7 +289,17 @@ __device__ __forceinline__ float dot_q_kx(const uint8_t* qrow_base, int qr7, con
     return acc;
 }
 
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: two threads per query row (warps w and w+4 share TMEM lane quadrant w&3).  Thread "half" h owns
+// score columns [128h, 128h+128): it reads them, writes its P columns in place inside its OWN column range
+// (keys 0..127 -> TMEM cols [0,64), keys 128..255 -> cols [128,192)) and later normalises O columns [32h, 32h+32)
+// (O lives in cols [192,256), dead score columns of half 1).  Row max / row sum / extra-key probabilities are
+// exchanged through shared memory.
+constexpr int k2OffXchg = k2OffBar + 128;                 // smax[2][128] | ssum[2][128] | spx[16][128] floats
+constexpr int k2XchgBytes = (2 + 2 + 16) * 128 * 4;
+constexpr int k2SmemTotal = k2OffXchg + k2XchgBytes + 1024;
+constexpr uint32_t k2TmemO3 = 192;
+
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                            const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kx,
                            const __grid_constant__ CUtensorMap tmap_vx, Fwd2Params p) {
@@ -296,8 +310,13 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     uint64_t* bar_s = bar_qk + 2;
     uint64_t* bar_o = bar_qk + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
+    float* smax = reinterpret_cast<float*>(smem + k2OffXchg);
+    float* ssum = smax + 256;
+    float* spx = ssum + 256;
 
     const int warp = threadIdx.x >> 5;
+    const int half = threadIdx.x >> 7;
+    const int row = threadIdx.x & 127;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int n_main = p.n_main, n_extra = p.n_extra;
     dbg_stamp(p.debug, 0);
@@ -344,41 +363,44 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         ptx::umma_commit(bar_s);
     }
 
-    const int row = threadIdx.x;
     const int qi = q0 + row;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     int lim = p.Tk;
     if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
     if (lim < 1) lim = 1;
     const uint8_t* qrow = smem + k2OffQ + (row >> 3) * 1024 + (row & 7) * 128;
-    const int qr7 = row & 7;
+    // this thread's score columns [dom0, dom1); `full`: end of the prefix that needs no masking.  Warp-uniform on
+    // purpose: the tcgen05.ld/st below are .sync.aligned, every lane must run the same trip counts.
+    const int dom0 = min(half * 128, n_main), dom1 = min(dom0 + 128, n_main);
+    const int lim_min = __reduce_min_sync(0xffffffffu, lim);
+    const int full = dom0 + (max(min(lim_min, dom1) - dom0, 0) & ~31);
+    const uint32_t pcol0 = half * 128;  // P columns of this half start here (in place, inside its own range)
 
-    // scores of the extra keys (CUDA cores), needed for the row max
-    ptx::mbar_wait(bar_qk, 0);  // Q / K / Kx are in shared memory
-    float sx[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) sx[e] = (e < n_extra && 256 + e < lim) ? dot_q_kx(qrow, qr7, smem + k2OffKx, e) : -INFINITY;
-
+    // scores of the extra keys (CUDA cores; half 0 only), needed for the row max.  They are parked in this
+    // thread's private slots of the exchange buffer (a rolled loop: 16 unrolled copies of the dot product blew
+    // the instruction cache).
+    float m = -INFINITY;
+    if (half == 0 && n_extra > 0) {
+        ptx::mbar_wait(bar_qk, 0);  // Q / Kx are in shared memory
+#pragma unroll 1
+        for (int e = 0; e < n_extra; ++e) {
+            const float sc = (256 + e < lim) ? dot_q_kx(qrow, row & 7, smem + k2OffKx, e) : -INFINITY;
+            spx[e * 128 + row] = sc;
+            m = fmaxf(m, sc);
+        }
+    }
     dbg_stamp(p.debug, 3);
     ptx::mbar_wait(bar_s, 0);
     ptx::tc_fence_after_sync();
     dbg_stamp(p.debug, 4);
-    float m = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) m = fmaxf(m, sx[e]);
-    // Columns below `full` need no masking (every key visible to this row): the common, non-causal case runs the
-    // predicate-free loops; only the boundary chunk pays for the per-element compares.
-    // (warp-uniform on purpose: the tcgen05.ld/st below are .sync.aligned, so every lane must run the same trip
-    // counts — with a causal mask `lim` differs per row and the smallest one in the warp decides.)
-    const int full = min(__reduce_min_sync(0xffffffffu, lim), n_main) & ~31;
-    for (int c = 0; c < full; c += 32) {
+    for (int c = dom0; c < full; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(trow + c, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
     }
-    for (int c = full; c < n_main; c += 16) {
+    for (int c = full; c < dom1; c += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(trow + c, r);
         ptx::tmem_ld_wait();
@@ -386,10 +408,13 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         for (int i = 0; i < 16; ++i)
             if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
     }
+    smax[half * 128 + row] = m;
+    __syncthreads();
+    m = fmaxf(smax[row], smax[128 + row]);
     const float mb = m * p.scale_log2e;
     float sum = 0.f;
     dbg_stamp(p.debug, 5);
-    for (int c = 0; c < full; c += 32) {
+    for (int c = dom0; c < full; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(trow + c, r);
         ptx::tmem_ld_wait();
@@ -398,15 +423,14 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         for (int i = 0; i < 16; ++i) {
             const float e0 = ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
             const float e1 = ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
+            sum += e0 + e1;
             const bf162 h2 = __floats2bfloat162_rn(e0, e1);
-            const float2 back = __bfloat1622float2(h2);  // sum what the tensor core will actually multiply
-            sum += back.x + back.y;
             pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        // P columns [c/2, c/2+16) overwrite S columns this thread has already consumed
-        ptx::tmem_st_32x32b_x16(trow + (c >> 1), pk);
+        // P columns overwrite score columns of this thread's own range that it has already consumed
+        ptx::tmem_st_32x32b_x16(trow + pcol0 + ((c - dom0) >> 1), pk);
     }
-    for (int c = full; c < n_main; c += 16) {
+    for (int c = full; c < dom1; c += 16) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(trow + c, r);
         ptx::tmem_ld_wait();
@@ -416,18 +440,21 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             const float e0 = (c + 2 * i < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb)) : 0.f;
             const float e1 =
                 (c + 2 * i + 1 < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb)) : 0.f;
+            sum += e0 + e1;
             const bf162 h2 = __floats2bfloat162_rn(e0, e1);
-            const float2 back = __bfloat1622float2(h2);
-            sum += back.x + back.y;
             pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        ptx::tmem_st_32x32b_x8(trow + (c >> 1), pk);
+        ptx::tmem_st_32x32b_x8(trow + pcol0 + ((c - dom0) >> 1), pk);
     }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        sx[e] = (e < n_extra && 256 + e < lim) ? ex2_fast(fmaf(sx[e], p.scale_log2e, -mb)) : 0.f;
-        sum += sx[e];
+    if (half == 0) {
+#pragma unroll 1
+        for (int e = 0; e < n_extra; ++e) {
+            const float pe = (256 + e < lim) ? ex2_fast(fmaf(spx[e * 128 + row], p.scale_log2e, -mb)) : 0.f;
+            sum += pe;
+            spx[e * 128 + row] = pe;
+        }
     }
+    ssum[half * 128 + row] = sum;
     dbg_stamp(p.debug, 6);
     ptx::tmem_st_wait();
     ptx::tc_fence_before_sync();
@@ -440,53 +467,51 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         const uint32_t sv = ptx::smem_u32(smem + k2OffV);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (MN-major)
         const int ksteps = n_main / 16;
-        for (int k = 0; k < ksteps; ++k)
-            ptx::umma_bf16_ts(tmem + k2TmemO, tmem + k * 8, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc,
+        for (int k = 0; k < ksteps; ++k) {
+            const uint32_t pa = k < 8 ? k * 8 : 128 + (k - 8) * 8;       // where that key block's P lives
+            ptx::umma_bf16_ts(tmem + k2TmemO3, tmem + pa, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc,
                               k != 0);
+        }
         ptx::umma_commit(bar_o);
     }
     ptx::mbar_wait(bar_v, 0);  // Vx visible to every thread
     ptx::mbar_wait(bar_o, 0);
     ptx::tc_fence_after_sync();
     dbg_stamp(p.debug, 8);
+    sum = ssum[row] + ssum[128 + row];
     const float inv = 1.0f / sum;
-    bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
-#pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(trow + k2TmemO + c, r);
+    {
+        // this thread normalises and stores O columns [32*half, 32*half + 32) of its row
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(trow + k2TmemO3 + half * 32, r);
         ptx::tmem_ld_wait();
-        float t0[8], t1[8];
+        float t[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            t0[i] = __uint_as_float(r[i]);
-            t1[i] = __uint_as_float(r[8 + i]);
-        }
+        for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(r[i]);
         for (int e = 0; e < n_extra; ++e) {  // rank-1 updates from the extra keys
             const uint8_t* vrow = smem + k2OffVx + (e >> 3) * 1024 + (e & 7) * 128;
-            float v0[8], v1[8];
-            unpack8(*reinterpret_cast<const uint4*>(vrow + ((((c >> 3)) ^ (e & 7)) << 4)), v0);
-            unpack8(*reinterpret_cast<const uint4*>(vrow + ((((c >> 3) + 1) ^ (e & 7)) << 4)), v1);
-            float pe = 0.f;
+            const float pe = spx[e * 128 + row];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pe = (j == e) ? sx[j] : pe;
+            for (int q = 0; q < 4; ++q) {
+                float v8[8];
+                unpack8(*reinterpret_cast<const uint4*>(vrow + (((half * 4 + q) ^ (e & 7)) << 4)), v8);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                t0[i] = fmaf(pe, v0[i], t0[i]);
-                t1[i] = fmaf(pe, v1[i], t1[i]);
+                for (int i = 0; i < 8; ++i) t[q * 8 + i] = fmaf(pe, v8[i], t[q * 8 + i]);
             }
         }
         if (qi < p.Tq) {
+            bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64 + half * 32;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                t0[i] *= inv;
-                t1[i] *= inv;
+            for (int q = 0; q < 4; ++q) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = t[q * 8 + i] * inv;
+                stg16(orow + q * 8, pack8(o8));
             }
-            stg16(orow + c, pack8(t0));
-            stg16(orow + c + 8, pack8(t1));
         }
     }
-    if (qi < p.Tq && p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
+    if (half == 0 && qi < p.Tq && p.lse != nullptr)
+        p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
     dbg_stamp(p.debug, 9);
     ptx::tc_fence_before_sync();
     __syncthreads();
@@ -554,7 +579,11 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (attn_small_applicable(Tq, Tk) && (dropout_p > 0.f || !(force && strcmp(force, "simt") == 0)))
         return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                               scale, dropout_p, seed_state, stream_id, s);
-    const bool want_tc = force ? (strcmp(force, "tcgen05") == 0) : (Tk > 64);
+    // long sequences (GPT-2 pretraining, T = 1024): streaming tcgen05 kernel
+    if ((Tk > kMaxKeys && !(force && strcmp(force, "simt") == 0)) || (force && strcmp(force, "flash") == 0))
+        return attn_flash_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                              scale, s);
+    const bool want_tc = force ? (strncmp(force, "tcgen05", 7) == 0) : (Tk > 64);
     if (!want_tc || Tk > kMaxKeys || Tq < 64 || (force && strcmp(force, "simt") == 0))
         return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                              scale, s, 0);
@@ -570,7 +599,7 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
         static bool configured2 = false;
         if (!configured2) {
             VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          k2SmemBytes));
+                                          k2SmemTotal));
             configured2 = true;
         }
         Fwd2Params p2;
@@ -599,7 +628,7 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
         rc = make_tmap3(&tvx, v, H * 64, Tk, B, v_rs, v_bs, 16);
         if (rc) return rc;
         const dim3 grid2((tc_rows + 127) / 128, H, B);
-        attn_fwd_tcgen05_v2_kernel<<<grid2, 128, k2SmemBytes, s>>>(tq, tk, tv, tkx, tvx, p2);
+        attn_fwd_tcgen05_v2_kernel<<<grid2, 256, k2SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p2);
         VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v2)");
         if (tail > 0)
             return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
