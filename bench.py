@@ -268,7 +268,6 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks):
                      "unit": "TFLOP/s", "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak,
                      "gemm_ms_per_micro_step": tot_ms, "traffic": None},
         "cpu_baseline": None, "final_loss": float(loss_h[-1]),
-        "note": "attention at T=1024 runs on the streaming CUDA-core kernels this round (DESIGN.md 7)",
     }
     print(json.dumps(line))
 

@@ -40,3 +40,15 @@ print(f"GPT-2 attn fwd B=64 H=12 T=64 causal: {us:.1f} us")
 us = timeit(lambda: ops.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, do, lse, dqkv[..., :C],
                                       dqkv[..., C:2 * C], dqkv[..., 2 * C:], H, True))
 print(f"GPT-2 attn bwd B=64 H=12 T=64 causal: {us:.1f} us")
+B, H, T = 16, 12, 1024
+C = H * 64
+qkv = torch.randn(B, T, 3 * C, device="cuda").bfloat16()
+o, lse = ops.attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], H, True)
+do = torch.randn_like(o)
+dqkv = torch.empty_like(qkv)
+us = timeit(lambda: ops.attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], H, True))
+fl = 4.0 * B * H * T * T * 64 / 2
+print(f"pretrain attn fwd B=16 H=12 T=1024 causal: {us:.1f} us  {fl/us/1e6:.0f} TFLOP/s")
+us = timeit(lambda: ops.attention_bwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], o, do, lse, dqkv[..., :C],
+                                      dqkv[..., C:2 * C], dqkv[..., 2 * C:], H, True))
+print(f"pretrain attn bwd B=16 H=12 T=1024 causal: {us:.1f} us  {2.5*fl/us/1e6:.0f} TFLOP/s")

@@ -103,6 +103,33 @@ def test_attention_fwd_bwd(cuda, B, H, Tq, Tk, causal):
     assert relerr(dv, vr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 12, 1024, 1024, True), (1, 4, 384, 384, True), (1, 2, 500, 500, False),
+                                              (2, 3, 129, 300, False), (1, 2, 640, 640, True)])
+def test_flash_attention_long_sequences(cuda, B, H, Tq, Tk, causal):
+    """Streaming tcgen05 forward/backward (GPT-2 pretraining shape T=1024 and ragged lengths) vs torch fp32."""
+    from gpt2_vision_language_b200 import ops
+    C = H * 64
+    g = torch.Generator(device="cuda").manual_seed(Tq + 7 * Tk)
+    if Tq == Tk:
+        qkv = torch.randn(B, Tq, 3 * C, device=cuda, generator=g).bfloat16()
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
+        kv = torch.randn(B, Tk, 2 * C, device=cuda, generator=g).bfloat16()
+        k, v = kv[..., :C], kv[..., C:]
+    o, lse = ops.attention_fwd(q, k, v, H, causal)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, H, causal)
+    assert relerr(o, ref) < 1.5e-2
+    d_o = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
+    ref.backward(d_o.float())
+    dq, dk, dv = torch.empty_like(q.contiguous()), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
+    ops.attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, H, causal)
+    assert relerr(dq, qr.grad) < 2e-2
+    assert relerr(dk, kr.grad) < 2e-2
+    assert relerr(dv, vr.grad) < 2e-2
+
+
 @pytest.mark.parametrize("rows,V", [(64, 50304), (7, 512), (300, 1024)])
 def test_lmhead_ce(cuda, rows, V):
     from gpt2_vision_language_b200 import ops
