@@ -476,7 +476,8 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {
         const char* force = getenv("VLK_ATTN_IMPL");
-        if (attn_small_applicable(Tq, Tk) && (dropout_p > 0.f || !(force && strcmp(force, "simt") == 0)))
+        if (attn_small_applicable(Tq, Tk) &&
+            (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0))))
             return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
                                   o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
                                   seed_state, stream_id, s);

@@ -576,7 +576,8 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
                 "vlk_attn_fwd: 16B alignment");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const char* force = getenv("VLK_ATTN_IMPL");
-    if (attn_small_applicable(Tq, Tk) && (dropout_p > 0.f || !(force && strcmp(force, "simt") == 0)))
+    if (attn_small_applicable(Tq, Tk) &&
+        (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0))))
         return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                               scale, dropout_p, seed_state, stream_id, s);
     // long sequences (GPT-2 pretraining, T = 1024): streaming tcgen05 kernel

@@ -38,6 +38,7 @@ struct EpiParams {
     int ldd, ldr, ld_aux;
     int act, dact, out_fp32;
     float alpha;
+    int split_k;  // > 1: the K range is cut into split_k slices, partial tiles are atomically added into fp32 D
     int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 };
 
@@ -117,10 +118,17 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
     }
     if (ep.out_fp32) {
         float* p = reinterpret_cast<float*>(ep.D) + static_cast<size_t>(row) * ep.ldd + col0;
+        if (ep.split_k > 1) {  // split-K partial: D was zeroed by the caller
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (c * 4 < ncols_valid)
-                *reinterpret_cast<float4*>(p + c * 4) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+            for (int c = 0; c < 32; ++c)
+                if (c < ncols_valid) atomicAdd(p + c, v[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c * 4 < ncols_valid)
+                    *reinterpret_cast<float4*>(p + c * 4) =
+                        make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+            }
         }
     } else {
         bf16* p = reinterpret_cast<bf16*>(ep.D) + static_cast<size_t>(row) * ep.ldd + col0;
@@ -357,8 +365,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     const int num_m_units = (num_m_blocks + CLUSTER - 1) / CLUSTER;
     const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m_units * num_n_blocks;
-    const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int num_out_tiles = num_m_units * num_n_blocks;
+    const int num_tiles = num_out_tiles * ep.split_k;  // split-K: slice index is the slowest-varying part
+    const int total_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_per_split = (total_k_blocks + ep.split_k - 1) / ep.split_k;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;  // two accumulator stages; power of two >= 32
     const int cta_rank = CLUSTER > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
     const int unit0 = blockIdx.x / CLUSTER, unit_stride = gridDim.x / CLUSTER;
@@ -395,9 +405,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
                 int m_unit, n_blk;
-                unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+                unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
                 const int m_blk = m_unit * CLUSTER + cta_rank;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
@@ -453,7 +464,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
                     const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -467,7 +479,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                  : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                  : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16_ss(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     // frees the smem slot (in every CTA that multicasts into it) when these MMAs retire
                     if constexpr (CLUSTER == 1) ptx::umma_commit(&empty_bar[stage]);
@@ -488,7 +500,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int local_tile = 0;
         for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
             int m_unit, n_blk;
-            unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+            unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
             const int m_blk = m_unit * CLUSTER + cta_rank;
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
@@ -563,8 +575,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
     const int num_m_units = (num_m_blocks + 1) / 2;
     const int num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
-    const int num_tiles = num_m_units * num_n_blocks;
-    const int num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int num_out_tiles = num_m_units * num_n_blocks;
+    const int num_tiles = num_out_tiles * ep.split_k;
+    const int total_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_per_split = (total_k_blocks + ep.split_k - 1) / ep.split_k;
     constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
 
@@ -599,10 +613,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
                 int m_unit, n_blk;
-                unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+                unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
                 const int m_blk = m_unit * 2 + cta_rank;
                 const int n0 = n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2);
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
@@ -640,7 +655,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
                     const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -651,7 +667,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                                  : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                  : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16_ss_2sm(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
                     }
                     ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
                     if (++stage == kStages) {
@@ -670,7 +686,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         int local_tile = 0;
         for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
             int m_unit, n_blk;
-            unit_to_mn(tile, num_m_units, num_n_blocks, group, m_unit, n_blk);
+            unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
             const int m_blk = m_unit * 2 + cta_rank;
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
@@ -743,7 +759,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
         configured = true;
     }
     const int m_units = ((M + BLOCK_M - 1) / BLOCK_M + CLUSTER - 1) / CLUSTER;
-    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N) * ep.split_k;
     const int max_clusters = sms / CLUSTER;
     const int grid = (units < max_clusters ? units : max_clusters) * CLUSTER;
     cudaLaunchConfig_t cfg = {};
@@ -781,7 +797,7 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
         configured = true;
     }
     const int m_units = ((M + BLOCK_M - 1) / BLOCK_M + 1) / 2;
-    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int units = m_units * ((N + BLOCK_N - 1) / BLOCK_N) * ep.split_k;
     const int max_clusters = sms / 2;
     const int grid = (units < max_clusters ? units : max_clusters) * 2;
     cudaLaunchConfig_t cfg = {};
@@ -850,7 +866,7 @@ using namespace vlk;
 extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                              int transA, int transB, const void* bias, const void* residual, int ldr,
                              const void* aux_in, void* aux_out, int ld_aux, const float* scale, int act, int dact,
-                             float alpha, int out_fp32, void* stream) {
+                             float alpha, int out_fp32, int split_k, void* stream) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -864,6 +880,18 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     VLK_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), VLK_ERR_ALIGNMENT, "vlk_gemm_bf16: 16B alignment");
     VLK_REQUIRE(act >= VLK_ACT_NONE && act <= VLK_ACT_QUICK_GELU, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: act=%d", act);
     VLK_REQUIRE(!dact || aux_in, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: dact needs aux_in");
+    if (split_k < 1) split_k = 1;
+    VLK_REQUIRE(split_k == 1 || (out_fp32 && !bias && !residual && !aux_in && !aux_out && !scale && act == VLK_ACT_NONE),
+                VLK_ERR_INVALID_ARG,
+                "vlk_gemm_bf16: split_k > 1 accumulates raw partial products atomically: it needs out_fp32 (zeroed by "
+                "the caller) and no epilogue operands");
+    {
+        // no empty slices: an empty slice would add an un-initialised accumulator
+        const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+        if (split_k > kblocks) split_k = kblocks;
+        const int per = (kblocks + split_k - 1) / split_k;
+        split_k = (kblocks + per - 1) / per;
+    }
     VLK_REQUIRE(!residual || (ldr % 8 == 0 && aligned16(residual)), VLK_ERR_ALIGNMENT, "vlk_gemm_bf16: residual");
     VLK_REQUIRE(!(aux_in || aux_out) || ld_aux % 8 == 0, VLK_ERR_ALIGNMENT, "vlk_gemm_bf16: ld_aux");
     VLK_REQUIRE(!bias || aligned16(bias), VLK_ERR_ALIGNMENT, "vlk_gemm_bf16: bias");
@@ -884,6 +912,7 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     ep.dact = dact;
     ep.out_fp32 = out_fp32;
     ep.alpha = alpha;
+    ep.split_k = split_k;
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
 

@@ -54,7 +54,7 @@ def _rows(t):
 # raw ops
 # ======================================================================================================
 def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in=None, aux_out=False,
-         scale=None, act=None, dact=False, alpha=1.0, out=None, out_fp32=False):
+         scale=None, act=None, dact=False, alpha=1.0, out=None, out_fp32=False, split_k=1):
     """D = epi(alpha * op(a) @ op(b)) with the epilogue of vlk_gemm_bf16 (include/vlk.h).
 
     a: [M,K] (or [K,M] if trans_a); b: [N,K] — nn.Linear weight layout — (or [K,N] if trans_b).
@@ -69,6 +69,17 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
     N, Kb = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
     if K != Kb:
         raise RuntimeError(f"gemm: contraction mismatch {K} vs {Kb}")
+    if split_k > 1:
+        # split-K partials are added atomically into an fp32 buffer, then rounded once
+        acc = torch.zeros((M, N), device=a.device, dtype=torch.float32)
+        gemm(a, b, trans_a=trans_a, trans_b=trans_b, alpha=alpha, out=acc, out_fp32=True, split_k=-split_k)
+        if out_fp32:
+            return acc
+        if out is None:
+            out = torch.empty((M, N), device=a.device, dtype=BF16)
+        check(lib.vlk_cast_f32_to_bf16(acc.data_ptr(), out.data_ptr(), acc.numel(), _stream()), "vlk_cast_f32_to_bf16")
+        return out
+    split_k = max(1, -split_k)   # internal call from the branch above
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else BF16)
     aux = None
@@ -86,7 +97,7 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
                            _p(aux) if (dact or aux_in is not None) else 0,
                            _p(aux) if aux_out else 0, aux.stride(0) if aux is not None else 0,
                            _p(scale), ACT[act] if not isinstance(act, int) else act, int(dact), float(alpha),
-                           int(out_fp32), _stream())
+                           int(out_fp32), int(split_k), _stream())
     check(rc, "vlk_gemm_bf16")
     return (out, aux) if aux_out else out
 
@@ -590,6 +601,7 @@ class LMHeadCEFn(torch.autograd.Function):
 
     CHUNK_ROWS = 512
     CHUNK_ROWS_DW = 4096
+    DH_SPLIT_K = 12
 
     @staticmethod
     def forward(ctx, h, weight, labels, row_weight):
@@ -621,7 +633,8 @@ class LMHeadCEFn(torch.autograd.Function):
                                           loss_row[r0:r1].data_ptr(), stats[1:].data_ptr(), r1 - r0, V, lg.stride(0),
                                           int(write_grad), _stream()), "vlk_softmax_ce_rows")
             if need_dh:
-                gemm(lg, weight, trans_b=True, out=dh[r0:r1])                 # d logits [r,V] x W [V,C]
+                # d logits [r,V] x W [V,C]: a handful of output tiles with K = V = 50304 -> split the contraction
+                gemm(lg, weight, trans_b=True, out=dh[r0:r1], split_k=LMHeadCEFn.DH_SPLIT_K)
             if need_dw:
                 if dw is None:
                     dw = gemm(lg, h2[r0:r1], trans_a=True, trans_b=True)      # d logits^T x h

@@ -119,6 +119,44 @@ class CaptionTrainStep:
         return self.loss
 
 
+class HostBatchFeeder:
+    """Double-buffered host -> device input pipeline for CaptionTrainStep.
+
+    The reference moves each batch with blocking ``.to(device)`` calls at the top of the step
+    (source/gpt2_linear/train.py:300-303).  Here the NEXT batch's pinned-host -> HBM copy (38.6 MB of fp32 pixels at
+    B=64) runs on a copy stream while the current step computes; at the step boundary a device-to-device copy
+    (a few microseconds) drops it into the step's static input buffers.  Every byte still crosses PCIe every step."""
+
+    def __init__(self, step):
+        self.step = step
+        self.copy_stream = torch.cuda.Stream()
+        self.stage = [tuple(torch.empty_like(t) for t in (step.pixels, step.x, step.y, step.mask)) for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D into stage[i] finished
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]   # D2D out of stage[i] finished
+        self._n_submit = self._n_load = 0
+        for e in self.consumed:
+            e.record()
+
+    def submit(self, pixels, x, y, mask):
+        """Start the asynchronous upload of one pinned host batch."""
+        i = self._n_submit & 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[i])
+            for dst, src in zip(self.stage[i], (pixels, x, y, mask)):
+                dst.copy_(src, non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self._n_submit += 1
+
+    def load(self):
+        """Make the oldest submitted batch the step's current input (on the compute stream)."""
+        i = self._n_load & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[i])
+        self.step.load_batch(*self.stage[i])
+        self.consumed[i].record(cur)
+        self._n_load += 1
+
+
 class PretrainStep:
     """GPT-2 124M pretraining step (source/gpt2/train_gpt2.py:456-478): ``grad_accum`` micro-batches of
     [micro_batch, seq] tokens -> loss/grad_accum -> backward (gradients accumulate in the flat bucket) -> all-reduce

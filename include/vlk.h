@@ -57,13 +57,16 @@ long long vlk_launch_count(void);
  *   gpt2_cross-att/model.py:49-57,83; gpt2_q_former/model.py:126-130,160 and the in/out projections of
  *   nn.MultiheadAttention (:119,:123); HF modeling_clip.py q/k/v/out_proj, fc1/fc2, patch_embedding,
  *   visual_projection; plus their autograd dgrad / wgrad GEMMs.
+ *   split_k > 1 cuts the contraction into slices computed by different CTAs and added atomically into an fp32 D
+ *   that the caller has zeroed (no epilogue operands allowed): for few-tile / huge-K products such as
+ *   d h = d logits . W (K = 50304).
  * Requirements: M,N,K > 0; N % 8 == 0 (and M % 8 == 0 when transA); lda/ldb/ldd/ldr/ld_aux % 8 == 0;
  *   16-byte aligned bases.  K is free (the tail of the last 64-wide k-block is zero-filled by TMA).
  */
 int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                   int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
                   void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
-                  void* stream);
+                  int split_k, void* stream);
 
 /* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
 int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);

@@ -31,13 +31,13 @@ def run_case(i):
     lib.vlk_last_error_string.restype = ctypes.c_char_p
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.vlk_gemm_bf16.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp, ci, vp, ci, ci,
-                                  cf, ci, vp]
+                                  cf, ci, ci, vp]
     torch.manual_seed(i)
     a = torch.randn((K, M) if ta else (M, K), device="cuda").bfloat16()
     b = torch.randn((K, N) if tb else (N, K), device="cuda").bfloat16()
     d = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     rc = lib.vlk_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, a.stride(0), b.stride(0), N, ta, tb,
-                           0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
+                           0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 1, torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         print(f"case {i} {CASES[i]}: rc={rc} {lib.vlk_last_error_string()}")
         return 1
@@ -51,11 +51,11 @@ def run_case(i):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         lib.vlk_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, a.stride(0), b.stride(0), N, ta, tb,
-                          0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
+                          0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 1, torch.cuda.current_stream().cuda_stream)
     s.record()
     for _ in range(20):
         lib.vlk_gemm_bf16(a.data_ptr(), b.data_ptr(), d.data_ptr(), M, N, K, a.stride(0), b.stride(0), N, ta, tb,
-                          0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, torch.cuda.current_stream().cuda_stream)
+                          0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 1, torch.cuda.current_stream().cuda_stream)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 20

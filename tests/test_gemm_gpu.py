@@ -92,6 +92,20 @@ def test_gemm_fp32_out_and_strided(cuda):
     _check(out, a.float() @ w.float().t(), tol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K,split", [(512, 768, 50304, 12), (256, 256, 640, 4), (100, 64, 4096, 7)])
+def test_gemm_split_k(cuda, M, N, K, split):
+    """Few output tiles + huge contraction (d h = d logits . W): K is cut into slices added atomically in fp32."""
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    b = torch.randn(K, N, device=cuda, generator=g).bfloat16()
+    out = ops.gemm(a, b, trans_b=True, split_k=split)
+    assert out.dtype == torch.bfloat16
+    _check(out, a.float() @ b.float())
+    with pytest.raises(RuntimeError):   # split-K is a raw-accumulate mode: no epilogue operands
+        ops.gemm(a, b, trans_b=True, bias=torch.zeros(N, device=cuda).bfloat16(), out_fp32=True, split_k=-split)
+
+
 def test_gemm_rejects_bad_args(cuda):
     from gpt2_vision_language_b200 import ops
     a = torch.randn(16, 12, device=cuda).bfloat16()
