@@ -342,22 +342,29 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
 // one WARP per (batch, head, row).  Lanes stride the keys for the scores (each K row is one 128-byte line),
 // softmax by warp shuffles, then each lane owns two output dims and walks the keys with coalesced V reads.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kFewMaxKeys = 288;  // 9 keys per lane
+constexpr int kFewMaxKeys = 512;
 
+// One CTA (4 warps) per (batch, head, row): the keys are split over the warps (so the serial chain per warp is
+// short), each warp runs an independent softmax over its slice — lane = key for the scores, lane = two output dims
+// for P.V with the V rows of 8 keys fetched per round — and the four partial (max, sum, acc) triples are merged
+// through shared memory.
 __global__ void __launch_bounds__(128)
 attn_fwd_fewrows_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                         bf16* __restrict__ o, float* __restrict__ lse, int B, int H, int Tq, int Tk, Addr qa, Addr ka,
                         Addr va, Addr oa, int causal, float scale, int q_row0) {
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ float sm_m[4], sm_l[4], sm_acc[4][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nrows = Tq - q_row0;
-    if (w >= B * H * nrows) return;
-    const int qi = q_row0 + w % nrows;
-    const int h = (w / nrows) % H, b = w / (nrows * H);
+    const int unit = blockIdx.x;
+    const int qi = q_row0 + unit % nrows;
+    const int h = (unit / nrows) % H, b = unit / (nrows * H);
     const bf16* qrow = q + b * qa.bs + static_cast<size_t>(qi) * qa.rs + h * D;
     const bf16* kb = k + b * ka.bs + h * D;
     const bf16* vb = v + b * va.bs + h * D;
     const int lim = causal ? min(Tk, qi + (Tk - Tq) + 1) : Tk;
+    // this warp's key slice: whole groups of 32 keys
+    const int groups = (lim + 31) / 32, gpw = (groups + 3) / 4;
+    const int g0 = w * gpw, g1 = min(groups, g0 + gpw);
     float qf[D];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -366,13 +373,14 @@ attn_fwd_fewrows_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) qf[c * 8 + i] = t[i] * scale;
     }
-    float s[kFewMaxKeys / 32];
+    constexpr int kMaxG = kFewMaxKeys / 32 / 4;  // key groups per warp
+    float s[kMaxG];
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
-        const int key = j * 32 + lane;
+    for (int j = 0; j < kMaxG; ++j) {
+        const int key = (g0 + j) * 32 + lane;
         s[j] = -INFINITY;
-        if (key < lim) {
+        if (g0 + j < g1 && key < lim) {
             const bf16* kr = kb + static_cast<size_t>(key) * ka.rs;
             float acc = 0.f;
 #pragma unroll
@@ -389,29 +397,58 @@ attn_fwd_fewrows_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, 
     m = warp_max(m);
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
-        s[j] = (j * 32 + lane < lim) ? __expf(s[j] - m) : 0.f;
+    for (int j = 0; j < kMaxG; ++j) {
+        s[j] = (s[j] > -INFINITY) ? __expf(s[j] - m) : 0.f;
         sum += s[j];
     }
     sum = warp_sum(sum);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < kFewMaxKeys / 32; ++j) {
-        const int base = j * 32;
-        if (base >= lim) break;
+    for (int j = 0; j < kMaxG; ++j) {
+        if (g0 + j >= g1) break;
+        const int base = (g0 + j) * 32;
         const int n = min(32, lim - base);
-        for (int t = 0; t < n; ++t) {
-            const float pj = __shfl_sync(0xffffffffu, s[j], t);
-            const float2 v2 = __bfloat1622float2(
-                reinterpret_cast<const bf162*>(vb + static_cast<size_t>(base + t) * va.rs)[lane]);
-            a0 = fmaf(pj, v2.x, a0);
-            a1 = fmaf(pj, v2.y, a1);
+#pragma unroll
+        for (int t0 = 0; t0 < 32; t0 += 8) {
+            if (t0 >= n) break;
+            float2 vv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {   // eight independent row fetches in flight
+                vv[u] = make_float2(0.f, 0.f);
+                if (t0 + u < n)
+                    vv[u] = __bfloat1622float2(
+                        reinterpret_cast<const bf162*>(vb + static_cast<size_t>(base + t0 + u) * va.rs)[lane]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float pj = __shfl_sync(0xffffffffu, s[j], t0 + u);
+                a0 = fmaf(pj, vv[u].x, a0);
+                a1 = fmaf(pj, vv[u].y, a1);
+            }
         }
     }
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    bf16* orow = o + b * oa.bs + static_cast<size_t>(qi) * oa.rs + h * D;
-    reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(a0 * inv, a1 * inv);
-    if (lse != nullptr && lane == 0) lse[(static_cast<size_t>(b) * H + h) * Tq + qi] = m + __logf(sum);
+    if (lane == 0) {
+        sm_m[w] = m;
+        sm_l[w] = sum;
+    }
+    sm_acc[w][2 * lane] = a0;
+    sm_acc[w][2 * lane + 1] = a1;
+    __syncthreads();
+    if (w == 0) {
+        float M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
+        float L = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const float f = sm_m[x] > -INFINITY ? __expf(sm_m[x] - M) : 0.f;
+            L += sm_l[x] * f;
+            o0 += sm_acc[x][2 * lane] * f;
+            o1 += sm_acc[x][2 * lane + 1] * f;
+        }
+        const float inv = L > 0.f ? 1.0f / L : 0.f;
+        bf16* orow = o + b * oa.bs + static_cast<size_t>(qi) * oa.rs + h * D;
+        reinterpret_cast<bf162*>(orow)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        if (lse != nullptr && lane == 0) lse[(static_cast<size_t>(b) * H + h) * Tq + qi] = M + __logf(L);
+    }
 }
 
 }  // namespace
@@ -421,8 +458,7 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
                   int o_rs, int causal, float scale, cudaStream_t stream, int q_row0) {
     // rows [q_row0, Tq) of every (batch, head)
     if (Tq - q_row0 <= 8 && Tk <= kFewMaxKeys) {
-        const int warps = B * H * (Tq - q_row0);
-        attn_fwd_fewrows_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(
+        attn_fwd_fewrows_kernel<<<B * H * (Tq - q_row0), 128, 0, stream>>>(
             static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
             static_cast<bf16*>(o), lse, B, H, Tq, Tk, Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs},
             Addr{o_bs, o_rs}, causal, scale, q_row0);

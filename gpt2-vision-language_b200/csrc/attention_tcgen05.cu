@@ -522,6 +522,461 @@ attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     dbg_stamp(p.debug, 10);
 }
 
+// ------------------------------------------------------------------------------------------------
+// v4: persistent, warp-specialised pipeline (one CTA per SM).  Work unit = one (batch, head): its K / V tiles are
+// loaded ONCE (double-buffered across units) and shared by all of its 128-row query blocks; two query blocks are in
+// flight at a time, each in its own 256-column TMEM slot with its own 128-thread softmax group, so one block's
+// exp / store phase overlaps the other's MMAs and epilogue and the next unit's TMA loads.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: group 0   warps 8-11: group 1
+// Per-slot TMEM layout as in v2: S fp32 [0,256) -> P bf16x2 in place [0,128); O fp32 [128,192).
+// ------------------------------------------------------------------------------------------------
+constexpr int k4KVStage = 68 * 1024;                       // K 32 KB | Kx 2 KB | V 32 KB | Vx 2 KB
+constexpr int k4OffQ = 2 * k4KVStage;                      // two Q slots of 16 KB
+constexpr int k4OffXchg = k4OffQ + 2 * 16 * 1024;          // per group: extra-key scores/probabilities [16][128] fp32
+constexpr int k4OffTail = k4OffXchg + 2 * 16 * 128 * 4;   // per group: qx[64] | sp[288] | red[8] | part[4][64] floats
+constexpr int k4TailFloats = 64 + 288 + 8 + 256;
+constexpr int k4OffBar = k4OffTail + 2 * k4TailFloats * 4;
+constexpr int k4SmemTotal = k4OffBar + 256 + 1024;
+
+struct Fwd4Params {
+    bf16* o;
+    float* lse;
+    long long o_bs;
+    int o_rs;
+    int B, H, Tq, Tk, n_main, n_extra, causal, nqb;        // nqb: 128-row query blocks handled here per (b,h)
+    float scale_log2e, scale;
+    int debug;
+    // query rows beyond the last full 128-row block (CLIP: the 257th token) are folded into the same kernel: the
+    // group that owns the unit's last tile processes them on the CUDA cores out of the K / V tiles already in
+    // shared memory, in the gap where it would otherwise wait for its P.V product
+    const bf16* q;
+    long long q_bs;
+    int q_rs, tail_rows;
+};
+
+__device__ __forceinline__ void dbg4(int enabled, bool who, int g, uint32_t tile, int slot) {
+    if (enabled && who && blockIdx.x == 0 && tile >= 2 && tile < 6) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_attn_dbg[(g * 4 + (tile - 2)) * 16 + slot] = t;
+    }
+}
+
+// swizzled 128-byte row `j` of the K (or V) tile of a stage: keys < 256 in the main tile, the rest in the 16-row box
+__device__ __forceinline__ const uint8_t* kv_row(const uint8_t* main_tile, int j) {
+    const uint8_t* base = j < 256 ? main_tile : main_tile + 32 * 1024;
+    const int r = j & 255;
+    return base + (r >> 3) * 1024 + (r & 7) * 128;
+}
+
+// One query row against all keys of the unit, by the 128 threads of a softmax group (CUDA cores).
+__device__ __forceinline__ void tail_row(const Fwd4Params& p, const uint8_t* st, float* scr, int g, int b, int h, int qi,
+                                         int gt /* thread index inside the group */) {
+    float* qx = scr;            // [64]   scaled query
+    float* sp = scr + 64;       // [288]  scores -> probabilities
+    float* red = scr + 352;     // [8]
+    float* part = scr + 360;    // [4][64]
+    const int lane = gt & 31, w = gt >> 5;
+    const int lim = p.causal ? min(p.Tk, qi + (p.Tk - p.Tq) + 1) : p.Tk;
+    if (gt < 64) qx[gt] = __bfloat162float(p.q[b * p.q_bs + static_cast<size_t>(qi) * p.q_rs + h * 64 + gt]) * p.scale;
+    ptx::named_bar_sync(1 + g, 128);
+    float m = -INFINITY;
+    for (int j = gt; j < lim; j += 128) {
+        const uint8_t* kr = kv_row(st, j);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float kf[8];
+            unpack8(*reinterpret_cast<const uint4*>(kr + ((c ^ (j & 7)) << 4)), kf);
+            const float4 q0 = *reinterpret_cast<const float4*>(qx + c * 8);
+            const float4 q1 = *reinterpret_cast<const float4*>(qx + c * 8 + 4);
+            acc = fmaf(q0.x, kf[0], acc); acc = fmaf(q0.y, kf[1], acc); acc = fmaf(q0.z, kf[2], acc);
+            acc = fmaf(q0.w, kf[3], acc); acc = fmaf(q1.x, kf[4], acc); acc = fmaf(q1.y, kf[5], acc);
+            acc = fmaf(q1.z, kf[6], acc); acc = fmaf(q1.w, kf[7], acc);
+        }
+        sp[j] = acc;
+        m = fmaxf(m, acc);
+    }
+    m = warp_max(m);
+    if (lane == 0) red[w] = m;
+    ptx::named_bar_sync(1 + g, 128);
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sum = 0.f;
+    for (int j = gt; j < lim; j += 128) {
+        const float e = __expf(sp[j] - m);
+        sp[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[4 + w] = sum;
+    ptx::named_bar_sync(1 + g, 128);
+    sum = red[4] + red[5] + red[6] + red[7];
+    // O[d]: warp w walks keys j = w, w+4, ...; lane owns dims 2*lane, 2*lane+1 (conflict-free swizzled reads)
+    float a0 = 0.f, a1 = 0.f;
+    const uint8_t* vt = st + 34 * 1024;
+    for (int j = w; j < lim; j += 4) {
+        const uint8_t* vr = kv_row(vt, j);
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(vr + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4);
+        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&word));
+        const float pj = sp[j];
+        a0 = fmaf(pj, v2.x, a0);
+        a1 = fmaf(pj, v2.y, a1);
+    }
+    part[w * 64 + 2 * lane] = a0;
+    part[w * 64 + 2 * lane + 1] = a1;
+    ptx::named_bar_sync(1 + g, 128);
+    if (gt < 32) {
+        const float inv = 1.0f / sum;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            o0 += part[x * 64 + 2 * gt];
+            o1 += part[x * 64 + 2 * gt + 1];
+        }
+        bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
+        reinterpret_cast<bf162*>(orow)[gt] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        if (gt == 0 && p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m + __logf(sum);
+    }
+    ptx::named_bar_sync(1 + g, 128);  // scratch may be reused
+}
+
+__global__ void __launch_bounds__(384, 1)
+attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                           const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kx,
+                           const __grid_constant__ CUtensorMap tmap_vx, Fwd4Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k4OffBar);
+    uint64_t* kfull = bars;          // [2] per K/V stage
+    uint64_t* vfull = bars + 2;      // [2]
+    uint64_t* kv_empty = bars + 4;   // [2]  MMA commit + both groups
+    uint64_t* q_full = bars + 6;     // [2] per slot
+    uint64_t* q_empty = bars + 8;    // [2]
+    uint64_t* s_ready = bars + 10;   // [2]
+    uint64_t* p_ready = bars + 12;   // [2]
+    uint64_t* o_ready = bars + 14;   // [2]
+    uint64_t* s_free = bars + 16;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_main = p.n_main, n_extra = p.n_extra, nqb = p.nqb;
+    const int num_units = p.B * p.H;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::prefetch_tensormap(&tmap_v);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&kfull[i], 1);
+            ptx::mbar_init(&vfull[i], 1);
+            ptx::mbar_init(&kv_empty[i], 3);
+            ptx::mbar_init(&q_full[i], 1);
+            ptx::mbar_init(&q_empty[i], 1);
+            ptx::mbar_init(&s_ready[i], 1);
+            ptx::mbar_init(&p_ready[i], 1);
+            ptx::mbar_init(&o_ready[i], 1);
+            ptx::mbar_init(&s_free[i], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t kv_bytes = static_cast<uint32_t>(n_main) * 128u + (n_extra > 0 ? 2048u : 0u);
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            uint32_t qcnt[2] = {0, 0};
+            int it = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+                const int b = u / p.H, h = u % p.H, s = it & 1;
+                uint8_t* st = smem + s * k4KVStage;
+                ptx::mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&kfull[s], kv_bytes);
+                ptx::tma_load_3d(st, &tmap_k, &kfull[s], h * 64, 0, b);
+                if (n_extra > 0) ptx::tma_load_3d(st + 32 * 1024, &tmap_kx, &kfull[s], h * 64, 256, b);
+                ptx::mbar_arrive_expect_tx(&vfull[s], kv_bytes);
+                ptx::tma_load_3d(st + 34 * 1024, &tmap_v, &vfull[s], h * 64, 0, b);
+                if (n_extra > 0) ptx::tma_load_3d(st + 66 * 1024, &tmap_vx, &vfull[s], h * 64, 256, b);
+                for (int qb = 0; qb < nqb; ++qb) {
+                    const int g = qb & 1;
+                    ptx::mbar_wait(&q_empty[g], (qcnt[g] & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&q_full[g], kQBytes);
+                    ptx::tma_load_3d(smem + k4OffQ + g * 16 * 1024, &tmap_q, &q_full[g], h * 64, qb * 128, b);
+                    ++qcnt[g];
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        // Ping-pong schedule over the flat tile sequence t = 0, 1, 2, ... (slot = query block & 1):
+        //     wait softmax(t-1) done  ->  issue S(t)  ->  issue P.V(t-1)
+        // so the exp-heavy (MUFU-bound) phase of tile t never overlaps that of tile t-1; instead it runs under
+        // the P.V product, normalisation and stores of tile t-1 in the other group.
+        if (lane == 0) {
+            uint32_t cnt_s[2] = {0, 0}, cnt_o[2] = {0, 0};
+            const uint32_t idesc_s = ptx::make_idesc_bf16_f32(128, n_main, 0, 0);
+            const uint32_t idesc_o = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+            const int ksteps = n_main / 16;
+            int prev_g = -1, prev_s = 0, prev_last = 0;
+            uint32_t prev_kvpar = 0;
+            auto issue_pv = [&]() {
+                // P.V of the previous tile (its softmax was already waited for)
+                const uint32_t sv = ptx::smem_u32(smem + prev_s * k4KVStage) + 34 * 1024;
+                ptx::mbar_wait(&vfull[prev_s], prev_kvpar);
+                ptx::tc_fence_after_sync();
+                for (int k = 0; k < ksteps; ++k)
+                    ptx::umma_bf16_ts(tmem + prev_g * 256 + 128, tmem + prev_g * 256 + k * 8,
+                                      ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc_o, k != 0);
+                ptx::umma_commit(&o_ready[prev_g]);
+                ++cnt_o[prev_g];
+                if (prev_last) ptx::umma_commit(&kv_empty[prev_s]);  // every MMA of that unit has been issued
+            };
+            int it = 0;
+            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+                const int s = it & 1;
+                const uint32_t kvpar = (it >> 1) & 1;
+                const uint32_t sk = ptx::smem_u32(smem + s * k4KVStage);
+                ptx::mbar_wait(&kfull[s], kvpar);
+                for (int qb = 0; qb < nqb; ++qb) {
+                    const int g = qb & 1;
+                    // only when the previous tile's probabilities are complete may the next tile's scores be produced
+                    // (keeps the two groups' exp phases from overlapping); S(t) goes first because it is on the
+                    // critical path, P.V(t-1) right behind it
+                    const uint32_t par = cnt_s[g] & 1;
+                    bool pv_pending = prev_g >= 0;
+                    if (pv_pending) {
+                        ptx::mbar_wait(&p_ready[prev_g], cnt_o[prev_g] & 1);
+                        // if this tile's inputs are not there yet, do not let the finished tile's P.V queue behind them
+                        if (!(ptx::mbar_try_wait(&q_full[g], par) && ptx::mbar_try_wait(&s_free[g], par ^ 1))) {
+                            issue_pv();
+                            pv_pending = false;
+                        }
+                    }
+                    ptx::mbar_wait(&q_full[g], par);
+                    ptx::mbar_wait(&s_free[g], par ^ 1);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t sq = ptx::smem_u32(smem + k4OffQ + g * 16 * 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_bf16_ss(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                                          ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
+                    ptx::umma_commit(&s_ready[g]);
+                    ++cnt_s[g];
+                    if (pv_pending) issue_pv();
+                    prev_g = g;
+                    prev_s = s;
+                    prev_kvpar = kvpar;
+                    prev_last = (qb == nqb - 1);
+                }
+            }
+            if (prev_g >= 0) {  // drain: the last tile's P.V
+                ptx::mbar_wait(&p_ready[prev_g], cnt_o[prev_g] & 1);
+                issue_pv();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================== softmax / epilogue groups ========================
+        const int g = (warp - 4) >> 2;
+        const int row = ((warp & 3) << 5) + lane;
+        const uint32_t trow = tmem + g * 256 + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        float* spx = reinterpret_cast<float*>(smem + k4OffXchg) + g * 16 * 128;
+        const uint8_t* qrow = smem + k4OffQ + g * 16 * 1024 + (row >> 3) * 1024 + (row & 7) * 128;
+        const bool leader = (threadIdx.x & 127) == 0;
+        uint32_t cnt = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+            const int b = u / p.H, h = u % p.H, s = it & 1;
+            const uint32_t kvpar = (it >> 1) & 1;
+            const uint8_t* st = smem + s * k4KVStage;
+            // never run ahead of the unit (a group without a tile in this unit would otherwise arrive on kv_empty
+            // for a phase that has not started)
+            ptx::mbar_wait(&kfull[s], kvpar);
+            for (int qb = g; qb < nqb; qb += 2, ++cnt) {
+                const uint32_t par = cnt & 1;
+                const int qi = qb * 128 + row;
+                int lim = p.Tk;
+                if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
+                if (lim < 1) lim = 1;
+                float m = -INFINITY;
+                dbg4(p.debug, leader, g, cnt, 0);
+                if (n_extra > 0) {
+                    ptx::mbar_wait(&q_full[g], par);
+                    ptx::mbar_wait(&kfull[s], kvpar);
+#pragma unroll 1
+                    for (int e = 0; e < n_extra; ++e) {
+                        const float sc = (256 + e < lim) ? dot_q_kx(qrow, row & 7, st + 32 * 1024, e) : -INFINITY;
+                        spx[e * 128 + row] = sc;
+                        m = fmaxf(m, sc);
+                    }
+                }
+                dbg4(p.debug, leader, g, cnt, 1);
+                ptx::mbar_wait(&s_ready[g], par);
+                ptx::tc_fence_after_sync();
+                dbg4(p.debug, leader, g, cnt, 2);
+                const int full = min(__reduce_min_sync(0xffffffffu, lim), n_main) & ~31;
+                // software-pipelined TMEM reads: the next 32 columns are in flight while these are reduced
+                if (full > 0) {
+                    uint32_t ra[32], rb[32];
+                    ptx::tmem_ld_32x32b_x32(trow, ra);
+                    ptx::tmem_ld_wait();
+                    for (int c = 0; c < full; c += 64) {
+                        const bool more1 = c + 32 < full, more2 = c + 64 < full;
+                        if (more1) ptx::tmem_ld_32x32b_x32(trow + c + 32, rb);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(ra[i]));
+                        if (more1) {
+                            ptx::tmem_ld_wait();
+                            if (more2) ptx::tmem_ld_32x32b_x32(trow + c + 64, ra);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rb[i]));
+                            if (more2) ptx::tmem_ld_wait();
+                        }
+                    }
+                }
+                for (int c = full; c < n_main; c += 16) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x32b_x16(trow + c, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
+                }
+                const float mb = m * p.scale_log2e;
+                float sum = 0.f;
+                dbg4(p.debug, leader, g, cnt, 3);
+                if (full > 0) {
+                    uint32_t ra[32], rb[32];
+                    auto exp_store = [&](const uint32_t (&r)[32], int c) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float e0 = ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
+                            const float e1 = ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
+                            sum += e0 + e1;
+                            const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+                            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        }
+                        // P columns [c/2, c/2+16) overwrite score columns this thread has already consumed
+                        ptx::tmem_st_32x32b_x16(trow + (c >> 1), pk);
+                    };
+                    ptx::tmem_ld_32x32b_x32(trow, ra);
+                    ptx::tmem_ld_wait();
+                    for (int c = 0; c < full; c += 64) {
+                        const bool more1 = c + 32 < full, more2 = c + 64 < full;
+                        if (more1) ptx::tmem_ld_32x32b_x32(trow + c + 32, rb);
+                        exp_store(ra, c);
+                        if (more1) {
+                            ptx::tmem_ld_wait();
+                            if (more2) ptx::tmem_ld_32x32b_x32(trow + c + 64, ra);
+                            exp_store(rb, c + 32);
+                            if (more2) ptx::tmem_ld_wait();
+                        }
+                    }
+                }
+                for (int c = full; c < n_main; c += 16) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x32b_x16(trow + c, r);
+                    ptx::tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float e0 =
+                            (c + 2 * i < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb)) : 0.f;
+                        const float e1 = (c + 2 * i + 1 < lim)
+                                             ? ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb))
+                                             : 0.f;
+                        sum += e0 + e1;
+                        const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+                        pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                    ptx::tmem_st_32x32b_x8(trow + (c >> 1), pk);
+                }
+#pragma unroll 1
+                for (int e = 0; e < n_extra; ++e) {
+                    const float pe = (256 + e < lim) ? ex2_fast(fmaf(spx[e * 128 + row], p.scale_log2e, -mb)) : 0.f;
+                    sum += pe;
+                    spx[e * 128 + row] = pe;
+                }
+                dbg4(p.debug, leader, g, cnt, 4);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before_sync();
+                ptx::named_bar_sync(1 + g, 128);
+                if (leader) {
+                    ptx::mbar_arrive(&p_ready[g]);   // P complete -> MMA warp may issue P.V
+                    ptx::mbar_arrive(&q_empty[g]);   // this slot's Q tile is no longer needed (S done, dots done)
+                }
+                dbg4(p.debug, leader, g, cnt, 5);
+                if (p.tail_rows > 0 && qb == nqb - 1) {
+                    // leftover query rows of this (batch, head), while the tensor core works on this tile's P.V
+                    ptx::mbar_wait(&vfull[s], kvpar);
+                    float* scr = reinterpret_cast<float*>(smem + k4OffTail) + g * k4TailFloats;
+                    for (int tr = 0; tr < p.tail_rows; ++tr)
+                        tail_row(p, st, scr, g, b, h, nqb * 128 + tr, threadIdx.x & 127);
+                }
+                ptx::mbar_wait(&o_ready[g], par);
+                if (n_extra > 0) ptx::mbar_wait(&vfull[s], kvpar);
+                ptx::tc_fence_after_sync();
+                dbg4(p.debug, leader, g, cnt, 6);
+                const float inv = 1.0f / sum;
+                bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
+#pragma unroll
+                for (int c = 0; c < 64; c += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(trow + 128 + c, r);
+                    ptx::tmem_ld_wait();
+                    float t[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(r[i]);
+#pragma unroll 1
+                    for (int e = 0; e < n_extra; ++e) {
+                        const uint8_t* vrow = st + 66 * 1024 + (e >> 3) * 1024 + (e & 7) * 128;
+                        const float pe = spx[e * 128 + row];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float v8[8];
+                            unpack8(*reinterpret_cast<const uint4*>(vrow + ((((c >> 3) + q) ^ (e & 7)) << 4)), v8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t[q * 8 + i] = fmaf(pe, v8[i], t[q * 8 + i]);
+                        }
+                    }
+                    if (qi < p.Tq) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float o8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o8[i] = t[q * 8 + i] * inv;
+                            stg16(orow + c + q * 8, pack8(o8));
+                        }
+                    }
+                }
+                if (qi < p.Tq && p.lse != nullptr)
+                    p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
+                dbg4(p.debug, leader, g, cnt, 7);
+                ptx::tc_fence_before_sync();
+                ptx::named_bar_sync(1 + g, 128);
+                if (leader) ptx::mbar_arrive(&s_free[g]);  // TMEM slot (and spx) may be reused
+                dbg4(p.debug, leader, g, cnt, 8);
+            }
+            // this group is done with the unit's K/V stage (Kx / Vx reads included); also when it had no tile
+            ptx::named_bar_sync(1 + g, 128);
+            if (leader) ptx::mbar_arrive(&kv_empty[s]);
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem, 512);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -592,7 +1047,7 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     // full 128-row query blocks on the tensor cores; a short tail (e.g. the 257th CLIP token) on the CUDA cores
     int tail = Tq % 128;
     int tc_rows = Tq - tail;
-    if (tail > 32) {
+    if (tail > 8) {  // a longer remainder gets its own (partly empty) 128-row block
         tc_rows = Tq;
         tail = 0;
     }
@@ -616,7 +1071,7 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
         p2.causal = causal;
         p2.scale = scale;
         p2.scale_log2e = scale * 1.4426950408889634f;
-        p2.debug = getenv("VLK_ATTN_DEBUG") != nullptr;
+        p2.debug = getenv("VLK_ATTN_DEBUG") != nullptr ? atoi(getenv("VLK_ATTN_DEBUG")) : 0;
         CUtensorMap tq, tk, tv, tkx, tvx;
         int rc = make_tmap3(&tq, q, H * 64, Tq, B, q_rs, q_bs, 128);
         if (rc) return rc;
@@ -628,9 +1083,45 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
         if (rc) return rc;
         rc = make_tmap3(&tvx, v, H * 64, Tk, B, v_rs, v_bs, 16);
         if (rc) return rc;
-        const dim3 grid2((tc_rows + 127) / 128, H, B);
-        attn_fwd_tcgen05_v2_kernel<<<grid2, 256, k2SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p2);
-        VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v2)");
+        if (!(force && strcmp(force, "tcgen05v3") == 0)) {
+            // persistent pipeline: one CTA per SM walks the (batch, head) units
+            static bool configured4 = false;
+            if (!configured4) {
+                VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              k4SmemTotal));
+                configured4 = true;
+            }
+            Fwd4Params p4;
+            p4.o = p2.o;
+            p4.lse = p2.lse;
+            p4.o_bs = o_bs;
+            p4.o_rs = o_rs;
+            p4.B = B;
+            p4.H = H;
+            p4.Tq = Tq;
+            p4.Tk = Tk;
+            p4.n_main = p2.n_main;
+            p4.n_extra = p2.n_extra;
+            p4.causal = causal;
+            p4.nqb = (tc_rows + 127) / 128;
+            p4.scale = scale;
+            p4.scale_log2e = p2.scale_log2e;
+            p4.debug = p2.debug;
+            p4.q = static_cast<const bf16*>(q);
+            p4.q_bs = q_bs;
+            p4.q_rs = q_rs;
+            p4.tail_rows = tail;   // folded into the persistent kernel
+            tail = 0;
+            const int sms = device_sm_count();
+            VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
+            const int units = B * H;
+            attn_fwd_tcgen05_v4_kernel<<<units < sms ? units : sms, 384, k4SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p4);
+            VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v4)");
+        } else {
+            const dim3 grid2((tc_rows + 127) / 128, H, B);
+            attn_fwd_tcgen05_v2_kernel<<<grid2, 256, k2SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p2);
+            VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v3)");
+        }
         if (tail > 0)
             return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                                  scale, s, tc_rows);
