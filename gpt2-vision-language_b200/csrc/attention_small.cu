@@ -45,9 +45,9 @@ __device__ __forceinline__ void load_tr(float* __restrict__ dst, const bf16* __r
 
 // acc[i][j] += sum_k At[k][4*ty + i] * Bt[k][4*tx + j]   (both operands stored contraction-major)
 __device__ __forceinline__ void mm_tt(const float* __restrict__ At, const float* __restrict__ Bt, int ty, int tx,
-                                      int kmax, float (&acc)[4][4]) {
+                                      int kmax, float (&acc)[4][4], int kmin = 0) {
 #pragma unroll 8
-    for (int k = 0; k < kmax; ++k) {
+    for (int k = kmin; k < kmax; ++k) {
         const float4 a = *reinterpret_cast<const float4*>(At + k * T + 4 * ty);
         const float4 b = *reinterpret_cast<const float4*>(Bt + k * T + 4 * tx);
         const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -109,10 +109,11 @@ attn_small_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
     load_tr(Kt, k + b * ka.bs + h * D, ka.rs, Tk, 1.f);
     load_nat(Vn, v + b * va.bs + h * D, va.rs, Tk, 1.f);
     __syncthreads();
+    const int shift = Tk - Tq;
     float s[4][4];
     zero(s);
-    mm_tt(Qt, Kt, ty, tx, D, s);
-    const int shift = Tk - Tq;
+    // causal: a 4x4 tile whose first key lies beyond its last query's horizon is entirely masked
+    if (!(causal && 4 * tx > 4 * ty + 3 + shift)) mm_tt(Qt, Kt, ty, tx, D, s);
     float rinv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -150,7 +151,8 @@ attn_small_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
     __syncthreads();
     float acc[4][4];
     zero(acc);
-    mm_tt(Pt, Vn, ty, tx, Tk, acc);   // O[i][d] = sum_j Pt[j][i] * V[j][d]
+    // O[i][d] = sum_j Pt[j][i] * V[j][d]; under a causal mask rows 4ty..4ty+3 see keys < 4ty+4+shift only
+    mm_tt(Pt, Vn, ty, tx, causal ? min(Tk, 4 * ty + 4 + shift) : Tk, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -214,12 +216,14 @@ attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
         }
     }
     __syncthreads();
+    const int shift = Tk - Tq;
     float s[4][4], dp[4][4];
     zero(s);
     zero(dp);
-    mm_tt(A0, A1, ty, tx, D, s);    // S[i][j] (already scaled)
-    mm_tt(A2, A3, ty, tx, D, dp);   // dP[i][j] = dO_i . V_j
-    const int shift = Tk - Tq;
+    if (!(causal && 4 * tx > 4 * ty + 3 + shift)) {  // skip tiles that are entirely masked
+        mm_tt(A0, A1, ty, tx, D, s);    // S[i][j] (already scaled)
+        mm_tt(A2, A3, ty, tx, D, dp);   // dP[i][j] = dO_i . V_j
+    }
     DropoutKey dkey;
     if (dropout_p > 0.f) dkey = make_dropout_key(seed_state, stream_id, dropout_p);
 #pragma unroll
@@ -250,17 +254,20 @@ attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
             make_float4(dp[0][j], dp[1][j], dp[2][j], dp[3][j]);
     __syncthreads();
     float acc[4][4];
+    // causal: key rows 4ty..4ty+3 are seen by queries i >= 4ty - shift only; query rows 4ty.. see keys < 4ty+4+shift
+    const int i_min = causal ? max(0, 4 * ty - shift) : 0;
+    const int j_max = causal ? min(Tk, 4 * ty + 4 + shift) : Tk;
     // dV[j][d] = sum_i P[i][j] dO[i][d]
     zero(acc);
-    mm_tt(A0, dOn, ty, tx, Tq, acc);
+    mm_tt(A0, dOn, ty, tx, Tq, acc, i_min);
     store_rows_bf16(dv + b * dva.bs + h * D, dva.rs, acc, ty, tx, Tk, 1.f);
     // dK[j][d] = scale * sum_i dS[i][j] Q[i][d]
     zero(acc);
-    mm_tt(A1, Qn, ty, tx, Tq, acc);
+    mm_tt(A1, Qn, ty, tx, Tq, acc, i_min);
     store_rows_bf16(dk + b * dka.bs + h * D, dka.rs, acc, ty, tx, Tk, scale);
     // dQ[i][d] = scale * sum_j dSt[j][i] K[j][d]
     zero(acc);
-    mm_tt(A2, Kn, ty, tx, Tk, acc);
+    mm_tt(A2, Kn, ty, tx, j_max, acc);
     store_rows_bf16(dq + b * dqa.bs + h * D, dqa.rs, acc, ty, tx, Tq, scale);
 }
 
