@@ -34,7 +34,8 @@ def _worker(rank, world, port, out):
     mod(x).square().mean().backward()             # autograd accumulates into the flat views
     local = bucket.flat.clone()
     bucket.all_reduce()
-    out.put((rank, lin.weight.detach().clone(), local, bucket.flat.clone(), lin.weight.grad.clone()))
+    # numpy arrays are pickled by value: torch tensors would travel as shared-memory handles that die with the worker
+    out.put((rank,) + tuple(t.detach().clone().numpy() for t in (lin.weight, local, bucket.flat, lin.weight.grad)))
     dist.destroy_process_group()
 
 
@@ -49,7 +50,7 @@ def test_flat_bucket_allreduce_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, w0, l0, a0, g0), (_, w1, l1, a1, g1) = res
+    (_, w0, l0, a0, g0), (_, w1, l1, a1, g1) = [(r[0],) + tuple(torch.from_numpy(a) for a in r[1:]) for r in res]
     assert torch.equal(w0, w1)                                   # broadcast made the replicas identical
     assert not torch.allclose(l0, l1)                            # different data -> different local grads
     assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-6)          # AVG, like DDP
