@@ -57,7 +57,7 @@ def summarize_clocks(samples):
 
 def synthetic_host_batch(B, seed, torch, pin):
     """Random 224x224 images and a 5-caption pool per image, one caption drawn per step (data.py:53 semantics)."""
-    from oracle.torch_oracle import synthetic_caption_batch
+    from gpt2_vision_language_b200.data import synthetic_caption_batch
     g = torch.Generator().manual_seed(seed)
     pixels = torch.randn(B, 3, 224, 224, generator=g)
     x, y, m, _ = synthetic_caption_batch(B, seed=seed + 1)

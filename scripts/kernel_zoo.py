@@ -1,0 +1,192 @@
+"""Every kernel class of the path at the shapes the bench workloads use, timed alone with CUDA events.
+
+Memory-bound kernels rotate over enough independent buffers that each launch reads cold data (working set per
+rotation > the 126 MB L2); the table reports algorithmic bytes / time against MEASURED_PEAKS.json
+(burst figures: kernels timed alone).  `--once` launches each kernel exactly once after one warm-up launch — the
+mode used under `ncu --set full` (profiles/r01_ncu_kernels.*).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gpt2_vision_language_b200 import ops, optim  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--once", action="store_true")
+ap.add_argument("--only", default="")
+args = ap.parse_args()
+
+peaks = {"hbm_gbs": 6451.2, "bf16_tflops": 1671.5}
+try:
+    peaks.update(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))))
+except Exception:
+    pass
+
+dev = "cuda"
+BF = torch.bfloat16
+rows_out = []
+
+
+def bench(name, make, fn, nbytes=None, flops=None, copies=None):
+    """make(i) -> state for copy i; fn(state) launches the kernel(s)."""
+    if args.only and args.only not in name:
+        return
+    if copies is None:
+        copies = 1 if nbytes is None else max(2, min(16, int(400e6 // max(nbytes, 1)) + 1))
+    states = [make(i) for i in range(copies)]
+    fn(states[0])
+    torch.cuda.synchronize()
+    if args.once:
+        torch.cuda.nvtx.range_push(name)
+        fn(states[-1])
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.synchronize()
+        return
+    iters = max(copies * 3, 12)
+    for i in range(copies):
+        fn(states[i])
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(states[i % copies])
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / iters * 1e3
+    line = f"{name:58s} {us:9.1f} us"
+    rec = {"kernel": name, "us": us}
+    if nbytes is not None:
+        gbs = nbytes / us / 1e3
+        line += f"  {nbytes/1e6:8.1f} MB  {gbs:7.0f} GB/s  {gbs/peaks['hbm_gbs']:.2f} of HBM copy peak"
+        rec.update(bytes=nbytes, gbs=gbs, frac_hbm=gbs / peaks["hbm_gbs"])
+    if flops is not None:
+        tf = flops / us / 1e6
+        line += f"  {tf:7.0f} TFLOP/s  {tf/peaks['bf16_tflops']:.2f} of bf16 burst peak"
+        rec.update(flops=flops, tflops=tf, frac_tensor=tf / peaks["bf16_tflops"])
+    print(line, flush=True)
+    rows_out.append(rec)
+    del states
+    torch.cuda.empty_cache()
+
+
+torch.manual_seed(0)
+
+# ---------------------------------------------------------------- LayerNorm (CLIP rows x 1024, GPT rows x 768)
+for rows, C, tag in ((64 * 257, 1024, "CLIP B=64"), (64 * 64, 768, "GPT-2 caption B=64,T=64"), (16 * 1024, 768, "pretrain 16x1024")):
+    def mk(i, rows=rows, C=C):
+        return (torch.randn(rows, C, device=dev).to(BF), torch.randn(C, device=dev).to(BF), torch.randn(C, device=dev).to(BF))
+    bench(f"layernorm_fwd {tag} [{rows}x{C}]", mk, lambda s: ops.layernorm_fwd(s[0], s[1], s[2], 1e-5, save_stats=True),
+          nbytes=rows * C * 2 * 2)
+
+    def mkb(i, rows=rows, C=C):
+        x = torch.randn(rows, C, device=dev).to(BF)
+        w = torch.randn(C, device=dev).to(BF)
+        _, mean, rstd = ops.layernorm_fwd(x, w, w, 1e-5)
+        return (torch.randn(rows, C, device=dev).to(BF), x, w, mean, rstd, torch.empty_like(x))
+    bench(f"layernorm_bwd dx only {tag}", mkb, lambda s: ops.layernorm_bwd(s[0], s[1], s[2], s[3], s[4], dx=s[5]),
+          nbytes=rows * C * 2 * 3)
+    if "pretrain" in tag:
+        bench(f"layernorm_bwd dx+dgamma+dbeta {tag}", mkb,
+              lambda s: ops.layernorm_bwd(s[0], s[1], s[2], s[3], s[4], param_grads=True, dx=s[5]), nbytes=rows * C * 2 * 3)
+
+# ---------------------------------------------------------------- pool 257 -> 33 + L2 normalise
+bench("pool33_l2norm B=64 D=768 (bf16)", lambda i: torch.randn(64, 257, 768, device=dev).to(BF), lambda s: ops.pool33(s),
+      nbytes=64 * (257 + 33) * 768 * 2)
+bench("pool33_l2norm B=1024 D=768 (bf16)", lambda i: torch.randn(1024, 257, 768, device=dev).to(BF), lambda s: ops.pool33(s),
+      nbytes=1024 * (257 + 33) * 768 * 2, copies=2)
+
+# ---------------------------------------------------------------- embedding + concat
+wte = torch.randn(50304, 768, device=dev).to(BF)
+wpe = torch.randn(1024, 768, device=dev).to(BF)
+bench("embed_concat caption B=64 P=33 T=31", lambda i: (torch.randint(0, 50257, (64, 31), device=dev), torch.randn(64, 33, 768, device=dev).to(BF)),
+      lambda s: ops.embed_concat(s[0], wte, wpe, s[1]), nbytes=64 * (31 * 3 + 33 * 2) * 768 * 2)
+bench("embed pretrain B=16 T=1024", lambda i: torch.randint(0, 50257, (16, 1024), device=dev),
+      lambda s: ops.embed_concat(s, wte, wpe, None), nbytes=16 * 1024 * 768 * 2 * 3)
+
+# ---------------------------------------------------------------- softmax-CE over a logits chunk (in place)
+lib = ops._lib.load()
+for rows, tag in ((512, "caption chunk"), (4096, "pretrain chunk")):
+    V = 50304
+
+    def mkce(i, rows=rows):
+        return (torch.randn(rows, V, device=dev).to(BF), torch.randint(0, 50257, (rows,), device=dev),
+                torch.empty(rows, device=dev), torch.ones(1, device=dev))
+
+    def runce(s, rows=rows):
+        ops.check(lib.vlk_softmax_ce_rows(s[0].data_ptr(), s[1].data_ptr(), 0, s[2].data_ptr(), s[3].data_ptr(), rows, V,
+                                          V, 1, torch.cuda.current_stream().cuda_stream), "ce")
+    bench(f"softmax_ce_rows {tag} [{rows}x{V}] (cold logits)", mkce, runce, nbytes=rows * V * 2 * 2)
+
+# ---------------------------------------------------------------- clip-norm + AdamW
+for numel, tag in ((590592, "linear bridge"), (19521792, "Q-Former bridge"), (124475904, "GPT-2 124M")):
+    def mkopt(i, numel=numel):
+        p = torch.nn.Parameter(torch.randn(numel, device=dev).to(BF))
+        p.grad = torch.randn(numel, device=dev).to(BF)
+        o = optim.FusedAdamW([p], lr=1e-3, weight_decay=0.1)
+        o.clip_grad_norm(1.0)
+        o.step()
+        return o
+    copies = 2 if numel > 1e8 else (4 if numel > 1e7 else 16)
+    bench(f"grad_sumsq {tag} ({numel} params)", mkopt, lambda o: o.clip_grad_norm(1.0), nbytes=numel * 2, copies=copies)
+
+    def runstep(o):
+        o._pending_max_norm = 1.0
+        o.step()
+    bench(f"adamw {tag} ({numel} params)", mkopt, runstep, nbytes=numel * 14, copies=copies)
+
+# ---------------------------------------------------------------- attention
+def attn_case(name, B, H, Tq, causal, bwd, copies=2):
+    C = H * 64
+    fl = 4.0 * B * H * Tq * Tq * 64 * (0.5 if causal else 1.0)
+
+    def mk(i):
+        qkv = (torch.randn(B, Tq, 3 * C, device=dev) * 0.5).to(BF)
+        o, lse = ops.attention_fwd(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], H, causal)
+        return qkv, o, lse, torch.randn_like(o), torch.empty_like(qkv)
+    bench(f"attention fwd {name}", mk,
+          lambda s: ops.attention_fwd(s[0][..., :C], s[0][..., C:2 * C], s[0][..., 2 * C:], H, causal, need_lse=bwd),
+          flops=fl, copies=copies)
+    if bwd:
+        bench(f"attention bwd {name}", mk,
+              lambda s: ops.attention_bwd(s[0][..., :C], s[0][..., C:2 * C], s[0][..., 2 * C:], s[1], s[3], s[2],
+                                          s[4][..., :C], s[4][..., C:2 * C], s[4][..., 2 * C:], H, causal),
+              flops=2.5 * fl, copies=copies)
+
+
+attn_case("CLIP B=64 H=16 T=257", 64, 16, 257, False, False)
+attn_case("GPT-2 caption B=64 H=12 T=64 causal", 64, 12, 64, True, True)
+attn_case("pretrain B=16 H=12 T=1024 causal", 16, 12, 1024, True, True)
+
+# ---------------------------------------------------------------- GEMMs of the step
+def gemm_case(name, M, N, K, **kw):
+    def mk(i):
+        a = torch.randn(M, K, device=dev).to(BF)
+        b = torch.randn(N, K, device=dev).to(BF)
+        bias = torch.randn(N, device=dev).to(BF)
+        res = torch.randn(M, N, device=dev).to(BF)
+        return a, b, bias, res, torch.empty(M, N, device=dev, dtype=BF)
+
+    def run(s):
+        k2 = dict(kw)
+        if k2.pop("use_bias", False):
+            k2["bias"] = s[2]
+        if k2.pop("use_res", False):
+            k2["residual"] = s[3]
+        ops.gemm(s[0], s[1], out=s[4], **k2)
+    bench(f"gemm {name} M={M} N={N} K={K}", mk, run, flops=2.0 * M * N * K, copies=2)
+
+
+gemm_case("CLIP qkv (bias)", 16448, 3072, 1024, use_bias=True)
+gemm_case("CLIP out_proj (bias+residual)", 16448, 1024, 1024, use_bias=True, use_res=True)
+gemm_case("CLIP fc1 (bias+quick_gelu)", 16448, 4096, 1024, use_bias=True, act="quick_gelu")
+gemm_case("CLIP fc2 (bias+residual)", 16448, 1024, 4096, use_bias=True, use_res=True)
+gemm_case("GPT-2 c_fc pretrain (bias+gelu)", 16384, 3072, 768, use_bias=True, act="gelu_tanh")
+gemm_case("GPT-2 lm_head chunk", 4096, 50304, 768)
+gemm_case("plain 8192^3", 8192, 8192, 8192)
+
+if not args.once:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump({"peaks": peaks, "kernels": rows_out}, open("gpurun_out/kernel_zoo.json", "w"), indent=1)

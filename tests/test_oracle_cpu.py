@@ -119,3 +119,20 @@ def test_oracle_against_live_reference_full_width():
     lo, ls = O.caption_linear_forward(sd, z, x, labels, 2, 12)
     close(lo, logits.detach())
     assert abs(ls.item() - loss.item()) < 1e-5
+
+
+def test_host_caption_encoding_matches_oracle_and_reference_rule():
+    """gpt2_vision_language_b200.data (host input formatting) vs the oracle's generator and the reference rule
+    (source/gpt2_linear/data.py:35-49): empty caption, short caption, caption longer than max_len."""
+    from gpt2_vision_language_b200 import data
+    a = data.synthetic_caption_batch(16, seed=3)
+    b = O.synthetic_caption_batch(16, seed=3)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    x, y, m = data.encode_caption_ids([], max_len=8)
+    assert x.tolist() == [data.EOT] * 7 and y.tolist() == [data.EOT] * 7 and m.tolist() == [True] + [False] * 6
+    x, y, m = data.encode_caption_ids([5, 6, 7], max_len=8)
+    assert x.tolist() == [5, 6, 7] + [data.EOT] * 4 and y.tolist() == [6, 7] + [data.EOT] * 5
+    assert m.tolist() == [True] * 3 + [False] * 4
+    x, y, m = data.encode_caption_ids(list(range(100, 120)), max_len=8)
+    assert x.tolist() == list(range(100, 107)) and y.tolist() == list(range(101, 107)) + [data.EOT] and m.all()
