@@ -37,15 +37,16 @@ def bench(name, make, fn, nbytes=None, flops=None, copies=None):
         return
     if copies is None:
         copies = 1 if nbytes is None else max(2, min(16, int(400e6 // max(nbytes, 1)) + 1))
+    if args.once:
+        st = make(0)
+        torch.cuda.synchronize()
+        print("once:", name, flush=True)
+        fn(st)
+        torch.cuda.synchronize()
+        return
     states = [make(i) for i in range(copies)]
     fn(states[0])
     torch.cuda.synchronize()
-    if args.once:
-        torch.cuda.nvtx.range_push(name)
-        fn(states[-1])
-        torch.cuda.nvtx.range_pop()
-        torch.cuda.synchronize()
-        return
     iters = max(copies * 3, 12)
     for i in range(copies):
         fn(states[i])
