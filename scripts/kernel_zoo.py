@@ -50,13 +50,28 @@ def bench(name, make, fn, nbytes=None, flops=None, copies=None):
     iters = max(copies * 3, 12)
     for i in range(copies):
         fn(states[i])
+    torch.cuda.synchronize()
+    # one CUDA graph of `iters` launches: no host launch overhead between kernels (small kernels would otherwise
+    # be timed at the speed of the Python/ctypes call path)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn(states[0])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(states[i % copies])
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for i in range(iters):
-        fn(states[i % copies])
+    for _ in range(3):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    us = s.elapsed_time(e) / iters * 1e3
+    us = s.elapsed_time(e) / (3 * iters) * 1e3
+    del g
     line = f"{name:58s} {us:9.1f} us"
     rec = {"kernel": name, "us": us}
     if nbytes is not None:
@@ -187,6 +202,18 @@ gemm_case("CLIP fc2 (bias+residual)", 16448, 1024, 4096, use_bias=True, use_res=
 gemm_case("GPT-2 c_fc pretrain (bias+gelu)", 16384, 3072, 768, use_bias=True, act="gelu_tanh")
 gemm_case("GPT-2 lm_head chunk", 4096, 50304, 768)
 gemm_case("plain 8192^3", 8192, 8192, 8192)
+# the GPT-2 GEMMs of the caption step (M = 64 x 64 rows)
+gemm_case("GPT-2 c_attn caption (bias)", 4096, 2304, 768, use_bias=True)
+gemm_case("GPT-2 attn c_proj caption (bias+residual)", 4096, 768, 768, use_bias=True, use_res=True)
+gemm_case("GPT-2 c_fc caption (bias+gelu)", 4096, 3072, 768, use_bias=True, act="gelu_tanh")
+gemm_case("GPT-2 mlp c_proj caption (bias+residual)", 4096, 768, 3072, use_bias=True, use_res=True)
+for bn, cl in ((256, 1), (128, 1), (128, 3), (64, 1)):
+    os.environ["VLK_GEMM_BN"], os.environ["VLK_GEMM_CLUSTER"] = str(bn), str(cl)
+    gemm_case(f"[bn={bn} cluster={cl}] c_attn", 4096, 2304, 768, use_bias=True)
+    gemm_case(f"[bn={bn} cluster={cl}] attn c_proj", 4096, 768, 768, use_bias=True, use_res=True)
+    gemm_case(f"[bn={bn} cluster={cl}] c_fc", 4096, 3072, 768, use_bias=True, act="gelu_tanh")
+    gemm_case(f"[bn={bn} cluster={cl}] mlp c_proj", 4096, 768, 3072, use_bias=True, use_res=True)
+os.environ.pop("VLK_GEMM_BN"); os.environ.pop("VLK_GEMM_CLUSTER")
 
 if not args.once:
     os.makedirs("gpurun_out", exist_ok=True)
