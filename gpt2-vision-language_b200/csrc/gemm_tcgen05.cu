@@ -38,7 +38,9 @@ struct EpiParams {
     int ldd, ldr, ld_aux;
     int act, dact, out_fp32;
     float alpha;
-    int split_k;  // > 1: the K range is cut into split_k slices, partial tiles are atomically added into fp32 D
+    int split_k;  // > 1: the K range is cut into split_k slices; each slice's partial tile goes to fp32 D either
+                  // atomically (split_stride == 0, D zeroed by the caller) or into its own slab s * split_stride
+    long long split_stride;
     int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 };
 
@@ -56,7 +58,7 @@ struct SmemLayout {
 
 // Apply the epilogue to 32 consecutive accumulator columns of one row and store them.
 __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint32_t (&acc)[32], int row, int col0,
-                                                 int ncols_valid) {
+                                                 int ncols_valid, size_t d_off) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * ep.alpha;
@@ -117,8 +119,8 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
         }
     }
     if (ep.out_fp32) {
-        float* p = reinterpret_cast<float*>(ep.D) + static_cast<size_t>(row) * ep.ldd + col0;
-        if (ep.split_k > 1) {  // split-K partial: D was zeroed by the caller
+        float* p = reinterpret_cast<float*>(ep.D) + d_off + static_cast<size_t>(row) * ep.ldd + col0;
+        if (ep.split_k > 1 && ep.split_stride == 0) {  // atomic split-K partial: D was zeroed by the caller
 #pragma unroll
             for (int c = 0; c < 32; ++c)
                 if (c < ncols_valid) atomicAdd(p + c, v[c]);
@@ -209,7 +211,8 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint4 (&p
 // One warp, its 32 accumulator rows (TMEM lanes), `ncols_warp` columns starting at global column n0.
 // stage = [input tile 4 KB | output tile 4 KB].
 __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint4 (&pre)[8], uint32_t taddr,
-                                              int row0, int n0, int ncols_warp, int M, int N, int lane) {
+                                              int row0, int n0, int ncols_warp, int M, int N, int lane,
+                                              size_t d_off = 0) {
     const int row = row0 + lane;
     if (ep.debug & 1) return;
     if (ep.out_fp32 || ncols_warp < 64) {
@@ -221,7 +224,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(taddr + c, r);
             ptx::tmem_ld_wait();
-            if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0));
+            if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0), d_off);
         }
         return;
     }
@@ -512,7 +515,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
-                          kColsPerWarp, M, N, lane);
+                          kColsPerWarp, M, N, lane, static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -698,7 +701,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
-                          kColsPerWarp, M, N, lane);
+                          kColsPerWarp, M, N, lane, static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // the leader's barrier
@@ -710,6 +713,30 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp_idx == 2) {
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    }
+}
+
+// Split-K second pass: out[r][c] = (accumulate ? out[r][c] : 0) + sum_s ws[s][r][c], rounded to bf16 once.
+// The slabs were just written by the GEMM and are L2-resident (a few MB); 8 columns per thread.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long slab, bf16* __restrict__ out, int M, int N,
+                     int ldd, int accumulate) {
+    const int n8 = N >> 3;
+    const long long total = static_cast<long long>(M) * n8;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / n8), c = static_cast<int>(i - static_cast<long long>(r) * n8) * 8;
+        const float* src = ws + static_cast<size_t>(r) * N + c;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bf16* dst = out + static_cast<size_t>(r) * ldd + c;
+        if (accumulate) unpack8(*reinterpret_cast<const uint4*>(dst), acc);
+        for (int s = 0; s < splits; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(src + s * slab);
+            const float4 b = *reinterpret_cast<const float4*>(src + s * slab + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        stg16(dst, pack8(acc));
     }
 }
 
@@ -863,10 +890,10 @@ int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, 
 
 using namespace vlk;
 
-extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
-                             int transA, int transB, const void* bias, const void* residual, int ldr,
-                             const void* aux_in, void* aux_out, int ld_aux, const float* scale, int act, int dact,
-                             float alpha, int out_fp32, int split_k, void* stream) {
+static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                     int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
+                     void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
+                     int split_k, long long split_stride, int* split_used, void* stream) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -913,6 +940,8 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     ep.out_fp32 = out_fp32;
     ep.alpha = alpha;
     ep.split_k = split_k;
+    ep.split_stride = split_k > 1 ? split_stride : 0;
+    if (split_used) *split_used = split_k;
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
 
@@ -950,4 +979,35 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
     if (!transA && transB) return dispatch<false, true>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
     if (transA && !transB) return dispatch<true, false>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
     return dispatch<true, true>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
+}
+
+extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                             int transA, int transB, const void* bias, const void* residual, int ldr,
+                             const void* aux_in, void* aux_out, int ld_aux, const float* scale, int act, int dact,
+                             float alpha, int out_fp32, int split_k, void* stream) {
+    return gemm_impl(A, B, D, M, N, K, lda, ldb, ldd, transA, transB, bias, residual, ldr, aux_in, aux_out, ld_aux, scale,
+                     act, dact, alpha, out_fp32, split_k, 0, nullptr, stream);
+}
+
+extern "C" int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float* workspace, int M, int N, int K,
+                                    int lda, int ldb, int ldd, int transA, int transB, float alpha, int split_k,
+                                    int accumulate, void* stream) {
+    VLK_REQUIRE(workspace != nullptr && aligned16(workspace), VLK_ERR_INVALID_ARG,
+                "vlk_gemm_bf16_splitk: needs a 16B-aligned fp32 workspace of split_k * M * N elements");
+    VLK_REQUIRE(split_k >= 1 && split_k <= 64, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16_splitk: split_k=%d", split_k);
+    VLK_REQUIRE(D && aligned16(D) && ldd % 8 == 0, VLK_ERR_ALIGNMENT, "vlk_gemm_bf16_splitk: D");
+    int used = 1;
+    const long long slab = static_cast<long long>(M) * N;
+    // slab mode needs split_k >= 2 inside gemm_impl; a single slice is just an fp32 GEMM into slab 0
+    int rc = gemm_impl(A, B, workspace, M, N, K, lda, ldb, N, transA, transB, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                       nullptr, VLK_ACT_NONE, 0, alpha, 1, split_k, slab, &used, stream);
+    if (rc) return rc;
+    const long long work = slab / 8;
+    const int sms = device_sm_count();
+    long long blocks = (work + 255) / 256;
+    if (blocks > sms * 8LL) blocks = sms * 8LL;
+    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        workspace, used, slab, static_cast<bf16*>(D), M, N, ldd, accumulate);
+    VLK_CHECK_LAUNCH("vlk_gemm_bf16_splitk(reduce)");
+    return VLK_OK;
 }

@@ -63,8 +63,11 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma,
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).  Warps walk rows grid-stride so the optional
 // dgamma / dbeta partials stay in registers until one atomicAdd per column per block.
-template <int CHUNKS, bool PARAM_GRADS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// With PARAM_GRADS the grid is only 2 blocks of 8 warps per SM: every block ends with one atomicAdd per column, and
+// the contention on those 2 x cols addresses (not the streaming loop) is what bounded the kernel when it ran with
+// 8 x SMs small blocks (138 us vs 25 us for dx alone at 16384 x 768).
+template <int CHUNKS, bool PARAM_GRADS, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, (PARAM_GRADS && CHUNKS <= 3) ? 2 : 1)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, bf16* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols, int dx_accum) {
@@ -82,7 +85,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
             db[c][i] = 0.f;
         }
     }
-    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < rows; row += gridDim.x * kWarpsPerBlock) {
+    for (int row = blockIdx.x * kWarps + warp; row < rows; row += gridDim.x * kWarps) {
         const size_t off = static_cast<size_t>(row) * cols;
         const float mu = mean[row], rs = rstd[row];
         float dyv[CHUNKS][8], xh[CHUNKS][8];
@@ -127,7 +130,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     }
     if (PARAM_GRADS) {
         // block-level reduction over the warps, then one atomic per column per block
-        __shared__ float red[kWarpsPerBlock][32 * 8 + 1];
+        __shared__ float red[kWarps][32 * 8 + 1];
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
             const int col = (c * 32 + lane) * 8;
@@ -143,7 +146,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
                     for (int i = 0; i < 8; ++i) {
                         float s = 0.f;
 #pragma unroll
-                        for (int w = 0; w < kWarpsPerBlock; ++w) s += red[w][lane * 8 + i];
+                        for (int w = 0; w < kWarps; ++w) s += red[w][lane * 8 + i];
                         atomicAdd(dst + col + i, s);
                     }
                 }
@@ -191,24 +194,26 @@ extern "C" int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamm
                 "vlk_layernorm_bwd: 16B alignment");
     const int sms = device_sm_count();
     VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_layernorm_bwd: no sm_100 device");
-    int blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int cap = sms * 8;  // persistent-ish: bounds the number of atomics when parameter grads are wanted
+    constexpr int kWarpsPG = 8;
+    const int warps = dgamma ? kWarpsPG : kWarpsPerBlock;
+    int blocks = (rows + warps - 1) / warps;
+    const int cap = dgamma ? sms * 2 : sms * 8;  // parameter grads: few, fat blocks (one atomic per column per block)
     if (blocks > cap) blocks = cap;
-    const dim3 grid(blocks), block(kWarpsPerBlock * 32);
+    const dim3 grid(blocks), block(warps * 32);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int chunks = (cols + 255) / 256;
-#define LAUNCH(C, PG)                                                                                        \
-    layernorm_bwd_kernel<C, PG><<<grid, block, 0, s>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
-                                                       static_cast<const bf16*>(gamma), mean, rstd,          \
-                                                       static_cast<bf16*>(dx), dgamma, dbeta, rows, cols, dx_accum)
+#define LAUNCH(C, PG, W)                                                                                        \
+    layernorm_bwd_kernel<C, PG, W><<<grid, block, 0, s>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
+                                                          static_cast<const bf16*>(gamma), mean, rstd,          \
+                                                          static_cast<bf16*>(dx), dgamma, dbeta, rows, cols, dx_accum)
     if (dgamma) {
-        if (chunks <= 3) LAUNCH(3, true);
-        else if (chunks <= 4) LAUNCH(4, true);
-        else LAUNCH(8, true);
+        if (chunks <= 3) LAUNCH(3, true, kWarpsPG);
+        else if (chunks <= 4) LAUNCH(4, true, kWarpsPG);
+        else LAUNCH(8, true, kWarpsPG);
     } else {
-        if (chunks <= 3) LAUNCH(3, false);
-        else if (chunks <= 4) LAUNCH(4, false);
-        else LAUNCH(8, false);
+        if (chunks <= 3) LAUNCH(3, false, kWarpsPerBlock);
+        else if (chunks <= 4) LAUNCH(4, false, kWarpsPerBlock);
+        else LAUNCH(8, false, kWarpsPerBlock);
     }
 #undef LAUNCH
     VLK_CHECK_LAUNCH("vlk_layernorm_bwd");

@@ -70,16 +70,18 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
     if K != Kb:
         raise RuntimeError(f"gemm: contraction mismatch {K} vs {Kb}")
     if split_k > 1:
-        # split-K partials are added atomically into an fp32 buffer, then rounded once
-        acc = torch.zeros((M, N), device=a.device, dtype=torch.float32)
-        gemm(a, b, trans_a=trans_a, trans_b=trans_b, alpha=alpha, out=acc, out_fp32=True, split_k=-split_k)
-        if out_fp32:
-            return acc
+        # deterministic split-K: fp32 partial slabs + one fixed-order reduction (vlk_gemm_bf16_splitk)
+        if out_fp32 or bias is not None or residual is not None or aux_in is not None or aux_out or scale is not None \
+                or act not in (None, "none", 0) or dact:
+            raise RuntimeError("gemm: split_k > 1 supports a plain bf16 product only")
+        ws = torch.empty((split_k, M, N), device=a.device, dtype=torch.float32)
         if out is None:
             out = torch.empty((M, N), device=a.device, dtype=BF16)
-        check(lib.vlk_cast_f32_to_bf16(acc.data_ptr(), out.data_ptr(), acc.numel(), _stream()), "vlk_cast_f32_to_bf16")
+        check(lib.vlk_gemm_bf16_splitk(a.data_ptr(), b.data_ptr(), out.data_ptr(), ws.data_ptr(), M, N, K, a.stride(0),
+                                       b.stride(0), out.stride(0), int(trans_a), int(trans_b), float(alpha),
+                                       int(split_k), 0, _stream()), "vlk_gemm_bf16_splitk")
         return out
-    split_k = max(1, -split_k)   # internal call from the branch above
+    split_k = -split_k if split_k < 0 else 1   # negative: raw atomic split-K into a caller-zeroed fp32 `out`
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32 if out_fp32 else BF16)
     aux = None
@@ -100,6 +102,33 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
                            int(out_fp32), int(split_k), _stream())
     check(rc, "vlk_gemm_bf16")
     return (out, aux) if aux_out else out
+
+
+_SM_COUNT = None
+
+
+def auto_split_k(M, N, K):
+    """Slices of the contraction for a product whose [M,N] output has too few 256x256 tiles to fill the GPU.
+    Cost model: waves of 2-CTA tile slots x (k-blocks per slice + ~6 k-blocks of per-tile prologue/epilogue)."""
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        _SM_COUNT = max(2, _lib.load().vlk_num_sms())
+    slots = _SM_COUNT // 2
+    units = -(-M // 256) * -(-N // 256)
+    kb = -(-K // 64)
+    if units * 2 > slots or kb < 32:
+        return 1
+    best, best_cost = 1, -(-units // slots) * (kb + 6)
+    for s in range(2, 17):
+        cost = -(-units * s // slots) * (-(-kb // s) + 6)
+        if cost < best_cost:
+            best, best_cost = s, cost
+    return best
+
+
+def wgrad(dy2, x2):
+    """dW[N_out, K_in] = dy^T . x  — the weight gradient of nn.Linear, contracted over the rows (tokens)."""
+    return gemm(dy2, x2, trans_a=True, trans_b=True, split_k=auto_split_k(dy2.shape[1], x2.shape[1], dy2.shape[0]))
 
 
 def colsum(x2d):
@@ -337,7 +366,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, weight, trans_b=True).view(ctx.x_shape)          # [M,N] x [N,K]
         if ctx.needs_input_grad[1]:
-            dw = gemm(dy2, x2, trans_a=True, trans_b=True)                  # dy^T [N,M] x x [M,K]
+            dw = wgrad(dy2, x2)                                             # dy^T [N,M] x x [M,K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2).to(BF16)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -381,11 +410,11 @@ class MLPFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(du, w_fc, trans_b=True).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dwfc = gemm(du, x2, trans_a=True, trans_b=True)
+            dwfc = wgrad(du, x2)
         if ctx.needs_input_grad[2]:
             dbfc = colsum(du).to(BF16)
         if ctx.needs_input_grad[3]:
-            dwp = gemm(dy2, h, trans_a=True, trans_b=True)
+            dwp = wgrad(dy2, h)
         if ctx.needs_input_grad[4]:
             dbp = colsum(dy2).to(BF16)
         if ctx.has_res and ctx.needs_input_grad[5]:

@@ -68,6 +68,17 @@ int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
                   int split_k, void* stream);
 
+/* Deterministic split-K product for few-tile / long-K shapes — the weight gradients dW = dy^T . x of nn.Linear
+ * (autograd of train_gpt2.py:35,42,56-58: [768..3072] x [768..3072] outputs contracted over B*T = 16,384 rows fill
+ * only 9..36 of the 74 tile slots) and d h = d logits . W (K = 50,304):
+ *   slice s of the contraction writes its fp32 partial tile into workspace[s][M][N] (plain vector stores, no
+ *   atomics); a second kernel sums the slices in a fixed order and writes D = bf16(alpha * A.B) — or
+ *   D = bf16(D + alpha * A.B) when accumulate != 0 (gradient accumulation over micro-batches,
+ *   train_gpt2.py:458-469).  workspace: split_k * M * N floats, 16-byte aligned, owned by the caller. */
+int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float* workspace, int M, int N, int K, int lda,
+                         int ldb, int ldd, int transA, int transB, float alpha, int split_k, int accumulate,
+                         void* stream);
+
 /* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
 int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);
 

@@ -94,7 +94,8 @@ def test_gemm_fp32_out_and_strided(cuda):
 
 @pytest.mark.parametrize("M,N,K,split", [(512, 768, 50304, 12), (256, 256, 640, 4), (100, 64, 4096, 7)])
 def test_gemm_split_k(cuda, M, N, K, split):
-    """Few output tiles + huge contraction (d h = d logits . W): K is cut into slices added atomically in fp32."""
+    """Few output tiles + huge contraction (d h = d logits . W): K is cut into slices whose fp32 partial tiles are
+    summed in a fixed order by vlk_gemm_bf16_splitk (deterministic: two runs agree bit for bit)."""
     from gpt2_vision_language_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(K)
     a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
@@ -102,8 +103,30 @@ def test_gemm_split_k(cuda, M, N, K, split):
     out = ops.gemm(a, b, trans_b=True, split_k=split)
     assert out.dtype == torch.bfloat16
     _check(out, a.float() @ b.float())
+    assert torch.equal(out, ops.gemm(a, b, trans_b=True, split_k=split))
     with pytest.raises(RuntimeError):   # split-K is a raw-accumulate mode: no epilogue operands
+        ops.gemm(a, b, trans_b=True, bias=torch.zeros(N, device=cuda).bfloat16(), split_k=split)
+    acc = torch.zeros(M, N, device=cuda)
+    ops.gemm(a, b, trans_b=True, out=acc, out_fp32=True, split_k=-split)          # raw atomic mode
+    _check(acc, a.float() @ b.float(), tol=1e-3)
+    with pytest.raises(RuntimeError):
         ops.gemm(a, b, trans_b=True, bias=torch.zeros(N, device=cuda).bfloat16(), out_fp32=True, split_k=-split)
+
+
+@pytest.mark.parametrize("rows,n_out,k_in", [(16384, 768, 768), (16384, 2304, 768), (4096, 768, 3072), (2112, 768, 768),
+                                             (640, 256, 128)])
+def test_wgrad_auto_split_k(cuda, rows, n_out, k_in):
+    """dW = dy^T . x (both operands MN-major) with the automatically chosen number of contraction slices."""
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + n_out)
+    dy = (torch.randn(rows, n_out, device=cuda, generator=g) * 0.1).bfloat16()
+    x = torch.randn(rows, k_in, device=cuda, generator=g).bfloat16()
+    split = ops.auto_split_k(n_out, k_in, rows)
+    if rows >= 16384 and n_out * k_in <= 2304 * 768:
+        assert split > 1
+    dw = ops.wgrad(dy, x)
+    assert dw.shape == (n_out, k_in)
+    _check(dw, dy.float().t() @ x.float())
 
 
 def test_gemm_rejects_bad_args(cuda):
