@@ -228,15 +228,23 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 __global__ void __launch_bounds__(128)
 flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta, int H, int Tq,
                    Strides os, int total_rows) {
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (w >= total_rows) return;
-    const int qi = w % Tq, h = (w / Tq) % H, b = w / (Tq * H);
-    const size_t off = b * os.bs + static_cast<size_t>(qi) * os.rs + h * 64;
-    const float2 a = __bfloat1622float2(reinterpret_cast<const bf162*>(o + off)[lane]);
-    const float2 g = __bfloat1622float2(reinterpret_cast<const bf162*>(d_o + off)[lane]);
-    const float s = warp_sum(a.x * g.x + a.y * g.y);
-    if (lane == 0) delta[w] = s;
+    // 8 lanes per (b,h,row): 16-byte loads, 4 rows per warp, 16 rows per block
+    const int lane = threadIdx.x & 31, sub = lane & 7;
+    const int w = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+    float s = 0.f;
+    if (w < total_rows) {
+        const int qi = w % Tq, h = (w / Tq) % H, b = w / (Tq * H);
+        const size_t off = b * os.bs + static_cast<size_t>(qi) * os.rs + h * 64 + sub * 8;
+        float a[8], g[8];
+        unpack8(ldg16(o + off), a);
+        unpack8(ldg16(d_o + off), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(a[i], g[i], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && w < total_rows) delta[w] = s;
 }
 
 struct FlashBwdParams {
@@ -661,7 +669,7 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
         configured = true;
     }
     const int rows = B * H * Tq;
-    flash_delta_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(static_cast<const bf16*>(o), static_cast<const bf16*>(d_o),
+    flash_delta_kernel<<<(rows + 15) / 16, 128, 0, stream>>>(static_cast<const bf16*>(o), static_cast<const bf16*>(d_o),
                                                           delta, H, Tq, Strides{o_bs, o_rs}, rows);
     VLK_CHECK_LAUNCH("vlk_attn_bwd(delta)");
     CUtensorMap tq, tk, tv, tdo;

@@ -473,6 +473,13 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
     return VLK_OK;
 }
 
+bool attn_pair_applicable(int B, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs,
+                          int v_rs, long long o_bs, int o_rs);
+int attn_pair_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                  void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
+                  int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
+                  long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
+                  const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
 bool attn_small_applicable(int Tq, int Tk);
 int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
@@ -513,10 +520,18 @@ extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const v
     {
         const char* force = getenv("VLK_ATTN_IMPL");
         if (attn_small_applicable(Tq, Tk) &&
-            (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0))))
+            (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0)))) {
+            if (!(force && strcmp(force, "small") == 0) &&
+                attn_pair_applicable(B, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs) && dq_rs % 8 == 0 &&
+                dk_rs % 8 == 0 && dv_rs % 8 == 0 && dq_bs % 8 == 0 && dk_bs % 8 == 0 && dv_bs % 8 == 0 && aligned16(dq) &&
+                aligned16(dk) && aligned16(dv))
+                return attn_pair_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
+                                     o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
+                                     seed_state, stream_id, s);
             return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
                                   o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
                                   seed_state, stream_id, s);
+        }
     }
     {
         // everything longer than the one-CTA-per-head tile runs on the tensor cores (streaming tcgen05 backward)

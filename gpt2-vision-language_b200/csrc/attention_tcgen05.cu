@@ -24,6 +24,12 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
                   int o_rs, int causal, float scale, cudaStream_t stream, int q_row0);
 
+bool attn_pair_applicable(int B, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs,
+                          int v_rs, long long o_bs, int o_rs);
+int attn_pair_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                  long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
+                  int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
+                  unsigned int stream_id, cudaStream_t stream);
 bool attn_small_applicable(int Tq, int Tk);
 int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                    long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
@@ -1032,9 +1038,15 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const char* force = getenv("VLK_ATTN_IMPL");
     if (attn_small_applicable(Tq, Tk) &&
-        (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0))))
+        (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0)))) {
+        // two heads per CTA on the tensor cores; VLK_ATTN_IMPL=small keeps the CUDA-core kernel for cross-checks
+        if (!(force && strcmp(force, "small") == 0) &&
+            attn_pair_applicable(B, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs))
+            return attn_pair_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
+                                 scale, dropout_p, seed_state, stream_id, s);
         return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
                               scale, dropout_p, seed_state, stream_id, s);
+    }
     // long sequences (GPT-2 pretraining, T = 1024): streaming tcgen05 kernel
     if ((Tk > kMaxKeys && !(force && strcmp(force, "simt") == 0)) || (force && strcmp(force, "flash") == 0))
         return attn_flash_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,

@@ -182,7 +182,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ X,
     const int col = (blockIdx.x * 32 + lane) * 8;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (col < cols) {
-        for (int r = blockIdx.y * 8 + g; r < rows; r += gridDim.y * 8) {
+        const int stride = gridDim.y * 8;
+        int r = blockIdx.y * 8 + g;
+        // four independent 16-byte loads in flight per thread (the kernel is a pure HBM stream)
+        for (; r + 3 * stride < rows; r += 4 * stride) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = ldg16(X + static_cast<size_t>(r + u * stride) * ldx + col);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(q[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+        }
+        for (; r < rows; r += stride) {
             float f[8];
             unpack8(ldg16(X + static_cast<size_t>(r) * ldx + col), f);
 #pragma unroll
@@ -406,8 +421,12 @@ extern "C" int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, in
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     VLK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
     const int gx = (cols + 255) / 256;
-    int gy = (rows + 63) / 64;
-    if (gy > 64) gy = 64;
+    const int sms = device_sm_count();
+    VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_colsum_bf16: no sm_100 device");
+    int gy = (rows + 31) / 32;                 // at least 4 rows per thread ...
+    const int cap = (sms * 6 + gx - 1) / gx;   // ... and about 6 resident blocks per SM
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
     colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>(static_cast<const bf16*>(X), out, rows, cols, ldx);
     VLK_CHECK_LAUNCH("vlk_colsum_bf16");
     return VLK_OK;

@@ -198,21 +198,31 @@ __device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int
     return ep.dact ? ep.aux_in : nullptr;
 }
 
-// Called BEFORE waiting for the accumulator: the epilogue warp is idle while the MMAs of its tile run, so the
-// first input tile is fetched under them.
-__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint4 (&pre)[8], int row0, int n0,
+// Called BEFORE waiting for the accumulator: the epilogue warp is idle while the MMAs of its tile run, so ALL of its
+// staged input (the residual, or the activation-gradient input; up to two 32 x 64 chunks) is fetched under them and
+// parked in the warp's two staging tiles.  (Fetching chunk c+1 only while chunk c was being consumed left a DRAM
+// round trip exposed per chunk: +33 % kernel time on the K = 768 / 1024 residual GEMMs, profiles/r01_gemm_short_probe.log.)
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* stage, int row0, int n0,
                                                   int ncols_warp, int M, int N, int lane) {
     if (ep.out_fp32 || ncols_warp < 64 || (ep.debug & 1) || n0 >= N) return;
     int ld;
     const bf16* in = epi_staged_input(ep, ld);
-    if (in != nullptr) tile_prefetch(pre, in, ld, row0, n0, M, min(64, N - n0), lane);
+    if (in == nullptr) return;
+    uint4 pre0[8], pre1[8];
+    const bool two = ncols_warp > 64 && n0 + 64 < N;
+    tile_prefetch(pre0, in, ld, row0, n0, M, min(64, N - n0), lane);
+    if (two) tile_prefetch(pre1, in, ld, row0, n0 + 64, M, min(64, N - n0 - 64), lane);
+    stage_put(stage, pre0, lane);
+    if (two) stage_put(stage + 4096, pre1, lane);
+    __syncwarp();
 }
 
-// One warp, its 32 accumulator rows (TMEM lanes), `ncols_warp` columns starting at global column n0.
-// stage = [input tile 4 KB | output tile 4 KB].
-__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint4 (&pre)[8], uint32_t taddr,
-                                              int row0, int n0, int ncols_warp, int M, int N, int lane,
-                                              size_t d_off = 0) {
+// One warp, its 32 accumulator rows (TMEM lanes), `ncols_warp` (<= 128) columns starting at global column n0.
+// stage = two 4 KB tiles, one per 64-column chunk; a chunk's tile first holds the staged input, is then updated IN
+// PLACE with the results (row-per-thread: a lane reads and writes only its own row's 16-byte slots) and finally
+// stored with 8 lanes per row.
+__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
+                                              int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
     const int row = row0 + lane;
     if (ep.debug & 1) return;
     if (ep.out_fp32 || ncols_warp < 64) {
@@ -228,10 +238,9 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         }
         return;
     }
-    uint8_t* stage_in = stage;
-    uint8_t* stage_out = stage + 4096;
     int staged_ld;
-    const bf16* staged_in = epi_staged_input(ep, staged_ld);
+    const bool staged = epi_staged_input(ep, staged_ld) != nullptr;
+    (void)staged;
     const bool aux_direct = ep.dact && ep.residual != nullptr;  // both present: aux_in falls back to direct loads
     const float scale = ep.scale != nullptr ? __ldg(ep.scale) : 1.0f;
 #pragma unroll 1
@@ -239,16 +248,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         const int col0 = n0 + c;
         if (col0 >= N) break;  // warp-uniform
         const int ncols = min(64, N - col0);
-        if (staged_in != nullptr) {
-            stage_put(stage_in, pre, lane);
-            __syncwarp();
-            // next input tile: in flight while this one is consumed
-            if (c + 64 < ncols_warp && col0 + 64 < N)
-                tile_prefetch(pre, staged_in, staged_ld, row0, col0 + 64, M, min(64, N - col0 - 64), lane);
-        }
-        // sweep 0 (only with aux_out): pre-activation tile; sweep 1: the output tile
+        uint8_t* buf = stage + (c >> 6) * 4096;
+        // sweep 1: the output tile (consumes the staged input); sweep 0 (only with aux_out): the pre-activation tile
 #pragma unroll 1
-        for (int sweep = (ep.aux_out != nullptr ? 0 : 1); sweep < 2; ++sweep) {
+        for (int sweep = 1; sweep >= (ep.aux_out != nullptr ? 0 : 1); --sweep) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h * 32 >= ncols) break;  // warp-uniform
@@ -285,7 +288,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
                                         for (int i = 0; i < 8; ++i) u[i] = 0.f;
                                     }
                                 } else {
-                                    unpack8(*reinterpret_cast<const uint4*>(stage_at(stage_in, lane, h * 4 + q)), u);
+                                    unpack8(*reinterpret_cast<const uint4*>(stage_at(buf, lane, h * 4 + q)), u);
                                 }
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[q * 8 + i] *= act_grad(ep.act, u[i]);
@@ -304,7 +307,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
                         for (int q = 0; q < 4; ++q) {
                             if (q * 8 < hcols) {
                                 float u[8];
-                                unpack8(*reinterpret_cast<const uint4*>(stage_at(stage_in, lane, h * 4 + q)), u);
+                                unpack8(*reinterpret_cast<const uint4*>(stage_at(buf, lane, h * 4 + q)), u);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[q * 8 + i] += u[i];
                             }
@@ -316,12 +319,12 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
                     float t[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) t[i] = v[q * 8 + i];
-                    *reinterpret_cast<uint4*>(stage_at(stage_out, lane, h * 4 + q)) = pack8(t);
+                    *reinterpret_cast<uint4*>(stage_at(buf, lane, h * 4 + q)) = pack8(t);
                 }
             }
             __syncwarp();
-            stage_store_tile(stage_out, sweep == 0 ? ep.aux_out : reinterpret_cast<bf16*>(ep.D),
-                                 sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
+            stage_store_tile(buf, sweep == 0 ? ep.aux_out : reinterpret_cast<bf16*>(ep.D),
+                             sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
             __syncwarp();
         }
     }
@@ -508,14 +511,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
             const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
-            uint4 pre[8];
-            epilogue_prefetch(ep, pre, row0, n0, kColsPerWarp, M, N, lane);
+            uint8_t* stage = smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes;
+            epilogue_prefetch(ep, stage, row0, n0, kColsPerWarp, M, N, lane);
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
-                          kColsPerWarp, M, N, lane, static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
+            epilogue_warp(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
+                          static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -694,14 +697,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
             const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
-            uint4 pre[8];
-            epilogue_prefetch(ep, pre, row0, n0, kColsPerWarp, M, N, lane);
+            uint8_t* stage = smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes;
+            epilogue_prefetch(ep, stage, row0, n0, kColsPerWarp, M, N, lane);
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp(ep, smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes, pre, taddr, row0, n0,
-                          kColsPerWarp, M, N, lane, static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
+            epilogue_warp(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
+                          static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // the leader's barrier

@@ -175,6 +175,10 @@ def attn_case(name, B, H, Tq, causal, bwd, copies=2):
 attn_case("CLIP B=64 H=16 T=257", 64, 16, 257, False, False)
 attn_case("GPT-2 caption B=64 H=12 T=64 causal", 64, 12, 64, True, True)
 attn_case("pretrain B=16 H=12 T=1024 causal", 16, 12, 1024, True, True)
+attn_case("Q-Former B=64 H=12 T=32", 64, 12, 32, False, True)
+os.environ["VLK_ATTN_IMPL"] = "small"
+attn_case("[CUDA-core kernel] GPT-2 caption B=64 H=12 T=64 causal", 64, 12, 64, True, True)
+os.environ.pop("VLK_ATTN_IMPL")
 
 # ---------------------------------------------------------------- GEMMs of the step
 def gemm_case(name, M, N, K, **kw):

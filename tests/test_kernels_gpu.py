@@ -78,7 +78,10 @@ def _attn_ref(q, k, v, H, causal):
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 12, 64, 64, True), (3, 12, 63, 63, True), (2, 12, 31, 33, False),
                                               (2, 12, 32, 32, False), (2, 16, 257, 257, False), (1, 2, 300, 300, True),
-                                              (2, 12, 1, 1, True), (1, 12, 130, 130, True)])
+                                              (2, 12, 1, 1, True), (1, 12, 130, 130, True),
+                                              # head-pair tcgen05 kernels: odd number of (batch, head) problems, ragged
+                                              (1, 3, 40, 40, True), (3, 1, 17, 64, False), (5, 3, 64, 9, False),
+                                              (1, 1, 8, 8, True), (7, 12, 33, 33, True)])
 def test_attention_fwd_bwd(cuda, B, H, Tq, Tk, causal):
     from gpt2_vision_language_b200 import ops
     C = H * 64
@@ -101,6 +104,33 @@ def test_attention_fwd_bwd(cuda, B, H, Tq, Tk, causal):
     assert relerr(dq, qr.grad) < 2e-2
     assert relerr(dk, kr.grad) < 2e-2
     assert relerr(dv, vr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,causal,p", [(4, 12, 64, 64, True, 0.0), (3, 3, 32, 33, False, 0.0),
+                                                (4, 12, 32, 32, False, 0.1), (3, 5, 32, 33, False, 0.25)])
+def test_pair_attention_matches_cuda_core_kernel(cuda, monkeypatch, B, H, Tq, Tk, causal, p):
+    """The two-heads-per-CTA tcgen05 kernels (attention_pair.cu) against the one-CTA-per-head CUDA-core kernels
+    (attention_small.cu, VLK_ATTN_IMPL=small) on the same inputs — with dropout both draw the SAME Philox mask."""
+    from gpt2_vision_language_b200 import ops
+    C = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + Tq)
+    q = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
+    kv = torch.randn(B, Tk, 2 * C, device=cuda, generator=g).bfloat16()
+    k, v = kv[..., :C], kv[..., C:]
+    d_o = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
+    rng = ops.DropoutState(cuda, seed=1234) if p > 0 else None
+    res = {}
+    for impl in ("pair", "small"):
+        if impl == "small":
+            monkeypatch.setenv("VLK_ATTN_IMPL", "small")
+        o, lse = ops.attention_fwd(q, k, v, H, causal, dropout_p=p, rng=rng, stream_id=7)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
+        ops.attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, H, causal, dropout_p=p, rng=rng, stream_id=7)
+        res[impl] = (o, lse, dq, dk, dv)
+    monkeypatch.delenv("VLK_ATTN_IMPL")
+    for a, b, name in zip(res["pair"], res["small"], ("o", "lse", "dq", "dk", "dv")):
+        assert torch.isfinite(a.float()).all(), name
+        assert relerr(a, b) < (1e-4 if name == "lse" else 2e-2), name
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 12, 1024, 1024, True), (1, 4, 384, 384, True), (1, 2, 500, 500, False),
