@@ -114,7 +114,7 @@ def time_cpu(torch, step_fn, B, steps, warmup, seed=0):
     return (time.perf_counter() - t0) / steps
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -136,7 +136,7 @@ def run_reference(args):
                              "sample": f"{args.steps} steps of B={B} (of the B=64 workload), fp32 torch, {cores} threads"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -166,7 +166,7 @@ def build_gpu_problem(torch, args, dev, rank):
     return model, clip, clip_sd, step
 
 
-def run_pretrain(args, torch, dist, dev, world, rank, local, peaks):
+def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdout):
     """GPT-2 124M pretraining step (BASELINE.json configs[4]): tokens/s, strong scaling over the ranks."""
     from gpt2_vision_language_b200 import _lib, gpt2
     from gpt2_vision_language_b200.dp import broadcast_parameters
@@ -269,7 +269,7 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks):
                      "gemm_ms_per_micro_step": tot_ms, "traffic": None},
         "cpu_baseline": None, "final_loss": float(loss_h[-1]),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 def gemm_roofline(torch, step, peaks):
@@ -333,7 +333,7 @@ def stage(msg):
         sys.stderr.flush()
 
 
-def run_b200(args):
+def run_b200(args, out=sys.stdout):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -353,7 +353,7 @@ def run_b200(args):
         pass
 
     if args.workload == "pretrain":
-        run_pretrain(args, torch, dist, dev, world, rank, local, peaks)
+        run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out)
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -460,7 +460,7 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "roofline": roof, "cpu_baseline": cpu, "final_loss": float(loss_h[-1]),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -478,9 +478,15 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    # stdout carries exactly ONE line (the JSON record): everything the libraries print on the way (the reference's
+    # configure_optimizers prints its parameter groups, train_gpt2.py:137-142) goes to stderr
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    try:
+        rc = run_reference(args, real_stdout) if args.impl == "reference" else run_b200(args, real_stdout)
+    finally:
+        sys.stdout = real_stdout
+    return rc
 
 
 if __name__ == "__main__":

@@ -683,3 +683,35 @@ class LMHeadCEFn(torch.autograd.Function):
 
 def lmhead_ce(h, weight, labels, row_weight=None):
     return LMHeadCEFn.apply(h, weight, labels, row_weight)
+
+
+@torch.no_grad()
+def cross_entropy_rows(logits2d, labels):
+    """Per-row cross-entropy (F.cross_entropy(..., reduction='none'), ignore_index rows -> 0) of bf16 logits
+    [rows, V]; the logits are only read."""
+    _need_cuda(logits2d, labels)
+    lg = _rows(logits2d)
+    labels = labels.reshape(-1).contiguous()
+    rows, V = lg.shape
+    out = torch.empty(rows, device=lg.device, dtype=torch.float32)
+    one = torch.ones(1, device=lg.device, dtype=torch.float32)
+    check(_lib.load().vlk_softmax_ce_rows(lg.data_ptr(), labels.data_ptr(), 0, out.data_ptr(), one.data_ptr(), rows, V,
+                                          lg.stride(0), 0, _stream()), "vlk_softmax_ce_rows")
+    return out
+
+
+@torch.no_grad()
+def lmhead_ce_rows(h, weight, labels, chunk=2048):
+    """Per-token losses of (h @ W^T) against labels without holding the [rows, V] logits (evaluation paths:
+    get_most_likely_row at train_gpt2.py:190-202, validation at gpt2_linear/train.py:218-252)."""
+    _param_ok(weight)
+    h2 = _rows(h)
+    rows = h2.shape[0]
+    labels = labels.reshape(-1).contiguous()
+    out = torch.empty(rows, device=h2.device, dtype=torch.float32)
+    logits = torch.empty((min(chunk, rows), weight.shape[0]), device=h2.device, dtype=BF16)
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        lg = gemm(h2[r0:r1], weight, out=logits[: r1 - r0])
+        out[r0:r1] = cross_entropy_rows(lg, labels[r0:r1])
+    return out

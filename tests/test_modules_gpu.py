@@ -179,6 +179,92 @@ def test_greedy_decode_ids_match_oracle(cuda):
     assert rate >= 0.99, rate
 
 
+@pytest.mark.parametrize("kind", ["linear", "qformer", "xattn"])
+def test_kv_cached_decode_matches_recompute(cuda, kind):
+    """The KV-cached greedy decode (prefill + one row per step) against the reference-shaped loop that re-runs the
+    whole captioner per token: same ids while the two trajectories agree, on decisive (non-tied) positions; and the
+    hidden state of the first step agrees to bf16 round-off."""
+    from gpt2_vision_language_b200 import gpt2, gpt2_linear, gpt2_q_former, gpt2_cross_att as xa
+    from gpt2_vision_language_b200 import decode as D
+    from gpt2_vision_language_b200 import ops
+    if kind == "xattn":
+        g = load("caption_xattn_tiny.pt")
+        m = xa.GPT(xa.GPTConfig(**g["cfg"]))
+        m.load_state_dict(g["sd"])
+        with torch.no_grad():
+            for i, blk in enumerate(m.transformer.h):
+                blk.cross_gate.fill_(0.5 - 0.2 * i)      # gates are 0 at init: open them so the cached K/V matter
+            m.lm_head.weight.mul_(8.0)
+        prompt, dkind = g["idx"][:, :3], "xattn"
+    else:
+        g = load("caption_linear_tiny.pt" if kind == "linear" else "caption_qformer_tiny.pt")
+        mod = gpt2_linear if kind == "linear" else gpt2_q_former
+        m = mod.GPT_Caption(enc_dim=64, lm=gpt2.GPT_previous(gpt2.GPTConfig(**g["cfg"])),
+                            m_vis_tokens=32 if kind == "linear" else 8)
+        m.load_state_dict(g["sd"])
+        with torch.no_grad():
+            m.gpt.lm_head.weight.mul_(8.0)
+        prompt, dkind = g["input_ids"][:, :3], "prefix"
+    m = m.to(cuda).to(torch.bfloat16).eval()
+    z = g["pooled"].to(torch.bfloat16).to(cuda)
+    prompt = prompt.to(cuda)
+    with torch.no_grad():      # first step: cached prefill hidden == recompute hidden (last row)
+        dec = D._Decoder(m, dkind, z, n_text_max=8)
+        h_c = dec.prefill(prompt.contiguous())
+        h_r = (D._xattn_hidden(m, prompt, z) if dkind == "xattn" else D._prefix_hidden(m, prompt, z))[:, -1, :]
+        assert cos(h_c, h_r) > 0.9995
+        w = m.lm_head.weight if dkind == "xattn" else m.gpt.lm_head.weight
+        # second step through the cache vs a recompute on the extended sequence
+        nxt = dec.next_token(h_c)
+        h_c2 = dec.step(nxt)
+        ext = torch.cat([prompt, nxt[:, None]], dim=1)
+        h_r2 = (D._xattn_hidden(m, ext, z) if dkind == "xattn" else D._prefix_hidden(m, ext, z))[:, -1, :]
+        assert cos(h_c2, h_r2) > 0.9995
+        margins = ops.gemm(h_r2.contiguous(), w).float().topk(2, dim=-1).values
+    a = D.greedy_decode(m, z, prompt, max_new_tokens=24, kind=dkind).cpu()
+    b = D.greedy_decode_recompute(m, z, prompt, max_new_tokens=24, kind=dkind).cpu()
+    assert a.shape == b.shape == (prompt.shape[0], 27)
+    assert torch.equal(a[:, :4], b[:, :4]) or (margins[:, 0] - margins[:, 1]).min() < 0.05
+    agree = (a[:, 3:] == b[:, 3:]).long().cumprod(dim=1)
+    # bf16 round-off may flip a near-tie; once a sequence diverges it is no longer comparable
+    assert agree.float().mean().item() >= 0.9, agree
+
+
+def test_eval_helpers_match_torch(cuda):
+    """get_most_likely_row (train_gpt2.py:190-202) with given logits and in its logits-free form, and per-row CE."""
+    from gpt2_vision_language_b200 import gpt2, evaluate, ops
+    g = load("gpt2_tiny.pt")
+    m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+    m.load_state_dict(g["sd"])
+    m = m.to(cuda).to(torch.bfloat16).eval()
+    gen = torch.Generator().manual_seed(5)
+    V = g["cfg"]["vocab_size"]
+    tokens = torch.randint(0, V, (4, 24), generator=gen).to(cuda)
+    mask = torch.zeros(4, 24, dtype=torch.long)
+    mask[:, 10:20] = 1
+    mask[2, 18:] = 0
+    mask = mask.to(cuda)
+    with torch.no_grad():
+        logits, _ = m(tokens)
+    lf = logits.float()
+    ref_losses = F.cross_entropy(lf[:, :-1].reshape(-1, V), tokens[:, 1:].reshape(-1), reduction="none").view(4, -1)
+    sm = mask[:, 1:].float()
+    ref_avg = (ref_losses * sm).sum(1) / sm.sum(1)
+    got = evaluate.masked_row_losses(tokens, mask, logits=logits)
+    assert (got - ref_avg).abs().max().item() < 2e-3 * ref_avg.abs().max().item()
+    assert evaluate.get_most_likely_row(tokens, mask, logits) == int(ref_avg.argmin())
+    fused = evaluate.masked_row_losses(tokens, mask, hidden=m.trunk(ops.embed(tokens, m.transformer.wte.weight,
+                                                                             m.transformer.wpe.weight)).detach(),
+                                       lm_weight=m.lm_head.weight)
+    assert (fused - ref_avg).abs().max().item() < 2e-3 * ref_avg.abs().max().item()
+    assert evaluate.most_likely_row(m, tokens, mask) == int(ref_avg.argmin())
+    lab = tokens[:, 1:].reshape(-1).clone()
+    lab[::5] = -100
+    rows = ops.cross_entropy_rows(logits[:, :-1].reshape(-1, V), lab)
+    ref_rows = F.cross_entropy(lf[:, :-1].reshape(-1, V), lab, reduction="none", ignore_index=-100)
+    assert (rows - ref_rows).abs().max().item() < 2e-3 * ref_rows.abs().max().item()
+
+
 def test_smoke_entry(cuda):
     import __graft_entry__
     __graft_entry__.smoke()
