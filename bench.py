@@ -478,14 +478,20 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    # stdout carries exactly ONE line (the JSON record): everything the libraries print on the way (the reference's
-    # configure_optimizers prints its parameter groups, train_gpt2.py:137-142) goes to stderr
-    real_stdout = sys.stdout
-    sys.stdout = sys.stderr
+    # stdout carries exactly ONE line (the JSON record).  Everything else that libraries print on the way goes to
+    # stderr: the reference's configure_optimizers prints its parameter groups (train_gpt2.py:137-142) and NCCL
+    # announces its version with a C-level printf, so file descriptor 1 itself is pointed at stderr for the run.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved_fd, "w")
+    py_stdout, sys.stdout = sys.stdout, sys.stderr
     try:
         rc = run_reference(args, real_stdout) if args.impl == "reference" else run_b200(args, real_stdout)
     finally:
-        sys.stdout = real_stdout
+        sys.stdout = py_stdout
+        real_stdout.flush()
+        os.dup2(saved_fd, 1)
     return rc
 
 

@@ -42,3 +42,133 @@ def synthetic_caption_batch(B, seed, max_len=32, vocab=50257, eot=EOT):
 
 def synthetic_pixels(B, seed):
     return torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# on-disk formats either side of the path
+# ----------------------------------------------------------------------------------------------------------
+class TokenShardLoader:
+    """Pretraining token stream with the reference's sharding arithmetic (``DataLoaderLite``,
+    source/gpt2/train_gpt2.py:149-187): ``.npy`` shards whose names contain the split, sorted; rank r starts at
+    B*T*r and every batch advances all ranks by B*T*num_processes; x = buf[:-1], y = buf[1:]; the next shard is
+    loaded when the following batch (+1 token) would not fit.  Batches come back as pinned int64 host tensors (or on
+    ``device`` when given) so the H2D copy can overlap compute."""
+
+    def __init__(self, B, T, process_rank, num_processes, split, data_root, device=None, pin=False):
+        import os
+        if split not in ("train", "val"):
+            raise AssertionError("split must be 'train' or 'val'")
+        self.B, self.T, self.process_rank, self.num_processes = B, T, process_rank, num_processes
+        self.device, self.pin = device, pin
+        shards = sorted(s for s in os.listdir(data_root) if split in s)
+        self.shards = [os.path.join(data_root, s) for s in shards]
+        if not self.shards:
+            raise AssertionError(f"no shards found for split {split}")
+        self.reset()
+
+    @staticmethod
+    def load_tokens(filename):
+        import numpy as np
+        return torch.from_numpy(np.load(filename).astype("int64"))     # np.int32 -> torch.long in the reference
+
+    def reset(self):
+        self.current_shard = 0
+        self.tokens = self.load_tokens(self.shards[0])
+        self.current_position = self.B * self.T * self.process_rank
+
+    def next_batch(self):
+        B, T = self.B, self.T
+        buf = self.tokens[self.current_position: self.current_position + B * T + 1]
+        x, y = buf[:-1].view(B, T), buf[1:].view(B, T)
+        self.current_position += B * T * self.num_processes
+        if self.current_position + (B * T * self.num_processes + 1) > len(self.tokens):
+            self.current_shard = (self.current_shard + 1) % len(self.shards)
+            self.tokens = self.load_tokens(self.shards[self.current_shard])
+            self.current_position = B * T * self.process_rank
+        if self.device is not None:
+            return x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+        if self.pin:
+            return x.contiguous().pin_memory(), y.contiguous().pin_memory()
+        return x, y
+
+
+class ClipTokenShards:
+    """The pre-computed CLIP feature cache the caption datasets read (``CocoClipFullTokensDataset``,
+    source/gpt2_linear/data.py:25-28,55-63): ``index.json`` = list of ``{"shard": name, "row": r}`` (one entry per
+    image, dataset order) next to ``.pt`` shards holding ``[n, 257, 768]`` tensors.  ``write`` produces that layout
+    from feature batches (e.g. ``clip.ClipVisionTower`` outputs), ``__getitem__`` reads it with the reference's
+    one-shard cache."""
+
+    def __init__(self, tokens_dir):
+        import json
+        import os
+        self.tokens_dir = tokens_dir
+        with open(os.path.join(tokens_dir, "index.json")) as f:
+            self.index = json.load(f)
+        self._name, self._tensor = None, None
+
+    def __len__(self):
+        return len(self.index)
+
+    def __getitem__(self, idx):
+        import os
+        e = self.index[idx]
+        if e["shard"] != self._name:
+            self._tensor = torch.load(os.path.join(self.tokens_dir, e["shard"]), map_location="cpu")
+            self._name = e["shard"]
+        return self._tensor[e["row"]]
+
+    @staticmethod
+    def write(tokens_dir, feature_batches, rows_per_shard=1024, dtype=torch.float16):
+        """feature_batches: iterable of [b, 257, D] tensors (any device).  Returns the number of images written."""
+        import json
+        import os
+        os.makedirs(tokens_dir, exist_ok=True)
+        index, pend, n_shard = [], [], 0
+
+        def flush():
+            nonlocal pend, n_shard
+            if not pend:
+                return
+            t = torch.cat(pend, dim=0)
+            name = f"shard_{n_shard:05d}.pt"
+            torch.save(t, os.path.join(tokens_dir, name))
+            index.extend({"shard": name, "row": r} for r in range(t.shape[0]))
+            pend, n_shard = [], n_shard + 1
+
+        have = 0
+        for fb in feature_batches:
+            fb = fb.detach().to("cpu", dtype)
+            while fb.shape[0]:
+                take = min(rows_per_shard - have, fb.shape[0])
+                pend.append(fb[:take])
+                fb, have = fb[take:], have + take
+                if have == rows_per_shard:
+                    flush()
+                    have = 0
+        flush()
+        with open(os.path.join(tokens_dir, "index.json"), "w") as f:
+            json.dump(index, f)
+        return len(index)
+
+
+def save_checkpoint(path, raw_model, optimizer, step, val_loss, world_size=1):
+    """The reference's rolling-checkpoint dict (source/gpt2/train_gpt2.py:363-375), written atomically."""
+    import os
+    import time
+    tmp = path + ".tmp"
+    torch.save({"model": raw_model.state_dict(), "optimizer": optimizer.state_dict() if optimizer is not None else None,
+                "config": getattr(raw_model, "config", None), "step": int(step), "val_loss": float(val_loss),
+                "ddp_world_size": int(world_size), "ts": time.strftime("%Y-%m-%d %H:%M:%S")}, tmp)
+    os.replace(tmp, path)
+
+
+def load_checkpoint(path, raw_model, optimizer=None, map_location="cpu", strict=True):
+    """Resume like source/gpt2/train_gpt2.py:319-325: returns the step to start from.  A checkpoint written by the
+    reference itself loads too (same state_dict keys); ``strict=False`` mirrors gpt2_linear/train.py:103-104."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
+    raw_model.load_state_dict(sd, strict=strict)
+    if optimizer is not None and isinstance(ckpt, dict) and ckpt.get("optimizer") is not None:
+        optimizer.load_state_dict(ckpt["optimizer"])
+    return int(ckpt.get("step", 0)) + 1 if isinstance(ckpt, dict) else 0

@@ -1,0 +1,79 @@
+"""Host-side data formats either side of the path: token shards with DataLoaderLite's
+arithmetic, the CLIP feature cache layout, the checkpoint dict.  No GPU, no kernels."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from gpt2_vision_language_b200 import data
+
+
+def _reference_stream(tokens, B, T, rank, world, n_batches):
+    """Restatement of DataLoaderLite.next_batch for ONE shard (train_gpt2.py:176-187)."""
+    pos, out = B * T * rank, []
+    for _ in range(n_batches):
+        buf = tokens[pos:pos + B * T + 1]
+        out.append((buf[:-1].view(B, T), buf[1:].view(B, T)))
+        pos += B * T * world
+        if pos + (B * T * world + 1) > len(tokens):
+            pos = B * T * rank
+    return out
+
+
+def test_token_shard_loader_matches_reference_arithmetic(tmp_path):
+    rng = np.random.default_rng(0)
+    for i, split in enumerate(["train", "train", "val"]):
+        np.save(tmp_path / f"edufineweb_{split}_{i:06d}.npy", rng.integers(0, 50257, size=1000 + 37 * i, dtype=np.uint16))
+    B, T, world = 2, 8, 2
+    for rank in range(world):
+        ld = data.TokenShardLoader(B, T, rank, world, "train", str(tmp_path))
+        assert len(ld.shards) == 2 and all("train" in s for s in ld.shards)
+        first = torch.from_numpy(np.load(ld.shards[0]).astype("int64"))
+        ref = _reference_stream(first, B, T, rank, world, 5)
+        for xr, yr in ref:
+            x, y = ld.next_batch()
+            assert x.dtype == torch.int64 and x.shape == (B, T)
+            assert torch.equal(x, xr) and torch.equal(y, yr)
+            assert torch.equal(x.flatten()[1:], y.flatten()[:-1])
+    # shard roll-over: 1000 tokens, B*T*world = 32: after n batches the next one needs 32n + 33 <= 1000, so the
+    # loader moves to the second shard after the 31st batch
+    ld = data.TokenShardLoader(B, T, 0, world, "train", str(tmp_path))
+    for _ in range(30):
+        ld.next_batch()
+    assert ld.current_shard == 0
+    ld.next_batch()
+    assert ld.current_shard == 1 and ld.current_position == 0
+    ranks = [data.TokenShardLoader(B, T, r, world, "train", str(tmp_path)).next_batch()[0] for r in range(world)]
+    assert not torch.equal(ranks[0], ranks[1])      # ranks read disjoint slices
+
+
+def test_clip_token_shards_roundtrip(tmp_path):
+    g = torch.Generator().manual_seed(1)
+    batches = [torch.randn(b, 257, 16, generator=g) for b in (5, 3, 7)]
+    n = data.ClipTokenShards.write(str(tmp_path), batches, rows_per_shard=4, dtype=torch.float32)
+    assert n == 15
+    index = json.load(open(tmp_path / "index.json"))
+    assert index[0] == {"shard": "shard_00000.pt", "row": 0} and index[5] == {"shard": "shard_00001.pt", "row": 1}
+    assert sorted(os.listdir(tmp_path)) == ["index.json"] + [f"shard_{i:05d}.pt" for i in range(4)]
+    ds = data.ClipTokenShards(str(tmp_path))
+    allrows = torch.cat(batches)
+    assert len(ds) == 15
+    for i in (0, 3, 4, 14, 7):
+        assert torch.equal(ds[i], allrows[i]) and ds[i].shape == (257, 16)
+
+
+def test_checkpoint_dict_layout_and_resume(tmp_path):
+    m = torch.nn.Linear(4, 3)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    m(torch.randn(2, 4)).sum().backward()
+    opt.step()
+    path = str(tmp_path / "model_last.pt")
+    data.save_checkpoint(path, m, opt, step=41, val_loss=3.25, world_size=8)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model", "optimizer", "config", "step", "val_loss", "ddp_world_size", "ts"}   # train_gpt2.py:365-373
+    m2 = torch.nn.Linear(4, 3)
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+    assert data.load_checkpoint(path, m2, opt2) == 42
+    assert torch.equal(m2.weight, m.weight)
+    assert opt2.state_dict()["state"][0]["step"] == opt.state_dict()["state"][0]["step"]
