@@ -162,7 +162,9 @@ def build_gpu_problem(torch, args, dev, rank):
     clip_sd = ClipVisionTower.random_state_dict(1337, device=dev)
     clip = ClipVisionTower.from_state_dict(clip_sd, device=dev)
     broadcast_parameters(model)
-    step = CaptionTrainStep(model, clip, args.workload, args.batch, TEXT_LEN, use_graph=not args.no_graph)
+    # VLK_NO_OVERLAP=1 switches the split-backward / early all-reduce path off (A/B measurement only)
+    step = CaptionTrainStep(model, clip, args.workload, args.batch, TEXT_LEN, use_graph=not args.no_graph,
+                            overlap_comm=False if os.environ.get("VLK_NO_OVERLAP") else None)
     return model, clip, clip_sd, step
 
 
@@ -176,7 +178,8 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
     broadcast_parameters(model)
     mb, T = args.micro_batch, 1024
     accum = max(1, PRETRAIN_TOKENS_PER_STEP // (mb * T * world))
-    step = PretrainStep(model, mb, T, accum, use_graph=not args.no_graph)
+    step = PretrainStep(model, mb, T, accum, use_graph=not args.no_graph,
+                        overlap_comm=False if os.environ.get("VLK_NO_OVERLAP") else None)
     g = torch.Generator().manual_seed(rank)
     x_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
     y_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
@@ -256,7 +259,7 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "GPT-2 124M pretraining step, T=1024, AdamW, clip 1.0, grad accumulation",
                    "tokens_per_step": tokens, "micro_batch": mb, "seq_len": T, "grad_accum_per_rank": accum,
-                   "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "overlap_comm": bool(getattr(step, "overlap", False)),
                    "l2": "no explicit flush: 250 MB of weights + GBs of activations per micro-step >> 126 MB L2"},
         "algorithmic_tflops": tflop / (ms * 1e-3), "frac_of_bf16_sustained_peak": tflop / (ms * 1e-3) / peak / world,
         "clocks": summarize_clocks(clocks),
@@ -448,7 +451,7 @@ def run_b200(args, out=sys.stdout):
             "config": {"workload": f"caption-{args.workload} train step: frozen CLIP ViT-L/14 fwd + 257->33 pool + "
                                    f"{args.workload} bridge + frozen GPT-2 124M fwd/bwd + chunked lm_head+CE + clip-norm+AdamW",
                        "global_batch": gb, "per_gpu_batch": B, "text_len": TEXT_LEN, "image": "3x224x224",
-                       "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                       "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "overlap_comm": bool(getattr(step, "overlap", False)),
                        "l2": "no explicit flush: one step streams ~0.9 GB of weights plus >2 GB of activations, "
                              "far above the 126 MB L2"},
             "tokens_per_s": gb * TEXT_LEN / (ms * 1e-3),

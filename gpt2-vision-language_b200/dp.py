@@ -31,23 +31,30 @@ class FlatGradBucket:
         self.extra_off = total
         total += (extra_slots + align - 1) // align * align
         self.flat = torch.zeros(total, dtype=dtype, device=device)
+        self.offsets = {id(p): o for p, o in zip(self.params, offs)}
         for p, o in zip(self.params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
         self.extra = self.flat[self.extra_off:self.extra_off + extra_slots]
+
+    def offset_of(self, param):
+        """Element offset of a parameter's gradient inside the flat buffer (parameters are laid out in
+        ``model.parameters()`` order, so the gradients of the last layers form a contiguous tail)."""
+        return self.offsets[id(param)]
 
     def zero(self):
         """Replaces optimizer.zero_grad(): one memset; the .grad views stay attached (static addresses)."""
         self.flat.zero_()
 
-    def all_reduce(self, group=None):
-        """Average over ranks, in place, on the current stream."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    def all_reduce(self, group=None, lo=0, hi=None):
+        """Average elements [lo, hi) over ranks, in place, on the current stream (default: the whole bucket)."""
+        buf = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+        if buf.numel() and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if dist.get_backend(group) == "nccl":
-                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+                dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)
             else:  # gloo has no AVG and no bf16 arithmetic: sum in fp32, divide
-                tmp = self.flat.float()
+                tmp = buf.float()
                 dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
-                self.flat.copy_(tmp / dist.get_world_size(group))
+                buf.copy_(tmp / dist.get_world_size(group))
         return self.flat
 
 

@@ -16,11 +16,73 @@ from .caption import pool_clip_197_to_33_avg_with_cls
 from .dp import FlatGradBucket
 
 
+def _gpt_split_forward(model, idx, targets, split):
+    """``GPT.forward`` (source/gpt2/train_gpt2.py:111-125) with the autograd graph CUT after block ``split-1``:
+    returns (loss, [xm], [xd]) where xd is a detached copy of the activation xm entering block ``split``.
+    ``loss.backward()`` then stops at xd (gradients of blocks split.., ln_f and the lm_head are complete), and
+    ``torch.autograd.backward([xm], [xd.grad])`` finishes the lower half — in between, the upper gradients can
+    already travel."""
+    t = model.transformer
+    x = ops.embed(idx, t.wte.weight, t.wpe.weight)
+    for blk in t.h[:split]:
+        x = blk(x)
+    xd = x.detach().requires_grad_(True)
+    y = xd
+    for blk in t.h[split:]:
+        y = blk(y)
+    y = ops.layernorm(y, t.ln_f.weight, t.ln_f.bias, t.ln_f.eps)
+    return ops.lmhead_ce(y, model.lm_head.weight, targets), [x], [xd]
+
+
+def _xattn_split_forward(model, idx, z, targets, mask, split):
+    """Same cut for the cross-attention captioner (source/gpt2_cross-att/model.py:152-186); the projected image
+    tokens feed every layer, so they are cut as well."""
+    t = model.transformer
+    x = ops.embed(idx, t.wte.weight, t.wpe.weight)
+    zp = t.vis_proj(z)
+    for blk in t.h[:split]:
+        x = blk(x, zp)
+    xd, zd = x.detach().requires_grad_(True), zp.detach().requires_grad_(True)
+    y = xd
+    for blk in t.h[split:]:
+        y = blk(y, zd)
+    y = ops.layernorm(y, t.ln_f.weight, t.ln_f.bias, t.ln_f.eps)
+    return ops.lmhead_ce(y, model.lm_head.weight, targets, mask), [x, zp], [xd, zd]
+
+
+def _upper_range(bucket, blocks, split):
+    """[lo, hi) of the flat gradient bucket holding blocks[split:] and everything after them."""
+    for blk in blocks[split:]:
+        for p in blk.parameters():
+            if p.requires_grad:
+                return bucket.offset_of(p), bucket.extra_off
+    return bucket.extra_off, bucket.extra_off
+
+
+class _CommOverlap:
+    """Second stream for the early half of the gradient exchange."""
+
+    def __init__(self):
+        self.stream = torch.cuda.Stream()
+
+    def launch(self, fn):
+        """Run fn (a collective) on the comm stream, ordered after everything already on the current stream."""
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 class CaptionTrainStep:
     def __init__(self, model, clip_tower, kind, batch, text_len=31, lr=1e-3, weight_decay=0.1, max_norm=1.0,
-                 use_graph=True, pixels_dtype=torch.float32, group=None):
+                 use_graph=True, pixels_dtype=torch.float32, group=None, overlap_comm=None):
         """kind: 'linear' | 'qformer' (GPT_Caption(patch_tokens, input_ids, labels)) or 'xattn'
-        (GPT(idx, z, targets, target_mask))."""
+        (GPT(idx, z, targets, target_mask)).
+        overlap_comm (xattn only; default: on when data parallel): backward is cut in the middle of the stack and
+        the all-reduce of the upper layers' gradients runs on a second stream UNDER the lower half of backward.
+        (Linear / Q-Former bridge gradients all materialise at the very end of backward: nothing to overlap.)"""
         assert kind in ("linear", "qformer", "xattn")
         self.model, self.clip, self.kind, self.group = model, clip_tower, kind, group
         self.max_norm, self.use_graph = max_norm, use_graph
@@ -36,22 +98,45 @@ class CaptionTrainStep:
         self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
         self.graph = None
         self._warm = 0
+        if overlap_comm is None:
+            overlap_comm = self._multi()
+        self.overlap = bool(overlap_comm) and kind == "xattn"
+        if self.overlap:
+            self.split = len(model.transformer.h) // 2
+            self.upper = _upper_range(self.bucket, model.transformer.h, self.split)
+            self.comm = _CommOverlap()
+            self._cut = None
 
     # -------------------------------------------------------------------------------------------------
     def _multi(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _fwd_bwd(self):
+        self._fwd_phase1()
+        if self.overlap:
+            self._phase2()
+
+    def _fwd_phase1(self):
+        """CLIP forward, pooling, captioner forward and backward (down to the cut when overlapping)."""
         feats = self.clip(self.pixels)                                    # [B,257,768]
         z = pool_clip_197_to_33_avg_with_cls(feats)                       # [B,33,768], unit-norm rows
         self.bucket.zero()
-        if self.kind == "xattn":
+        if self.overlap:
+            loss, outs, cuts = _xattn_split_forward(self.model, self.x, z, self.y, self.mask, self.split)
+            self._cut = (outs, cuts)
+        elif self.kind == "xattn":
             _, loss = self.model(self.x, z=z, targets=self.y, target_mask=self.mask)
         else:
             labels = self.y.masked_fill(~self.mask, -100)
             _, loss = self.model(z, self.x, labels=labels)
         loss.backward()
         self.loss.copy_(loss.detach())
+
+    def _phase2(self):
+        """Lower half of backward, from the cut to the first layer."""
+        outs, cuts = self._cut
+        torch.autograd.backward(outs, [c.grad for c in cuts])
+        self._cut = None
 
     def _exchange(self):
         """The one exchange step of the path: average the flat gradient bucket (and the scalar loss) over ranks."""
@@ -67,9 +152,27 @@ class CaptionTrainStep:
             # fresh dropout masks next step, also under CUDA-graph replay (the Philox step counter lives on device)
             ops.DropoutState.default(self.dev).advance()
 
+    def _exchange_upper_async(self):
+        if self._multi():
+            lo, hi = self.upper
+            self.comm.launch(lambda: self.bucket.all_reduce(self.group, lo, hi))
+
+    def _exchange_lower(self):
+        if self._multi():
+            self.bucket.all_reduce(self.group, 0, self.upper[0])
+            self.comm.join()
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
+            self.loss.div_(dist.get_world_size(self.group))
+
     def _body(self):
-        self._fwd_bwd()
-        self._exchange()
+        if self.overlap:
+            self._fwd_phase1()
+            self._exchange_upper_async()
+            self._phase2()
+            self._exchange_lower()
+        else:
+            self._fwd_bwd()
+            self._exchange()
         self._update()
 
     def set_lr(self, lr):
@@ -100,7 +203,17 @@ class CaptionTrainStep:
                 torch.cuda.current_stream().wait_stream(s)
                 self._warm += 1
                 return self.loss
-            if self._multi():
+            if self.overlap:
+                # three graphs: forward + upper backward | lower backward | update; the two halves of the gradient
+                # exchange are launched between them (NCCL stays outside capture), the first one on the comm stream
+                self.graph = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                with torch.cuda.graph(self.graph[0]):
+                    self._fwd_phase1()
+                with torch.cuda.graph(self.graph[1], pool=self.graph[0].pool()):
+                    self._phase2()
+                with torch.cuda.graph(self.graph[2], pool=self.graph[0].pool()):
+                    self._update()
+            elif self._multi():
                 self.graph = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
                 with torch.cuda.graph(self.graph[0]):
                     self._fwd_bwd()
@@ -110,7 +223,13 @@ class CaptionTrainStep:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._body()
-        if isinstance(self.graph, tuple):
+        if isinstance(self.graph, tuple) and len(self.graph) == 3:
+            self.graph[0].replay()
+            self._exchange_upper_async()
+            self.graph[1].replay()
+            self._exchange_lower()
+            self.graph[2].replay()
+        elif isinstance(self.graph, tuple):
             self.graph[0].replay()
             self._exchange()
             self.graph[1].replay()
@@ -164,7 +283,12 @@ class PretrainStep:
     slots) and one update (all-reduce + clip + AdamW)."""
 
     def __init__(self, model, micro_batch=16, seq=1024, grad_accum=32, lr=6e-4, weight_decay=0.1, max_norm=1.0,
-                 use_graph=True, group=None):
+                 use_graph=True, group=None, overlap_comm=None):
+        """overlap_comm (default: on when data parallel): the LAST micro-step's backward is cut in the middle of the
+        stack; the all-reduce of layers n/2.. + ln_f (half of the 249 MB) runs on a second stream under the lower
+        half of that backward, the rest (layers 0..n/2-1, wte — whose gradient also collects the lm_head's —, wpe)
+        follows.  DDP overlaps the same way with 25 MiB buckets (train_gpt2.py:467-468 enables the sync on the last
+        micro-step only)."""
         self.model, self.group, self.max_norm, self.use_graph = model, group, max_norm, use_graph
         self.grad_accum = grad_accum
         dev = next(model.parameters()).device
@@ -177,13 +301,47 @@ class PretrainStep:
         self.norm = torch.zeros((), device=dev, dtype=torch.float32)
         self.bucket = FlatGradBucket(model.parameters())
         self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
-        self.g_micro = self.g_update = None
+        self.g_micro = self.g_update = self.g_last = None
         self._warm = 0
+        if overlap_comm is None:
+            overlap_comm = self._multi()
+        self.overlap = bool(overlap_comm)
+        if self.overlap:
+            self.split = len(model.transformer.h) // 2
+            self.upper = _upper_range(self.bucket, model.transformer.h, self.split)
+            self.comm = _CommOverlap()
+            self._cut = None
+
+    def _multi(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _micro(self):
         _, loss = self.model(self.x, self.y)
         (loss / self.grad_accum).backward()
         self.loss += loss.detach() / self.grad_accum
+
+    def _last_phase1(self):
+        loss, outs, cuts = _gpt_split_forward(self.model, self.x, self.y, self.split)
+        self._cut = (outs, cuts)
+        (loss / self.grad_accum).backward()
+        self.loss += loss.detach() / self.grad_accum
+
+    def _last_phase2(self):
+        outs, cuts = self._cut
+        torch.autograd.backward(outs, [c.grad for c in cuts])
+        self._cut = None
+
+    def _exchange_upper_async(self):
+        if self._multi():
+            lo, hi = self.upper
+            self.comm.launch(lambda: self.bucket.all_reduce(self.group, lo, hi))
+
+    def _exchange_lower(self):
+        if self._multi():
+            self.bucket.all_reduce(self.group, 0, self.upper[0])
+            self.comm.join()
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
+            self.loss.div_(dist.get_world_size(self.group))
 
     def _exchange(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -217,25 +375,53 @@ class PretrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                for i in range(self.grad_accum):
+                for i in range(self.grad_accum - (1 if self.overlap else 0)):
                     self._set_slot(i)
                     self._micro()
-                self._exchange()
+                if self.overlap:
+                    self._set_slot(self.grad_accum - 1)
+                    self._last_phase1()
+                    self._exchange_upper_async()
+                    self._last_phase2()
+                    self._exchange_lower()
+                else:
+                    self._exchange()
                 self._update()
             torch.cuda.current_stream().wait_stream(s)
             self._warm += 1
             return self.loss
-        if self.g_micro is None:
+        if self.g_update is None:
             self._set_slot(0)
-            self.g_micro = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_micro):      # capture only records; nothing below has run yet
-                self._micro()
+            pool = None
+            if not self.overlap or self.grad_accum > 1:
+                self.g_micro = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g_micro):      # capture only records; nothing below has run yet
+                    self._micro()
+                pool = self.g_micro.pool()
+            if self.overlap:
+                # the last micro-step as two graphs (down to the cut | the rest); they share the micro-step's
+                # memory pool — the three never run concurrently
+                self.g_last = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                with torch.cuda.graph(self.g_last[0], pool=pool):
+                    self._last_phase1()
+                with torch.cuda.graph(self.g_last[1], pool=self.g_last[0].pool()):
+                    self._last_phase2()
             self.g_update = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_update):
                 self._update()
-        for i in range(self.grad_accum):
-            self._set_slot(i)
-            self.g_micro.replay()
-        self._exchange()                       # NCCL stays outside graph capture
+        if self.overlap:
+            for i in range(self.grad_accum - 1):
+                self._set_slot(i)
+                self.g_micro.replay()
+            self._set_slot(self.grad_accum - 1)
+            self.g_last[0].replay()
+            self._exchange_upper_async()           # NCCL stays outside graph capture, on the comm stream
+            self.g_last[1].replay()
+            self._exchange_lower()
+        else:
+            for i in range(self.grad_accum):
+                self._set_slot(i)
+                self.g_micro.replay()
+            self._exchange()
         self.g_update.replay()
         return self.loss

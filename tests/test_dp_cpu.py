@@ -33,7 +33,16 @@ def _worker(rank, world, port, out):
     x = torch.randn(5, 24, generator=g)
     mod(x).square().mean().backward()             # autograd accumulates into the flat views
     local = bucket.flat.clone()
+    # the exchange in two ranges (the split-backward overlap path reduces the tail of the bucket first) ...
+    k = bucket.offset_of(lin.bias)
+    assert 0 < k < bucket.extra_off
+    bucket.all_reduce(lo=k, hi=bucket.extra_off)
+    assert torch.equal(bucket.flat[:k], local[:k])            # ... leaves the head untouched until its own turn
+    bucket.all_reduce(lo=0, hi=k)
+    two_step = bucket.flat.clone()
+    bucket.flat.copy_(local)
     bucket.all_reduce()
+    assert torch.allclose(two_step, bucket.flat, atol=1e-7)
     # numpy arrays are pickled by value: torch tensors would travel as shared-memory handles that die with the worker
     out.put((rank,) + tuple(t.detach().clone().numpy() for t in (lin.weight, local, bucket.flat, lin.weight.grad)))
     dist.destroy_process_group()

@@ -113,3 +113,60 @@ def test_gpt2_pretrain_steps_with_grad_accumulation(cuda, use_graph):
     for a, b in zip(losses, ref_losses):
         assert abs(a - b) / b < 2e-2, (losses, ref_losses)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_split_backward_overlap_path_matches_monolithic(cuda, use_graph):
+    """The data-parallel overlap path (backward cut in the middle of the stack, upper gradients exchanged on a second
+    stream under the lower half) forced on a single GPU — the collectives are no-ops, the gradient math is what is
+    checked: same losses, gradient norms and updated weights as the monolithic step."""
+    from gpt2_vision_language_b200 import gpt2, gpt2_cross_att as xa
+    from gpt2_vision_language_b200.clip import ClipVisionTower
+    from gpt2_vision_language_b200.step import CaptionTrainStep, PretrainStep
+    # ---- GPT-2 pretraining step with gradient accumulation
+    g = load("gpt2_tiny.pt")
+    gen = torch.Generator().manual_seed(11)
+    accum, mb, T = 3, 2, 24
+    xs = torch.randint(0, 256, (accum, mb, T), generator=gen).to(cuda)
+    ys = torch.randint(0, 256, (accum, mb, T), generator=gen).to(cuda)
+    out = {}
+    for overlap in (False, True):
+        m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+        m.load_state_dict(g["sd"])
+        m = m.to(cuda).to(torch.bfloat16)
+        st = PretrainStep(m, micro_batch=mb, seq=T, grad_accum=accum, lr=3e-3, use_graph=use_graph, overlap_comm=overlap)
+        assert st.overlap == overlap
+        st.load_tokens(xs, ys)
+        losses = [st.run().item() for _ in range(4)]
+        out[overlap] = (losses, st.norm.item(), torch.cat([p.detach().float().flatten() for p in m.parameters()]))
+    assert out[True][0] == pytest.approx(out[False][0], rel=2e-3)
+    assert out[True][1] == pytest.approx(out[False][1], rel=2e-2)
+    assert F.cosine_similarity(out[True][2], out[False][2], dim=0) > 0.9999
+    assert (out[True][2] - out[False][2]).abs().max().item() < 2e-2
+    if out[True][2].numel():
+        lo, hi = st.upper
+        assert 0 < lo < hi == st.bucket.extra_off      # the upper half is a proper, non-empty tail of the bucket
+    # ---- cross-attention captioning step
+    g, gc = load("caption_xattn_tiny.pt"), load("clip_tiny.pt")
+    B = 2
+    out = {}
+    for overlap in (False, True):
+        m = xa.GPT(xa.GPTConfig(**g["cfg"]))
+        m.load_state_dict(g["sd"])
+        with torch.no_grad():
+            for i, blk in enumerate(m.transformer.h):
+                blk.cross_gate.fill_(0.3 + 0.1 * i)
+        m = m.to(cuda).to(torch.bfloat16)
+        tower = ClipVisionTower.from_state_dict(gc["sd"], layers=2, heads=2, device=cuda)
+        T = g["idx"].shape[1]
+        st = CaptionTrainStep(m, tower, "xattn", B, T, lr=1e-2, use_graph=use_graph, overlap_comm=overlap)
+        assert st.overlap == overlap
+        st.load_batch(gc["pixels"].float()[:B].to(cuda), g["idx"][:B].to(cuda), g["targets"][:B].to(cuda),
+                      g["mask"][:B].to(cuda))
+        losses = [st.run().item() for _ in range(4)]
+        out[overlap] = (losses, st.norm.item(),
+                        torch.cat([p.detach().float().flatten() for p in m.parameters() if p.requires_grad]))
+    assert out[True][0] == pytest.approx(out[False][0], rel=2e-3)
+    assert out[True][1] == pytest.approx(out[False][1], rel=2e-2)
+    assert (out[True][2] - out[False][2]).abs().max().item() < 2e-2
+    assert out[False][0][-1] < out[False][0][0]
