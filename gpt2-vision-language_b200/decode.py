@@ -131,6 +131,49 @@ def greedy_decode(model, z, prompt_ids, max_new_tokens=24, kind="prefix"):
         model.train(was_training)
 
 
+def _sample_top_p(logits, temperature, top_p, generator):
+    """The sampler of ``evaluate_cider`` (source/gpt2_linear/data.py:114-125): softmax(logits / T), keep the smallest
+    prefix of the sorted distribution whose mass exceeds top_p (the first token always survives), renormalise, draw."""
+    probs = torch.softmax(logits.float() / temperature, dim=-1)
+    sorted_probs, sorted_idx = torch.sort(probs, descending=True)
+    cutoff = sorted_probs.cumsum(dim=-1) > top_p
+    cutoff[..., 1:] = cutoff[..., :-1].clone()
+    cutoff[..., 0] = False
+    sorted_probs = sorted_probs.masked_fill(cutoff, 0.0)
+    sorted_probs = sorted_probs / sorted_probs.sum(dim=-1, keepdim=True)
+    return sorted_idx.gather(-1, torch.multinomial(sorted_probs, 1, generator=generator)).squeeze(-1)
+
+
+def _sample_top_k(logits, k, generator):
+    """The sampler of the pretraining script's text generation (source/gpt2/train_gpt2.py:444-449)."""
+    topk_probs, topk_idx = torch.topk(torch.softmax(logits.float(), dim=-1), k, dim=-1)
+    return topk_idx.gather(-1, torch.multinomial(topk_probs, 1, generator=generator)).squeeze(-1)
+
+
+@torch.no_grad()
+def sample_decode(model, z, prompt_ids, max_new_tokens=24, kind="prefix", temperature=0.8, top_p=0.9, top_k=None,
+                  generator=None):
+    """KV-cached decode with the reference's samplers instead of argmax: nucleus (temperature 0.8, top-p 0.9 — the
+    CIDEr evaluation loop) or, with ``top_k`` set, plain top-k (k = 50 in the pretraining script).  The last-row
+    logits come from the libvlk GEMM; the draw itself is host-side policy on a [B, vocab] tensor."""
+    ops._need_cuda(z, prompt_ids)
+    was_training = model.training
+    model.eval()
+    try:
+        dec = _Decoder(model, kind, z, n_text_max=prompt_ids.shape[1] + max_new_tokens)
+        out = [prompt_ids]
+        h = dec.prefill(prompt_ids.contiguous())
+        for t in range(max_new_tokens):
+            logits = ops.gemm(h, dec.lm_w)
+            nxt = _sample_top_k(logits, top_k, generator) if top_k else _sample_top_p(logits, temperature, top_p, generator)
+            out.append(nxt[:, None])
+            if t + 1 < max_new_tokens:
+                h = dec.step(nxt)
+        return torch.cat(out, dim=1)
+    finally:
+        model.train(was_training)
+
+
 @torch.no_grad()
 def greedy_decode_recompute(model, z, prompt_ids, max_new_tokens=24, kind="prefix"):
     """The reference's loop shape: the whole captioner is re-run on the growing sequence for every token."""

@@ -77,3 +77,19 @@ def test_checkpoint_dict_layout_and_resume(tmp_path):
     assert data.load_checkpoint(path, m2, opt2) == 42
     assert torch.equal(m2.weight, m.weight)
     assert opt2.state_dict()["state"][0]["step"] == opt.state_dict()["state"][0]["step"]
+
+
+def test_samplers_follow_the_reference_rules():
+    """Nucleus / top-k samplers of the decode path (data.py:114-125, train_gpt2.py:444-449) on a hand-made
+    distribution: tokens outside the nucleus / the top-k are never drawn, the argmax always can be."""
+    from gpt2_vision_language_b200.decode import _sample_top_k, _sample_top_p
+    g = torch.Generator().manual_seed(0)
+    logits = torch.log(torch.tensor([[0.5, 0.3, 0.15, 0.04, 0.01]])).repeat(2000, 1)
+    draws = _sample_top_p(logits, 1.0, 0.9, g)
+    # cumulative mass 0.5, 0.8, 0.95: the third token is the first to push the mass over 0.9 and is kept
+    assert set(draws.tolist()) == {0, 1, 2}
+    assert (draws == 0).float().mean().item() == __import__("pytest").approx(0.5 / 0.95, abs=0.04)
+    draws = _sample_top_k(logits, 2, g)
+    assert set(draws.tolist()) == {0, 1}
+    one = _sample_top_p(torch.tensor([[10.0, 0.0, 0.0]]), 0.8, 0.9, g)
+    assert one.tolist() == [0]
