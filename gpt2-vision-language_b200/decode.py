@@ -59,9 +59,13 @@ def _xattn_block_cached(block, x2, cache, zkv, B, L0, Ln):
 class _Decoder:
     """Holds the per-layer caches of one decode call."""
 
-    def __init__(self, model, kind, z, n_text_max):
+    def __init__(self, model, kind, z, n_text_max, batch=None):
         self.kind = kind
-        if kind == "xattn":
+        if kind == "gpt":                       # plain GPT-2 (source/gpt2/train_gpt2.py): no image tokens at all
+            t = model.transformer
+            self.blocks, self.ln_f, self.wte, self.wpe, self.lm_w = t.h, t.ln_f, t.wte.weight, t.wpe.weight, model.lm_head.weight
+            self.prefix = self.zkv = None
+        elif kind == "xattn":
             t = model.transformer
             self.blocks, self.ln_f, self.wte, self.wpe, self.lm_w = t.h, t.ln_f, t.wte.weight, t.wpe.weight, model.lm_head.weight
             zp = t.vis_proj(z)                                                  # [B,33,C], shared by all layers
@@ -77,10 +81,10 @@ class _Decoder:
             self.prefix = model.bridge(z[:, 0:1, :] if model.use_cls_only else z)
             self.zkv = None
         C = self.wte.shape[1]
-        B = z.shape[0]
+        B = z.shape[0] if z is not None else batch
         self.B, self.C = B, C
         max_len = (0 if self.prefix is None else self.prefix.shape[1]) + n_text_max
-        self.cache = [torch.empty(B, max_len, 2 * C, device=z.device, dtype=torch.bfloat16) for _ in self.blocks]
+        self.cache = [torch.empty(B, max_len, 2 * C, device=self.wte.device, dtype=torch.bfloat16) for _ in self.blocks]
         self.len = 0
 
     def _run(self, x):
@@ -112,13 +116,14 @@ class _Decoder:
 
 @torch.no_grad()
 def greedy_decode(model, z, prompt_ids, max_new_tokens=24, kind="prefix"):
-    """model: GPT_Caption (kind='prefix': linear / Q-Former) or cross-attention GPT (kind='xattn').
-    z: pooled CLIP tokens [B,33,D]; prompt_ids: int64 [B,P].  Returns int64 [B, P + max_new_tokens]."""
+    """model: GPT_Caption (kind='prefix': linear / Q-Former), cross-attention GPT (kind='xattn') or the plain GPT
+    (kind='gpt', z=None).  z: pooled CLIP tokens [B,33,D]; prompt_ids: int64 [B,P].
+    Returns int64 [B, P + max_new_tokens]."""
     ops._need_cuda(z, prompt_ids)
     was_training = model.training
     model.eval()                                   # decode is an eval-mode loop in the reference (data.py:77)
     try:
-        dec = _Decoder(model, kind, z, n_text_max=prompt_ids.shape[1] + max_new_tokens)
+        dec = _Decoder(model, kind, z, n_text_max=prompt_ids.shape[1] + max_new_tokens, batch=prompt_ids.shape[0])
         out = [prompt_ids]
         h = dec.prefill(prompt_ids.contiguous())
         for t in range(max_new_tokens):
@@ -160,7 +165,7 @@ def sample_decode(model, z, prompt_ids, max_new_tokens=24, kind="prefix", temper
     was_training = model.training
     model.eval()
     try:
-        dec = _Decoder(model, kind, z, n_text_max=prompt_ids.shape[1] + max_new_tokens)
+        dec = _Decoder(model, kind, z, n_text_max=prompt_ids.shape[1] + max_new_tokens, batch=prompt_ids.shape[0])
         out = [prompt_ids]
         h = dec.prefill(prompt_ids.contiguous())
         for t in range(max_new_tokens):

@@ -230,6 +230,35 @@ def test_kv_cached_decode_matches_recompute(cuda, kind):
     assert agree.float().mean().item() >= 0.9, agree
 
 
+def test_plain_gpt_cached_decode_and_sampling(cuda):
+    """kind='gpt': the KV-cached decode of the plain GPT-2 against argmax of a full forward on the same prefix, and the
+    top-k sampler (train_gpt2.py:444-449) staying inside the top-k set of the full-forward logits."""
+    from gpt2_vision_language_b200 import gpt2
+    from gpt2_vision_language_b200 import decode as D
+    g = load("gpt2_tiny.pt")
+    m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+    m.load_state_dict(g["sd"])
+    with torch.no_grad():
+        m.lm_head.weight.mul_(8.0)
+    m = m.to(cuda).to(torch.bfloat16).eval()
+    prompt = g["idx"][:, :5].to(cuda)
+    ids = D.greedy_decode(m, None, prompt, max_new_tokens=6, kind="gpt")
+    assert ids.shape == (prompt.shape[0], 11) and torch.equal(ids[:, :5], prompt)
+    with torch.no_grad():
+        for t in range(5, 11):                       # teacher-forced check: each cached step = full forward argmax
+            logits, _ = m(ids[:, :t])
+            top2 = logits[:, -1].float().topk(2, dim=-1)
+            decisive = (top2.values[:, 0] - top2.values[:, 1]) > 0.05
+            assert torch.equal(ids[decisive, t], top2.indices[decisive, 0])
+    gen = torch.Generator(device=cuda).manual_seed(42)
+    smp = D.sample_decode(m, None, prompt, max_new_tokens=4, kind="gpt", top_k=5, generator=gen)
+    with torch.no_grad():
+        for t in range(5, 9):
+            logits, _ = m(smp[:, :t])
+            top = logits[:, -1].float().topk(8, dim=-1).indices       # slack of 3 for bf16 near-ties at the k-th place
+            assert all(smp[b, t].item() in top[b].tolist() for b in range(smp.shape[0]))
+
+
 def test_eval_helpers_match_torch(cuda):
     """get_most_likely_row (train_gpt2.py:190-202) with given logits and in its logits-free form, and per-row CE."""
     from gpt2_vision_language_b200 import gpt2, evaluate, ops
