@@ -221,28 +221,22 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* 
 // stage = two 4 KB tiles, one per 64-column chunk; a chunk's tile first holds the staged input, is then updated IN
 // PLACE with the results (row-per-thread: a lane reads and writes only its own row's 16-byte slots) and finally
 // stored with 8 lanes per row.
-__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
-                                              int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
+//
+// Specialised on the epilogue operands (template value -1 = decided at run time): with every option resolved at run
+// time inside the unrolled loops the kernel was 12.6 k SASS instructions (erff alone is inlined 64 times) and the
+// epilogue warps lost ~15 % of their issue slots to instruction-cache misses (`no_inst`,
+// profiles/r01_ncu_gemm_residual_source_summary.txt).  The dispatcher below picks one compact body per launch.
+template <int ACT, int DACT, int RES, int SCALE, int AUX>
+__device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
+                                                int ncols_warp, int M, int N, int lane, size_t d_off) {
     const int row = row0 + lane;
-    if (ep.debug & 1) return;
-    if (ep.out_fp32 || ncols_warp < 64) {
-        // fp32 output (rare) and 32-column slices keep the direct row-per-thread path
-#pragma unroll 1
-        for (int c = 0; c < ncols_warp; c += 32) {
-            const int col0 = n0 + c;
-            if (col0 >= N) break;
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(taddr + c, r);
-            ptx::tmem_ld_wait();
-            if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0), d_off);
-        }
-        return;
-    }
-    int staged_ld;
-    const bool staged = epi_staged_input(ep, staged_ld) != nullptr;
-    (void)staged;
-    const bool aux_direct = ep.dact && ep.residual != nullptr;  // both present: aux_in falls back to direct loads
-    const float scale = ep.scale != nullptr ? __ldg(ep.scale) : 1.0f;
+    const int act = ACT < 0 ? ep.act : ACT;
+    const bool dact = DACT < 0 ? (ep.dact != 0) : (DACT != 0);
+    const bool has_res = RES < 0 ? (ep.residual != nullptr) : (RES != 0);
+    const bool has_scale = SCALE < 0 ? (ep.scale != nullptr) : (SCALE != 0);
+    const bool has_aux_out = AUX < 0 ? (ep.aux_out != nullptr) : (AUX != 0);
+    const bool aux_direct = dact && has_res;  // both present: aux_in falls back to direct loads
+    const float scale = has_scale ? __ldg(ep.scale) : 1.0f;
 #pragma unroll 1
     for (int c = 0; c < ncols_warp; c += 64) {
         const int col0 = n0 + c;
@@ -251,7 +245,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         uint8_t* buf = stage + (c >> 6) * 4096;
         // sweep 1: the output tile (consumes the staged input); sweep 0 (only with aux_out): the pre-activation tile
 #pragma unroll 1
-        for (int sweep = 1; sweep >= (ep.aux_out != nullptr ? 0 : 1); --sweep) {
+        for (int sweep = 1; sweep >= (has_aux_out ? 0 : 1); --sweep) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (h * 32 >= ncols) break;  // warp-uniform
@@ -275,7 +269,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
                     }
                 }
                 if (sweep == 1) {
-                    if (ep.dact) {
+                    if (dact) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (q * 8 < hcols) {
@@ -291,18 +285,18 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
                                     unpack8(*reinterpret_cast<const uint4*>(stage_at(buf, lane, h * 4 + q)), u);
                                 }
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) v[q * 8 + i] *= act_grad(ep.act, u[i]);
+                                for (int i = 0; i < 8; ++i) v[q * 8 + i] *= act_grad(act, u[i]);
                             }
                         }
-                    } else if (ep.act != VLK_ACT_NONE) {
+                    } else if (act != VLK_ACT_NONE) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = act_apply(ep.act, v[i]);
+                        for (int i = 0; i < 32; ++i) v[i] = act_apply(act, v[i]);
                     }
-                    if (ep.scale != nullptr) {
+                    if (has_scale) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] *= scale;
                     }
-                    if (ep.residual != nullptr) {
+                    if (has_res) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             if (q * 8 < hcols) {
@@ -328,6 +322,42 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
             __syncwarp();
         }
     }
+}
+
+
+__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
+                                              int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
+    if (ep.debug & 1) return;
+    if (ep.out_fp32 || ncols_warp < 64) {
+        // fp32 output (split-K slabs) and 32-column slices keep the direct row-per-thread path
+        const int row = row0 + lane;
+#pragma unroll 1
+        for (int c = 0; c < ncols_warp; c += 32) {
+            const int col0 = n0 + c;
+            if (col0 >= N) break;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c, r);
+            ptx::tmem_ld_wait();
+            if (row < M) epilogue_store32(ep, r, row, col0, min(32, N - col0), d_off);
+        }
+        return;
+    }
+#define VLK_EPI(ACT, DACT, RES, SCALE, AUX) \
+    epilogue_warp_t<ACT, DACT, RES, SCALE, AUX>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
+    const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
+    if (!sc && !ep.dact && ep.act == VLK_ACT_NONE && !aux) {          // (bias) [+ residual]: projections, dgrad, wgrad
+        if (res) VLK_EPI(0, 0, 1, 0, 0);
+        else VLK_EPI(0, 0, 0, 0, 0);
+    } else if (!sc && !ep.dact && !res && ep.act == VLK_ACT_GELU_TANH) {   // GPT-2 c_fc (+ saved pre-activation)
+        VLK_EPI(VLK_ACT_GELU_TANH, 0, 0, 0, -1);
+    } else if (!sc && !ep.dact && !res && ep.act == VLK_ACT_QUICK_GELU) {  // CLIP fc1
+        VLK_EPI(VLK_ACT_QUICK_GELU, 0, 0, 0, -1);
+    } else if (!sc && ep.dact && !res && !aux && ep.act == VLK_ACT_GELU_TANH) {  // GPT-2 c_proj dgrad x gelu'
+        VLK_EPI(VLK_ACT_GELU_TANH, 1, 0, 0, 0);
+    } else {                                                          // everything else (erf-GELU, gated residual, ...)
+        VLK_EPI(-1, -1, -1, -1, -1);
+    }
+#undef VLK_EPI
 }
 
 // Rasterisation of work units onto the output grid.  A wave of ~148 concurrently running CTAs should touch as few
