@@ -258,7 +258,10 @@ struct FlashBwdParams {
 };
 
 // ---- kernel A: dK_j, dV_j.  smem: K | V | (Q,dO) x 2 | lse/delta x 2 | barriers ----
-__global__ void __launch_bounds__(128, 1)
+// TMEM: 256 columns (two CTAs per SM): S^T [0,128) -> P^T bf16 in [0,64), this query block's dV contribution in
+// [64,128); dP^T [128,256) -> dS^T bf16 in [128,192), dK contribution in [192,256).  The contributions are added to
+// register accumulators each iteration (the next iteration's S^T / dP^T overwrite all 256 columns).
+__global__ void __launch_bounds__(128, 2)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                      FlashBwdParams p) {
@@ -295,14 +298,20 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_alloc(tmem_slot, 256);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+    const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 64, tDK = tmem + 192;
+    float acc_dv[64], acc_dk[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        acc_dv[i] = 0.f;
+        acc_dk[i] = 0.f;
+    }
 
     auto load_q = [&](int i) {
         const int buf = (i - qb0) & 1;
@@ -389,40 +398,44 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
 #pragma unroll
             for (int k = 0; k < BQ / 16; ++k) {
-                ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc,
-                                  (it | k) != 0);
-                ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc,
-                                  (it | k) != 0);
+                ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
+                ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
             }
             ptx::umma_commit(bar_acc);
         }
-        // the accumulating MMAs read P^T / dS^T and this Q/dO buffer: wait before either is overwritten
+        // these MMAs read P^T / dS^T and this Q/dO buffer: wait before either is overwritten
         ptx::mbar_wait(bar_acc, it & 1);
         ptx::tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tDV + lane_base + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) acc_dv[c + t] += __uint_as_float(r[t]);
+            ptx::tmem_ld_32x32b_x32(tDK + lane_base + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) acc_dk[c + t] += __uint_as_float(r[t]);
+        }
+        // the next iteration's products overwrite every column: all reads must be complete first
+        ptx::tc_fence_before_sync();
+        __syncthreads();
     }
     // ---- write dK (scaled) and dV ----
     if (qb0 < nqb) {
+        if (kj < p.Tk) {
+            bf16* rk = p.out0 + b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs + h * 64;
+            bf16* rv = p.out1 + b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs + h * 64;
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            const uint32_t tacc = which == 0 ? tDK : tDV;
-            bf16* dst = (which == 0 ? p.out0 : p.out1);
-            const Strides ss = which == 0 ? p.s0 : p.s1;
-            const float mul = which == 0 ? p.scale : 1.0f;
+            for (int q = 0; q < 8; ++q) {
+                float t[8];
 #pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tacc + lane_base + c, r);
-                ptx::tmem_ld_wait();
-                if (kj < p.Tk) {
-                    bf16* orow = dst + b * ss.bs + static_cast<size_t>(kj) * ss.rs + h * 64 + c;
+                for (int u = 0; u < 8; ++u) t[u] = acc_dk[q * 8 + u] * p.scale;
+                stg16(rk + q * 8, pack8(t));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float t[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) t[u] = __uint_as_float(r[q * 8 + u]) * mul;
-                        stg16(orow + q * 8, pack8(t));
-                    }
-                }
+                for (int u = 0; u < 8; ++u) t[u] = acc_dv[q * 8 + u];
+                stg16(rv + q * 8, pack8(t));
             }
         }
     } else if (kj < p.Tk) {  // no query sees this key block: zero gradients
@@ -439,12 +452,15 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, 512);
+        ptx::tmem_dealloc(tmem, 256);
     }
 }
 
 // ---- kernel B: dQ_i.  smem: Q | dO | (K,V) x 2 | barriers ----
-__global__ void __launch_bounds__(128, 1)
+// TMEM: 256 columns (two CTAs per SM, so one CTA's exp / store phase runs under the other's MMAs): S [0,128),
+// dP [128,256) -> dS bf16 in place; this block's dQ contribution lands in [0,64) (S is consumed by then) and is added
+// to a register accumulator, because the next iteration's S overwrites it.
+__global__ void __launch_bounds__(128, 2)
 flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                     FlashBwdParams p) {
@@ -479,14 +495,17 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_alloc(tmem_slot, 256);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+    const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem;
+    float dq[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) dq[i] = 0.f;
 
     auto load_kv = [&](int j) {
         uint8_t* dst = sKV + (j & 1) * 2 * kTile;
@@ -560,34 +579,36 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K_j read MN-major: N = d, K = keys
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-                ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc,
-                                  (j | k) != 0);
+                ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
             ptx::umma_commit(bar_acc);
         }
         ptx::mbar_wait(bar_acc, j & 1);
         ptx::tc_fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tDQ + lane_base + c, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dq[c + i] += __uint_as_float(r[i]);
+        }
+        // the next iteration's S / dP products overwrite every column: all reads must be complete first
+        ptx::tc_fence_before_sync();
+        __syncthreads();
     }
+    if (qi < p.Tq) {
+        bf16* orow = p.out0 + b * p.s0.bs + static_cast<size_t>(qi) * p.s0.rs + h * 64;
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tDQ + lane_base + c, r);
-        ptx::tmem_ld_wait();
-        if (qi < p.Tq) {
-            bf16* orow = p.out0 + b * p.s0.bs + static_cast<size_t>(qi) * p.s0.rs + h * 64 + c;
+        for (int q = 0; q < 8; ++q) {
+            float t[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float t[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __uint_as_float(r[q * 8 + u]) * p.scale;
-                stg16(orow + q * 8, pack8(t));
-            }
+            for (int u = 0; u < 8; ++u) t[u] = dq[q * 8 + u] * p.scale;
+            stg16(orow + q * 8, pack8(t));
         }
     }
-    ptx::tc_fence_before_sync();
-    __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, 512);
+        ptx::tmem_dealloc(tmem, 256);
     }
 }
 
