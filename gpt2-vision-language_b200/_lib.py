@@ -22,6 +22,9 @@ SIGNATURES = {
                       c_int, c_void_p],
     "vlk_gemm_bf16_splitk": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_float, c_int, c_int, c_void_p],
+    "vlk_row_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
+    "vlk_gemm_bf16_lnfold": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int, c_void_p],
     "vlk_colsum_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vlk_transpose_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,

@@ -9,7 +9,16 @@ puts that forward on the hot path, so this module reproduces HF ``CLIPVisionMode
 Layout choices for B200: q/k/v weights are fused into one [3072,1024] GEMM whose packed output feeds the
 attention kernel in place; the 14x14/14 patch convolution is an im2col + GEMM with K padded 588 -> 640
 (16-byte TMA rows); bias, quick-GELU and both residual adds live in GEMM epilogues; weights are bf16.
+
+The tower is frozen, so every LayerNorm that feeds a Linear (layer_norm1 -> q/k/v, layer_norm2 -> fc1,
+post_layernorm -> visual_projection: 49 of the 50 norms) is FOLDED into that Linear's weights once
+(``ops.fold_layernorm``): the GEMM runs on the raw residual stream, the per-row mean / rstd come from a
+statistics-only kernel and are applied in the GEMM epilogue.  No normalised copy of the [B*257, 1024]
+activations is ever written or re-read (67 MB of HBM traffic per norm at B=64).  ``VLK_CLIP_NO_LNFOLD=1``
+restores the LayerNorm kernel + plain GEMM pair (cross-check).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -109,6 +118,25 @@ class ClipVisionTower(nn.Module):
         return sd
 
     @torch.no_grad()
+    def _fold(self):
+        """(Re)build the LayerNorm-folded weights from the current buffers."""
+        q, f = [], []
+        for i in range(self.n_layers):
+            q.append(ops.fold_layernorm(self.qkv_w[i], self.qkv_b[i], self.ln1_w[i], self.ln1_b[i]))
+            f.append(ops.fold_layernorm(self.fc1_w[i], self.fc1_b[i], self.ln2_w[i], self.ln2_b[i]))
+        self._fq, self._ff = q, f
+        self._fp = ops.fold_layernorm(self.proj_w, None, self.post_ln_w, self.post_ln_b)
+        self._fold_key = self.qkv_w._version
+
+    def _folded(self):
+        if os.environ.get("VLK_CLIP_NO_LNFOLD"):
+            return False
+        if getattr(self, "_fq", None) is None or self._fold_key != self.qkv_w._version \
+                or self._fq[0][0].device != self.qkv_w.device:
+            self._fold()
+        return True
+
+    @torch.no_grad()
     def hidden_states(self, pixel_values):
         """last_hidden_state [B,257,hidden] (before post_layernorm)."""
         B = pixel_values.shape[0]
@@ -117,6 +145,17 @@ class ClipVisionTower(nn.Module):
         patch = ops.gemm(cols, self.patch_w)
         x = ops.clip_assemble(patch, self.cls, self.pos, B).view(B * 257, H)
         x, _, _ = ops.layernorm_fwd(x, self.pre_ln_w, self.pre_ln_b, self.eps, save_stats=False)
+        if self._folded():
+            for i in range(self.n_layers):
+                wq, cq, bq = self._fq[i]
+                qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps).view(B, 257, 3 * H)
+                a, _ = ops.attention_fwd(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], self.heads, False,
+                                         need_lse=False)
+                x = ops.gemm(a.view(B * 257, H), self.out_w[i], bias=self.out_b[i], residual=x)
+                wf, cf, bf_ = self._ff[i]
+                f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu")
+                x = ops.gemm(f, self.fc2_w[i], bias=self.fc2_b[i], residual=x)
+            return x.view(B, 257, H)
         for i in range(self.n_layers):
             h, _, _ = ops.layernorm_fwd(x, self.ln1_w[i], self.ln1_b[i], self.eps, save_stats=False)
             qkv = ops.gemm(h, self.qkv_w[i], bias=self.qkv_b[i]).view(B, 257, 3 * H)
@@ -133,5 +172,8 @@ class ClipVisionTower(nn.Module):
         """pixel_values [B,3,224,224] (fp32 or bf16) -> per-token features [B,257,proj_dim] (bf16)."""
         B = pixel_values.shape[0]
         x = self.hidden_states(pixel_values).view(B * 257, self.hidden)
+        if self._folded():
+            wp, cp, bp = self._fp
+            return ops.gemm_lnfold(x, wp, bp, cp, self.eps).view(B, 257, self.proj_dim)
         y, _, _ = ops.layernorm_fwd(x, self.post_ln_w, self.post_ln_b, self.eps, save_stats=False)
         return ops.gemm(y, self.proj_w).view(B, 257, self.proj_dim)

@@ -41,6 +41,10 @@ struct EpiParams {
     int split_k;  // > 1: the K range is cut into split_k slices; each slice's partial tile goes to fp32 D either
                   // atomically (split_stride == 0, D zeroed by the caller) or into its own slab s * split_stride
     long long split_stride;
+    // LayerNorm folded into the weights (vlk_gemm_bf16_lnfold): v = rstd[m] * (acc - mean[m] * colsum[n]), then bias
+    const float* ln_mean;
+    const float* ln_rstd;
+    const float* ln_colsum;
     int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 };
 
@@ -63,6 +67,12 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * ep.alpha;
 
+    if (ep.ln_mean != nullptr) {  // LayerNorm folded into the weights (narrow-tile path)
+        const float mu = __ldg(ep.ln_mean + row), rs = __ldg(ep.ln_rstd + row);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols_valid) v[i] = rs * (v[i] - mu * __ldg(ep.ln_colsum + col0 + i));
+    }
     if (ep.bias != nullptr) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -226,7 +236,7 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* 
 // time inside the unrolled loops the kernel was 12.6 k SASS instructions (erff alone is inlined 64 times) and the
 // epilogue warps lost ~15 % of their issue slots to instruction-cache misses (`no_inst`,
 // profiles/r01_ncu_gemm_residual_source_summary.txt).  The dispatcher below picks one compact body per launch.
-template <int ACT, int DACT, int RES, int SCALE, int AUX>
+template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF>
 __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                                 int ncols_warp, int M, int N, int lane, size_t d_off) {
     const int row = row0 + lane;
@@ -235,6 +245,12 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
     const bool has_res = RES < 0 ? (ep.residual != nullptr) : (RES != 0);
     const bool has_scale = SCALE < 0 ? (ep.scale != nullptr) : (SCALE != 0);
     const bool has_aux_out = AUX < 0 ? (ep.aux_out != nullptr) : (AUX != 0);
+    const bool ln_fold = LNF < 0 ? (ep.ln_mean != nullptr) : (LNF != 0);
+    float ln_mu = 0.f, ln_rs = 1.f;
+    if (ln_fold && row < M) {
+        ln_mu = __ldg(ep.ln_mean + row);
+        ln_rs = __ldg(ep.ln_rstd + row);
+    }
     const bool aux_direct = dact && has_res;  // both present: aux_in falls back to direct loads
     const float scale = has_scale ? __ldg(ep.scale) : 1.0f;
 #pragma unroll 1
@@ -257,6 +273,18 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
                 const int hc0 = col0 + h * 32;
                 const int hcols = min(32, N - hc0);
+                if (ln_fold) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (q * 4 < hcols) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + hc0) + q);
+                            v[q * 4 + 0] = ln_rs * (v[q * 4 + 0] - ln_mu * c4.x);
+                            v[q * 4 + 1] = ln_rs * (v[q * 4 + 1] - ln_mu * c4.y);
+                            v[q * 4 + 2] = ln_rs * (v[q * 4 + 2] - ln_mu * c4.z);
+                            v[q * 4 + 3] = ln_rs * (v[q * 4 + 3] - ln_mu * c4.w);
+                        }
+                    }
+                }
                 if (ep.bias != nullptr) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -343,9 +371,15 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         return;
     }
 #define VLK_EPI(ACT, DACT, RES, SCALE, AUX) \
-    epilogue_warp_t<ACT, DACT, RES, SCALE, AUX>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
+    epilogue_warp_t<ACT, DACT, RES, SCALE, AUX, 0>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
+#define VLK_EPI_LN(ACT) \
+    epilogue_warp_t<ACT, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
-    if (!sc && !ep.dact && ep.act == VLK_ACT_NONE && !aux) {          // (bias) [+ residual]: projections, dgrad, wgrad
+    if (ep.ln_mean != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
+        if (ep.act == VLK_ACT_QUICK_GELU) VLK_EPI_LN(VLK_ACT_QUICK_GELU);
+        else if (ep.act == VLK_ACT_GELU_TANH) VLK_EPI_LN(VLK_ACT_GELU_TANH);
+        else VLK_EPI_LN(VLK_ACT_NONE);
+    } else if (!sc && !ep.dact && ep.act == VLK_ACT_NONE && !aux) {          // (bias) [+ residual]: projections, dgrad, wgrad
         if (res) VLK_EPI(0, 0, 1, 0, 0);
         else VLK_EPI(0, 0, 0, 0, 0);
     } else if (!sc && !ep.dact && !res && ep.act == VLK_ACT_GELU_TANH) {   // GPT-2 c_fc (+ saved pre-activation)
@@ -358,6 +392,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         VLK_EPI(-1, -1, -1, -1, -1);
     }
 #undef VLK_EPI
+#undef VLK_EPI_LN
 }
 
 // Rasterisation of work units onto the output grid.  A wave of ~148 concurrently running CTAs should touch as few
@@ -926,7 +961,8 @@ using namespace vlk;
 static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                      int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
                      void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
-                     int split_k, long long split_stride, int* split_used, void* stream) {
+                     int split_k, long long split_stride, int* split_used, void* stream,
+                     const float* ln_mean = nullptr, const float* ln_rstd = nullptr, const float* ln_colsum = nullptr) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -975,6 +1011,9 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     ep.split_k = split_k;
     ep.split_stride = split_k > 1 ? split_stride : 0;
     if (split_used) *split_used = split_k;
+    ep.ln_mean = ln_mean;
+    ep.ln_rstd = ln_rstd;
+    ep.ln_colsum = ln_colsum;
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
 
@@ -1043,4 +1082,15 @@ extern "C" int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float
         workspace, used, slab, static_cast<bf16*>(D), M, N, ldd, accumulate);
     VLK_CHECK_LAUNCH("vlk_gemm_bf16_splitk(reduce)");
     return VLK_OK;
+}
+
+extern "C" int vlk_gemm_bf16_lnfold(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw, int ldd,
+                                    const void* bias, const float* row_mean, const float* row_rstd,
+                                    const float* col_sum, int act, void* stream) {
+    VLK_REQUIRE(row_mean && row_rstd && col_sum, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16_lnfold: null statistics");
+    VLK_REQUIRE(aligned16(col_sum), VLK_ERR_ALIGNMENT, "vlk_gemm_bf16_lnfold: col_sum must be 16-byte aligned");
+    VLK_REQUIRE(act == VLK_ACT_NONE || act == VLK_ACT_QUICK_GELU || act == VLK_ACT_GELU_TANH, VLK_ERR_UNSUPPORTED,
+                "vlk_gemm_bf16_lnfold: act=%d", act);
+    return gemm_impl(X, Wf, D, M, N, K, ldx, ldw, ldd, 0, 0, bias, nullptr, 0, nullptr, nullptr, 0, nullptr, act, 0, 1.0f,
+                     0, 1, 0, nullptr, stream, row_mean, row_rstd, col_sum);
 }

@@ -61,6 +61,47 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma,
     }
 }
 
+// Row statistics only (mean, rstd): the input of a GEMM whose weights have the LayerNorm folded in
+// (vlk_gemm_bf16_lnfold).  One 2-byte read per element, nothing written back but 8 bytes per row.
+template <int CHUNKS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                 int cols, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const bf16* xr = x + static_cast<size_t>(row) * cols;
+    float v[CHUNKS][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < cols) {
+            unpack8(ldg16(xr + col), v[c]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum += v[c][i];
+        }
+    }
+    const float mean = warp_sum(sum) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < cols) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float d = v[c][i] - mean;
+                sq += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).  Warps walk rows grid-stride so the optional
 // dgamma / dbeta partials stay in registers until one atomicAdd per column per block.
 // With PARAM_GRADS the grid is only 2 blocks of 8 warps per SM: every block ends with one atomicAdd per column, and
@@ -179,6 +220,21 @@ extern "C" int vlk_layernorm_fwd(const void* x, const void* gamma, const void* b
     else LAUNCH(8);
 #undef LAUNCH
     VLK_CHECK_LAUNCH("vlk_layernorm_fwd");
+    return VLK_OK;
+}
+
+extern "C" int vlk_row_stats(const void* x, float* mean, float* rstd, int rows, int cols, float eps, void* stream) {
+    VLK_REQUIRE(x && mean && rstd, VLK_ERR_INVALID_ARG, "vlk_row_stats: null pointer");
+    VLK_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kMaxChunks * 256, VLK_ERR_INVALID_ARG,
+                "vlk_row_stats: rows=%d cols=%d (cols must be a multiple of 8, <= 2048)", rows, cols);
+    VLK_REQUIRE(aligned16(x), VLK_ERR_ALIGNMENT, "vlk_row_stats: 16B alignment");
+    const dim3 grid((rows + kWarpsPerBlock - 1) / kWarpsPerBlock), block(kWarpsPerBlock * 32);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int chunks = (cols + 255) / 256;
+    if (chunks <= 3) row_stats_kernel<3><<<grid, block, 0, s>>>(static_cast<const bf16*>(x), mean, rstd, rows, cols, eps);
+    else if (chunks <= 4) row_stats_kernel<4><<<grid, block, 0, s>>>(static_cast<const bf16*>(x), mean, rstd, rows, cols, eps);
+    else row_stats_kernel<8><<<grid, block, 0, s>>>(static_cast<const bf16*>(x), mean, rstd, rows, cols, eps);
+    VLK_CHECK_LAUNCH("vlk_row_stats");
     return VLK_OK;
 }
 

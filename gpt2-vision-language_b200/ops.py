@@ -162,6 +162,45 @@ def layernorm_fwd(x2d, weight, bias, eps=1e-5, save_stats=True):
     return y, mean, rstd
 
 
+def row_stats(x2d, eps=1e-5):
+    """(mean, rstd) fp32 [rows] of a bf16 [rows, cols] matrix — the LayerNorm statistics without the normalised copy."""
+    _need_cuda(x2d)
+    rows, cols = x2d.shape
+    mean = torch.empty(rows, device=x2d.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x2d.device, dtype=torch.float32)
+    check(_lib.load().vlk_row_stats(x2d.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols, float(eps), _stream()),
+          "vlk_row_stats")
+    return mean, rstd
+
+
+def fold_layernorm(weight, bias, gamma, beta):
+    """Fold LayerNorm(gamma, beta) into the Linear(weight [N,K], bias [N] or None) that consumes it (frozen weights):
+    returns (Wf bf16 [N,K], colsum fp32 [N] of the ROUNDED Wf, biasf bf16 [N])."""
+    w32, g32, b32 = weight.float(), gamma.float(), beta.float()
+    wf = (w32 * g32[None, :]).to(BF16)
+    colsum = wf.float().sum(dim=1).contiguous()
+    biasf = w32 @ b32
+    if bias is not None:
+        biasf = biasf + bias.float()
+    return wf.contiguous(), colsum, biasf.to(BF16).contiguous()
+
+
+def gemm_lnfold(x2d, wf, biasf, colsum, eps=1e-5, act=None, stats=None):
+    """act(LayerNorm(x) @ W^T + b) computed as rstd * (x @ Wf^T - mean * colsum) + biasf on the RAW x
+    (vlk_gemm_bf16_lnfold); stats = (mean, rstd) may be passed when several products share one input."""
+    _need_cuda(x2d, wf)
+    x2d = _bf16c(x2d)
+    M, K = x2d.shape
+    N = wf.shape[0]
+    mean, rstd = stats if stats is not None else row_stats(x2d, eps)
+    out = torch.empty((M, N), device=x2d.device, dtype=BF16)
+    check(_lib.load().vlk_gemm_bf16_lnfold(x2d.data_ptr(), wf.data_ptr(), out.data_ptr(), M, N, K, x2d.stride(0),
+                                           wf.stride(0), out.stride(0), _p(biasf), mean.data_ptr(), rstd.data_ptr(),
+                                           colsum.data_ptr(), ACT[act] if not isinstance(act, int) else act, _stream()),
+          "vlk_gemm_bf16_lnfold")
+    return out
+
+
 def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False):
     rows, cols = x2d.shape
     if dx is None:

@@ -79,6 +79,18 @@ int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float* workspace
                          int ldb, int ldd, int transA, int transB, float alpha, int split_k, int accumulate,
                          void* stream);
 
+/* LayerNorm folded into the following Linear, for FROZEN weights (the CLIP tower: layer_norm1 -> q/k/v,
+ * layer_norm2 -> fc1, post_layernorm -> visual_projection; modeling_clip.py:347-365, 1026):
+ *     LN(x) W^T + b  =  rstd_m * ( x Wf^T  -  mean_m * colsum_n )  +  biasf_n
+ * with Wf = W * gamma (column-scaled, precomputed once), colsum_n = sum_k Wf[n,k] (fp32), biasf = W beta + b.
+ * The GEMM runs on the RAW activations; the per-row statistics come from vlk_row_stats (one read of x, no
+ * normalised copy is ever written) and are applied in the epilogue together with bias and activation
+ * (act: VLK_ACT_NONE / QUICK_GELU / GELU_TANH).  X [M,K], Wf [N,K], D [M,N] bf16. */
+int vlk_row_stats(const void* x, float* mean, float* rstd, int rows, int cols, float eps, void* stream);
+int vlk_gemm_bf16_lnfold(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw, int ldd,
+                         const void* bias, const float* row_mean, const float* row_rstd, const float* col_sum,
+                         int act, void* stream);
+
 /* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
 int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);
 

@@ -108,6 +108,9 @@ for rows, C, tag in ((64 * 257, 1024, "CLIP B=64"), (64 * 64, 768, "GPT-2 captio
         bench(f"layernorm_bwd dx+dgamma+dbeta {tag}", mkb,
               lambda s: ops.layernorm_bwd(s[0], s[1], s[2], s[3], s[4], param_grads=True, dx=s[5]), nbytes=rows * C * 2 * 3)
 
+bench("row_stats CLIP B=64 [16448x1024] (statistics of a folded LayerNorm)", lambda i: torch.randn(16448, 1024, device=dev).to(BF),
+      lambda s: ops.row_stats(s, 1e-5), nbytes=16448 * 1024 * 2)
+
 # ---------------------------------------------------------------- pool 257 -> 33 + L2 normalise
 bench("pool33_l2norm B=64 D=768 (bf16)", lambda i: torch.randn(64, 257, 768, device=dev).to(BF), lambda s: ops.pool33(s),
       nbytes=64 * (257 + 33) * 768 * 2)
@@ -199,6 +202,20 @@ def gemm_case(name, M, N, K, **kw):
     bench(f"gemm {name} M={M} N={N} K={K}", mk, run, flops=2.0 * M * N * K, copies=2)
 
 
+def gemm_ln_case(name, M, N, K, act=None):
+    def mk(i):
+        x = torch.randn(M, K, device=dev).to(BF)
+        w = (torch.randn(N, K, device=dev) * 0.03).to(BF)
+        wf, cs, bf_ = ops.fold_layernorm(w, torch.randn(N, device=dev).to(BF), torch.ones(K, device=dev).to(BF),
+                                         torch.zeros(K, device=dev).to(BF))
+        mean, rstd = ops.row_stats(x, 1e-5)
+        return x, wf, bf_, cs, (mean, rstd)
+    bench(f"gemm {name} M={M} N={N} K={K}", mk, lambda s: ops.gemm_lnfold(s[0], s[1], s[2], s[3], 1e-5, act=act, stats=s[4]),
+          flops=2.0 * M * N * K, copies=2)
+
+
+gemm_ln_case("CLIP ln1+qkv (folded LayerNorm, bias)", 16448, 3072, 1024)
+gemm_ln_case("CLIP ln2+fc1 (folded LayerNorm, bias+quick_gelu)", 16448, 4096, 1024, act="quick_gelu")
 gemm_case("CLIP qkv (bias)", 16448, 3072, 1024, use_bias=True)
 gemm_case("CLIP out_proj (bias+residual)", 16448, 1024, 1024, use_bias=True, use_res=True)
 gemm_case("CLIP fc1 (bias+quick_gelu)", 16448, 4096, 1024, use_bias=True, act="quick_gelu")

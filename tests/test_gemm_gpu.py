@@ -129,6 +129,41 @@ def test_wgrad_auto_split_k(cuda, rows, n_out, k_in):
     _check(dw, dy.float().t() @ x.float())
 
 
+@pytest.mark.parametrize("M,N,K,act", [(16448, 3072, 1024, None), (2056, 4096, 1024, "quick_gelu"), (514, 768, 1024, None),
+                                        (300, 128, 64, "gelu_tanh"), (77, 256, 2048, None), (514, 64, 128, None),
+                                        (40, 40, 64, "quick_gelu")])
+def test_gemm_with_folded_layernorm(cuda, M, N, K, act):
+    """act(LayerNorm(x) W^T + b) with the norm folded into the weights and applied in the GEMM epilogue from
+    per-row statistics, vs torch fp32 on the same bf16 inputs (rows with a large common offset included: the
+    epilogue subtracts mean * colsum from the raw product)."""
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device=cuda, generator=g)
+    x[::7] += 6.0                                            # large-mean rows
+    x[:, ::97] *= 12.0                                       # outlier channels
+    x = x.bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * 0.03).bfloat16()
+    b = (torch.randn(N, device=cuda, generator=g) * 0.1).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(K, device=cuda, generator=g)).bfloat16()
+    beta = (0.1 * torch.randn(K, device=cuda, generator=g)).bfloat16()
+    mean, rstd = ops.row_stats(x, 1e-5)
+    xf = x.float()
+    assert torch.allclose(mean, xf.mean(-1), atol=1e-3, rtol=1e-4)
+    assert torch.allclose(rstd, (xf.var(-1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-3)
+    wf, colsum, biasf = ops.fold_layernorm(w, b, gamma, beta)
+    out = ops.gemm_lnfold(x, wf, biasf, colsum, 1e-5, act=act)
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma.float(), beta.float(), 1e-5) @ w.float().t() + b.float()
+    if act == "quick_gelu":
+        ref = ref * torch.sigmoid(1.702 * ref)
+    elif act == "gelu_tanh":
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    _check(out, ref, tol=2e-2)
+    # and against the unfused pair on the same kernels
+    h, _, _ = ops.layernorm_fwd(x, gamma, beta, 1e-5, save_stats=False)
+    pair = ops.gemm(h, w, bias=b, act=act)
+    assert (out.float() - ref).abs().mean().item() <= 1.5 * (pair.float() - ref).abs().mean().item() + 1e-4
+
+
 def test_gemm_rejects_bad_args(cuda):
     from gpt2_vision_language_b200 import ops
     a = torch.randn(16, 12, device=cuda).bfloat16()
