@@ -30,7 +30,8 @@ SIGNATURES = {
     "vlk_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                           c_void_p],
     "vlk_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                          c_int, c_int, c_void_p],
+                          c_int, c_int, c_int, c_void_p],
+    "vlk_sum_copies": [c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p],
     "vlk_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                      c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float,
                      c_float, c_void_p, ctypes.c_uint, c_void_p],

@@ -111,7 +111,8 @@ template <int CHUNKS, bool PARAM_GRADS, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, (PARAM_GRADS && CHUNKS <= 3) ? 2 : 1)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, bf16* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols, int dx_accum) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int cols, int dx_accum,
+                     int grad_copies) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     float g[CHUNKS][8];
@@ -182,7 +183,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
                 for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = pass == 0 ? dg[c][i] : db[c][i];
                 __syncthreads();
                 if (warp == 0 && col < cols) {
-                    float* dst = pass == 0 ? dgamma : dbeta;
+                    // `grad_copies` replicas of the accumulators spread the same-address atomics of the ~300 blocks
+                    float* dst = (pass == 0 ? dgamma : dbeta) + static_cast<size_t>(blockIdx.x % grad_copies) * cols;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float s = 0.f;
@@ -240,12 +242,13 @@ extern "C" int vlk_row_stats(const void* x, float* mean, float* rstd, int rows, 
 
 extern "C" int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                                  const float* rstd, void* dx, float* dgamma, float* dbeta, int rows, int cols,
-                                 int dx_accum, void* stream) {
+                                 int dx_accum, int grad_copies, void* stream) {
     VLK_REQUIRE(dy && x && gamma && mean && rstd && dx, VLK_ERR_INVALID_ARG, "vlk_layernorm_bwd: null pointer");
     VLK_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), VLK_ERR_INVALID_ARG,
                 "vlk_layernorm_bwd: dgamma and dbeta must both be given or both be NULL");
     VLK_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kMaxChunks * 256, VLK_ERR_INVALID_ARG,
                 "vlk_layernorm_bwd: rows=%d cols=%d", rows, cols);
+    if (grad_copies < 1) grad_copies = 1;
     VLK_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), VLK_ERR_ALIGNMENT,
                 "vlk_layernorm_bwd: 16B alignment");
     const int sms = device_sm_count();
@@ -261,7 +264,8 @@ extern "C" int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamm
 #define LAUNCH(C, PG, W)                                                                                        \
     layernorm_bwd_kernel<C, PG, W><<<grid, block, 0, s>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
                                                           static_cast<const bf16*>(gamma), mean, rstd,          \
-                                                          static_cast<bf16*>(dx), dgamma, dbeta, rows, cols, dx_accum)
+                                                          static_cast<bf16*>(dx), dgamma, dbeta, rows, cols, dx_accum, \
+                                                          grad_copies)
     if (dgamma) {
         if (chunks <= 3) LAUNCH(3, true, kWarpsPG);
         else if (chunks <= 4) LAUNCH(4, true, kWarpsPG);
@@ -273,5 +277,27 @@ extern "C" int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamm
     }
 #undef LAUNCH
     VLK_CHECK_LAUNCH("vlk_layernorm_bwd");
+    return VLK_OK;
+}
+
+// dst[i] = sum_c src[c][i]  (fp32 or bf16 destination): final reduction of replicated gradient accumulators
+__global__ void sum_copies_kernel(const float* __restrict__ src, int copies, long long n, float* __restrict__ dst_f32,
+                                  __nv_bfloat16* __restrict__ dst_bf16) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < copies; ++c) s += src[c * n + i];
+        if (dst_bf16) dst_bf16[i] = __float2bfloat16(s);
+        else dst_f32[i] = s;
+    }
+}
+
+extern "C" int vlk_sum_copies(const float* src, int copies, long long n, void* dst, int dst_bf16, void* stream) {
+    VLK_REQUIRE(src && dst && copies > 0 && n > 0, VLK_ERR_INVALID_ARG, "vlk_sum_copies: args");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    sum_copies_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, copies, n, dst_bf16 ? nullptr : static_cast<float*>(dst), dst_bf16 ? static_cast<__nv_bfloat16*>(dst) : nullptr);
+    VLK_CHECK_LAUNCH("vlk_sum_copies");
     return VLK_OK;
 }

@@ -86,8 +86,10 @@ class Block(nn.Module):
         self.mlp = MLP(config)
 
     def forward(self, x):
-        x = self.attn.attend(ops.layernorm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps), x)
-        return self.mlp.transform(ops.layernorm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps), x)
+        x, h = ops.residual_layernorm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
+        x = self.attn.attend(h, x)
+        x, h = ops.residual_layernorm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
+        return self.mlp.transform(h, x)
 
 
 class _BlockNoBuffer(Block):

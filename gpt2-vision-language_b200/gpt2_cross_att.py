@@ -68,11 +68,14 @@ class Block(nn.Module):
 
     def forward(self, x, z):
         if z is not None:
-            y = self.xattn.attend(ops.layernorm(x, self.ln_x.weight, self.ln_x.bias, self.ln_x.eps), z)
+            x, hx = ops.residual_layernorm(x, self.ln_x.weight, self.ln_x.bias, self.ln_x.eps)
+            y = self.xattn.attend(hx, z)
             # x + tanh(gate) * c_proj(y): gate scale and residual fused into the projection GEMM epilogue
             x = ops.gated_proj_residual(y, self.xattn.c_proj.weight, self.xattn.c_proj.bias, self.cross_gate, x)
-        x = self.attn.attend(ops.layernorm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps), x)
-        return self.mlp.transform(ops.layernorm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps), x)
+        x, h = ops.residual_layernorm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
+        x = self.attn.attend(h, x)
+        x, h = ops.residual_layernorm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
+        return self.mlp.transform(h, x)
 
 
 class GPT(nn.Module):

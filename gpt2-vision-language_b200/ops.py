@@ -201,18 +201,30 @@ def gemm_lnfold(x2d, wf, biasf, colsum, eps=1e-5, act=None, stats=None):
     return out
 
 
-def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False):
+LN_GRAD_COPIES = 8
+
+
+def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False, grads_bf16=False):
+    """-> dx, dgamma, dbeta.  The parameter gradients are accumulated by ~300 blocks into LN_GRAD_COPIES replicas
+    (fewer same-address atomics) that one small kernel sums — into fp32, or bf16 when ``grads_bf16``."""
     rows, cols = x2d.shape
+    lib = _lib.load()
     if dx is None:
         assert not accumulate
         dx = torch.empty_like(x2d)
+    acc = None
+    if param_grads:
+        acc = torch.zeros((2, LN_GRAD_COPIES, cols), device=x2d.device, dtype=torch.float32)
+    check(lib.vlk_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                dx.data_ptr(), _p(acc), acc[1].data_ptr() if acc is not None else 0, rows, cols,
+                                int(accumulate), LN_GRAD_COPIES, _stream()), "vlk_layernorm_bwd")
     dg = db = None
     if param_grads:
-        dg = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
-        db = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
-    check(_lib.load().vlk_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(),
-                                        rstd.data_ptr(), dx.data_ptr(), _p(dg), _p(db), rows, cols, int(accumulate),
-                                        _stream()), "vlk_layernorm_bwd")
+        out = torch.empty((2, cols), device=x2d.device, dtype=BF16 if grads_bf16 else torch.float32)
+        for k in range(2):
+            check(lib.vlk_sum_copies(acc[k].data_ptr(), LN_GRAD_COPIES, cols, out[k].data_ptr(), int(grads_bf16), _stream()),
+                  "vlk_sum_copies")
+        dg, db = out[0], out[1]
     return dx, dg, db
 
 
@@ -481,14 +493,57 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, weight, mean, rstd = ctx.saved_tensors
         pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = layernorm_bwd(_rows(dy).contiguous(), x2, weight, mean, rstd, param_grads=pg)
+        dx, dg, db = layernorm_bwd(_rows(dy).contiguous(), x2, weight, mean, rstd, param_grads=pg, grads_bf16=True)
         return (dx.view(ctx.x_shape) if ctx.needs_input_grad[0] else None,
-                dg.to(BF16) if (pg and ctx.needs_input_grad[1]) else None,
-                db.to(BF16) if (pg and ctx.needs_input_grad[2]) else None, None)
+                dg if (pg and ctx.needs_input_grad[1]) else None,
+                db if (pg and ctx.needs_input_grad[2]) else None, None)
 
 
 def layernorm(x, weight, bias, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
+
+
+class ResidualLayerNormFn(torch.autograd.Function):
+    """(x, LayerNorm(x)) for a pre-LN residual block (train_gpt2.py:72-73: ``x = x + f(ln(x))``).  Returning the
+    residual stream through the same node lets backward ADD the LayerNorm input gradient straight into the
+    incoming residual gradient inside the LayerNorm-backward kernel (one read-modify-write of dx) instead of
+    autograd launching a separate elementwise add per norm."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        _param_ok(weight, bias)
+        x2 = _rows(x)
+        need_bwd = any(ctx.needs_input_grad)
+        y, mean, rstd = layernorm_fwd(x2, weight, bias, eps, save_stats=need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.x_shape = x.shape
+        return x.view_as(x), y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g_x, g_y):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dx = dg = db = None
+        if g_y is None:
+            return g_x, None, None, None
+        dy2 = _rows(g_y).contiguous()
+        if g_x is not None and g_x.dtype == BF16 and g_x.is_contiguous():
+            # the residual gradient has no reader left but this node (its producers ran earlier in backward)
+            acc = g_x.view(-1, g_x.shape[-1])
+            _, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, dx=acc, accumulate=True, grads_bf16=True)
+            dx = g_x
+        else:
+            dxl, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, grads_bf16=True)
+            dx = dxl.view(ctx.x_shape) if g_x is None else g_x + dxl.view(ctx.x_shape)
+        return (dx if ctx.needs_input_grad[0] else None,
+                dg if (pg and ctx.needs_input_grad[1]) else None,
+                db if (pg and ctx.needs_input_grad[2]) else None, None)
+
+
+def residual_layernorm(x, weight, bias, eps=1e-5):
+    """-> (x, LayerNorm(x)); use the returned x as the residual operand of the branch (see ResidualLayerNormFn)."""
+    return ResidualLayerNormFn.apply(x, weight, bias, eps)
 
 
 class SelfAttnFn(torch.autograd.Function):

@@ -101,13 +101,18 @@ int vlk_transpose_bf16(const void* src, void* dst, int rows, int cols, int ld_sr
  * LayerNorm over the last dim, fp32 statistics (nn.LayerNorm at train_gpt2.py:66-72,94;
  * gpt2_cross-att/model.py:91-95; gpt2_q_former/model.py:118-125; CLIP pre/post/layer norms).
  * fwd: y = (x-mean)*rstd*gamma + beta; mean/rstd (fp32 [rows]) may be NULL for inference.
- * bwd: dx always; dgamma/dbeta (fp32 [cols], ACCUMULATED into) may both be NULL for frozen norms.
- *      If dx_accum != 0, dx += result (residual-stream accumulation).
+ * bwd: dx always; dgamma/dbeta (fp32 [grad_copies, cols], ACCUMULATED into; block b adds to replica
+ *      b % grad_copies so that the ~300 blocks do not serialise on 2 x cols addresses — sum the replicas with
+ *      vlk_sum_copies) may both be NULL for frozen norms.  If dx_accum != 0, dx += result (residual-stream
+ *      accumulation).
  */
 int vlk_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                       int rows, int cols, float eps, void* stream);
 int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                      void* dx, float* dgamma, float* dbeta, int rows, int cols, int dx_accum, void* stream);
+                      void* dx, float* dgamma, float* dbeta, int rows, int cols, int dx_accum, int grad_copies,
+                      void* stream);
+/* dst[i] = sum_c src[c*n + i], written as fp32 (dst_bf16 == 0) or bf16. */
+int vlk_sum_copies(const float* src, int copies, long long n, void* dst, int dst_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Scaled-dot-product attention, head dim 64, fp32 softmax (F.scaled_dot_product_attention at

@@ -1,0 +1,7 @@
+#!/bin/bash
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python scripts/kernel_zoo.py --only "layernorm_bwd" 2>&1 | tail -7
+python scripts/kernel_zoo.py --only "colsum" 2>&1 | tail -2
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-140
+python bench.py --workload xattn --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | cut -c1-140
+python bench.py --workload pretrain --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | cut -c1-140

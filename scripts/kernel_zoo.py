@@ -108,6 +108,9 @@ for rows, C, tag in ((64 * 257, 1024, "CLIP B=64"), (64 * 64, 768, "GPT-2 captio
         bench(f"layernorm_bwd dx+dgamma+dbeta {tag}", mkb,
               lambda s: ops.layernorm_bwd(s[0], s[1], s[2], s[3], s[4], param_grads=True, dx=s[5]), nbytes=rows * C * 2 * 3)
 
+for N in (768, 3072):
+    bench(f"colsum (bias gradient) pretrain [16384x{N}]", lambda i, N=N: torch.randn(16384, N, device=dev).to(BF),
+          lambda s: ops.colsum(s), nbytes=16384 * N * 2)
 bench("row_stats CLIP B=64 [16448x1024] (statistics of a folded LayerNorm)", lambda i: torch.randn(16448, 1024, device=dev).to(BF),
       lambda s: ops.row_stats(s, 1e-5), nbytes=16448 * 1024 * 2)
 
