@@ -126,9 +126,28 @@ def auto_split_k(M, N, K):
     return best
 
 
-def wgrad(dy2, x2):
-    """dW[N_out, K_in] = dy^T . x  — the weight gradient of nn.Linear, contracted over the rows (tokens)."""
-    return gemm(dy2, x2, trans_a=True, trans_b=True, split_k=auto_split_k(dy2.shape[1], x2.shape[1], dy2.shape[0]))
+def wgrad(dy2, x2, param=None):
+    """dW[N_out, K_in] = dy^T . x  — the weight gradient of nn.Linear, contracted over the rows (tokens).
+
+    When ``param`` already has a dense bf16 ``.grad`` (gradient accumulation over micro-batches, train_gpt2.py:458-469;
+    the flat bucket of dp.FlatGradBucket), the product is ACCUMULATED into it inside the GEMM — in the split-K
+    reduction or as the epilogue's residual operand, fp32 sum rounded once — and None is returned, so autograd does
+    not launch a separate bf16 add per parameter.  Otherwise the gradient tensor is returned as usual."""
+    split = auto_split_k(dy2.shape[1], x2.shape[1], dy2.shape[0])
+    g = None if param is None else param.grad
+    if g is not None and g.dtype == BF16 and g.is_cuda and g.is_contiguous() and g.dim() == 2 \
+            and g.data_ptr() % 16 == 0 and not torch.is_grad_enabled():
+        if split > 1:
+            dy2, x2 = _bf16c(dy2), _bf16c(x2)
+            M, N, K = dy2.shape[1], x2.shape[1], dy2.shape[0]
+            ws = torch.empty((split, M, N), device=g.device, dtype=torch.float32)
+            check(_lib.load().vlk_gemm_bf16_splitk(dy2.data_ptr(), x2.data_ptr(), g.data_ptr(), ws.data_ptr(), M, N, K,
+                                                   dy2.stride(0), x2.stride(0), g.stride(0), 1, 1, 1.0, int(split), 1,
+                                                   _stream()), "vlk_gemm_bf16_splitk")
+        else:
+            gemm(dy2, x2, trans_a=True, trans_b=True, out=g, residual=g)
+        return None
+    return gemm(dy2, x2, trans_a=True, trans_b=True, split_k=split)
 
 
 def colsum(x2d):
@@ -417,7 +436,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(dy2, weight, trans_b=True).view(ctx.x_shape)          # [M,N] x [N,K]
         if ctx.needs_input_grad[1]:
-            dw = wgrad(dy2, x2)                                             # dy^T [N,M] x x [M,K]
+            dw = wgrad(dy2, x2, weight)                                     # dy^T [N,M] x x [M,K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2).to(BF16)
         if ctx.has_res and ctx.needs_input_grad[3]:
@@ -461,11 +480,11 @@ class MLPFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm(du, w_fc, trans_b=True).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dwfc = wgrad(du, x2)
+            dwfc = wgrad(du, x2, w_fc)
         if ctx.needs_input_grad[2]:
             dbfc = colsum(du).to(BF16)
         if ctx.needs_input_grad[3]:
-            dwp = wgrad(dy2, h)
+            dwp = wgrad(dy2, h, w_proj)
         if ctx.needs_input_grad[4]:
             dbp = colsum(dy2).to(BF16)
         if ctx.has_res and ctx.needs_input_grad[5]:
