@@ -226,28 +226,15 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
     if rank != 0:
         return
     th.join(timeout=2)
-    # roofline of the GEMMs: one instrumented eager micro-step
-    from gpt2_vision_language_b200 import ops
-    records, orig = [], ops.gemm
-
-    def timed(a, b, **kw):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ta, tb = kw.get("trans_a", False), kw.get("trans_b", False)
-        M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
-        N = b.shape[1] if tb else b.shape[0]
-        ev0.record()
-        out = orig(a, b, **kw)
-        ev1.record()
-        records.append((ev0, ev1, 2.0 * M * N * K))
-        return out
-    ops.gemm = timed
-    try:
-        step.bucket.zero()
-        step._set_slot(0)
-        step._micro()
+    # roofline of the GEMMs: an instrumented eager micro-step (run twice: the first pass warms the allocator)
+    with GemmRecorder(torch) as rec:
+        for _ in range(2):
+            rec.records.clear()
+            step.bucket.zero()
+            step._set_slot(0)
+            step._micro()
         torch.cuda.synchronize()
-    finally:
-        ops.gemm = orig
+    records = [(a, b, 2.0 * m * n * k) for a, b, (m, n, k), _ in rec.records]
     tot_ms = sum(a.elapsed_time(b) for a, b, _ in records)
     tot_fl = sum(f for _, _, f in records)
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
@@ -275,52 +262,80 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
     print(json.dumps(line), file=out, flush=True)
 
 
+class GemmRecorder:
+    """CUDA events around every tensor-core product the step launches through ops (ops.gemm, ops.gemm_lnfold,
+    ops.wgrad); nested calls (wgrad -> gemm) are recorded once, at the outermost level."""
+
+    def __init__(self, torch):
+        from gpt2_vision_language_b200 import ops
+        self.torch, self.ops, self.records, self.depth = torch, ops, [], 0
+        self.orig = (ops.gemm, ops.gemm_lnfold, ops.wgrad)
+
+    def _wrap(self, fn, shape_of, kind):
+        def timed(*a, **kw):
+            if self.depth:
+                return fn(*a, **kw)
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            self.depth += 1
+            e0.record()
+            try:
+                out = fn(*a, **kw)
+            finally:
+                self.depth -= 1
+            e1.record()
+            self.records.append((e0, e1, shape_of(*a, **kw), kind))
+            return out
+        return timed
+
+    def __enter__(self):
+        def gemm_shape(a, b, **kw):
+            ta, tb = kw.get("trans_a", False), kw.get("trans_b", False)
+            M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+            return (M, b.shape[1] if tb else b.shape[0], K)
+        o = self.ops
+        o.gemm = self._wrap(self.orig[0], gemm_shape, "gemm")
+        o.gemm_lnfold = self._wrap(self.orig[1], lambda x, wf, *a, **kw: (x.shape[0], wf.shape[0], x.shape[1]), "lnfold")
+        o.wgrad = self._wrap(self.orig[2], lambda dy, x, *a, **kw: (dy.shape[1], x.shape[1], dy.shape[0]), "wgrad")
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.gemm, self.ops.gemm_lnfold, self.ops.wgrad = self.orig
+
+
 def gemm_roofline(torch, step, peaks):
     """Instrumented eager pass: CUDA events around every vlk_gemm_bf16 launch of one full step.  The roofline object
     is for the DOMINANT kernel = the GEMM launch shape with the largest total time in the step (CLIP fc1,
     16448 x 4096 x 1024 with bias + quick-GELU at B=64); the aggregate over all GEMM launches is reported beside it."""
-    from gpt2_vision_language_b200 import ops
-    records = []
-    orig = ops.gemm
-
-    def timed(a, b, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ta, tb = kw.get("trans_a", False), kw.get("trans_b", False)
-        M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
-        N = b.shape[1] if tb else b.shape[0]
-        e0.record()
-        out = orig(a, b, **kw)
-        e1.record()
-        records.append((e0, e1, (M, N, K)))
-        return out
-    ops.gemm = timed
-    try:
-        for _ in range(2):
-            records.clear()
-            step._fwd_bwd()      # rank-local: no collective here (only rank 0 runs this pass)
+    with GemmRecorder(torch) as rec:
+        for _ in range(2):           # the first pass warms the allocator: an allocation inside a timed window is host time
+            rec.records.clear()
+            step._fwd_bwd()          # rank-local: no collective here (only rank 0 runs this pass)
             step._update()
         torch.cuda.synchronize()
-    finally:
-        ops.gemm = orig
+    records = rec.records
     by_shape = {}
-    for e0, e1, shp in records:
+    for e0, e1, shp, kind in records:
         t = e0.elapsed_time(e1)
-        n, tot = by_shape.get(shp, (0, 0.0))
-        by_shape[shp] = (n + 1, tot + t)
+        n, tot = by_shape.get((shp, kind), (0, 0.0))
+        by_shape[(shp, kind)] = (n + 1, tot + t)
     tot_ms = sum(t for _, t in by_shape.values())
-    tot_fl = sum(2.0 * m * n * k * cnt for (m, n, k), (cnt, _) in by_shape.items())
-    (dm, dn, dk), (dcnt, dms) = max(by_shape.items(), key=lambda kv: kv[1][1])
+    tot_fl = sum(2.0 * m * n * k * cnt for ((m, n, k), _), (cnt, _) in by_shape.items())
+    ((dm, dn, dk), dkind), (dcnt, dms) = max(by_shape.items(), key=lambda kv: kv[1][1])
     flops = 2.0 * dm * dn * dk
     achieved = flops / (dms / dcnt * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
     traffic = None
+    epi = ""
     try:   # DRAM bytes of one launch of that shape from the committed `ncu --set full` capture
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_fc1.json")))
-        if [dm, dn, dk] == cap.get("shape"):
-            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_shapes.json")))
+        for c in cap["shapes"]:
+            if [dm, dn, dk] == c["shape"] and c["kind"] == dkind:
+                traffic = c["dram_bytes_read"] + c["dram_bytes_write"]
+                epi = ", " + c["epilogue"]
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": f"gemm_bf16_2cta_kernel, M={dm} N={dn} K={dk} ({dcnt} launches per step)",
+    return {"bound": "tensor",
+            "kernel": f"gemm_bf16_2cta_kernel ({dkind}{epi}), M={dm} N={dn} K={dk} ({dcnt} launches per step)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained",
             "algorithmic_flop_per_launch": flops, "avg_launch_us": dms / dcnt * 1e3,

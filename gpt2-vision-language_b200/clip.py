@@ -148,12 +148,12 @@ class ClipVisionTower(nn.Module):
         if self._folded():
             for i in range(self.n_layers):
                 wq, cq, bq = self._fq[i]
-                qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps).view(B, 257, 3 * H)
+                qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps, stats=ops.row_stats(x, self.eps)).view(B, 257, 3 * H)
                 a, _ = ops.attention_fwd(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], self.heads, False,
                                          need_lse=False)
                 x = ops.gemm(a.view(B * 257, H), self.out_w[i], bias=self.out_b[i], residual=x)
                 wf, cf, bf_ = self._ff[i]
-                f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu")
+                f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu", stats=ops.row_stats(x, self.eps))
                 x = ops.gemm(f, self.fc2_w[i], bias=self.fc2_b[i], residual=x)
             return x.view(B, 257, H)
         for i in range(self.n_layers):
@@ -174,6 +174,6 @@ class ClipVisionTower(nn.Module):
         x = self.hidden_states(pixel_values).view(B * 257, self.hidden)
         if self._folded():
             wp, cp, bp = self._fp
-            return ops.gemm_lnfold(x, wp, bp, cp, self.eps).view(B, 257, self.proj_dim)
+            return ops.gemm_lnfold(x, wp, bp, cp, self.eps, stats=ops.row_stats(x, self.eps)).view(B, 257, self.proj_dim)
         y, _, _ = ops.layernorm_fwd(x, self.post_ln_w, self.post_ln_b, self.eps, save_stats=False)
         return ops.gemm(y, self.proj_w).view(B, 257, self.proj_dim)

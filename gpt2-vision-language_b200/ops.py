@@ -134,7 +134,7 @@ def wgrad(dy2, x2, param=None):
     reduction or as the epilogue's residual operand, fp32 sum rounded once — and None is returned, so autograd does
     not launch a separate bf16 add per parameter.  Otherwise the gradient tensor is returned as usual."""
     split = auto_split_k(dy2.shape[1], x2.shape[1], dy2.shape[0])
-    g = None if param is None else param.grad
+    g = param.grad if (param is not None and param.is_leaf) else None   # slices of packed weights are not leaves
     if g is not None and g.dtype == BF16 and g.is_cuda and g.is_contiguous() and g.dim() == 2 \
             and g.data_ptr() % 16 == 0 and not torch.is_grad_enabled():
         if split > 1:
