@@ -742,8 +742,7 @@ class LMHeadCEFn(torch.autograd.Function):
     The gradient is produced in the forward pass and scaled by the incoming scalar in backward."""
 
     CHUNK_ROWS = 512
-    CHUNK_ROWS_DW = 4096
-    DH_SPLIT_K = 12
+    CHUNK_ROWS_DW = 16384
 
     @staticmethod
     def forward(ctx, h, weight, labels, row_weight):
@@ -764,7 +763,8 @@ class LMHeadCEFn(torch.autograd.Function):
         dh = torch.empty_like(h2) if need_dh else None
         dw = None
         # frozen lm_head (captioning): 512-row chunks keep the chunk's logits L2-resident; trainable lm_head
-        # (pretraining): larger chunks so that dW is rounded to bf16 only a few times per micro-batch
+        # (pretraining): one chunk per micro-batch (1.65 GB of bf16 logits at 16 x 1024 rows), so dW is a single
+        # K = 16,384 product instead of a chain of read-modify-write accumulations
         chunk = LMHeadCEFn.CHUNK_ROWS if not need_dw else max(LMHeadCEFn.CHUNK_ROWS, LMHeadCEFn.CHUNK_ROWS_DW)
         logits = torch.empty((min(chunk, rows), V), device=dev, dtype=BF16)
         for r0 in range(0, rows, chunk):
@@ -776,7 +776,7 @@ class LMHeadCEFn(torch.autograd.Function):
                                           int(write_grad), _stream()), "vlk_softmax_ce_rows")
             if need_dh:
                 # d logits [r,V] x W [V,C]: a handful of output tiles with K = V = 50304 -> split the contraction
-                gemm(lg, weight, trans_b=True, out=dh[r0:r1], split_k=LMHeadCEFn.DH_SPLIT_K)
+                gemm(lg, weight, trans_b=True, out=dh[r0:r1], split_k=auto_split_k(r1 - r0, C, V))
             if need_dw:
                 if dw is None:
                     dw = gemm(lg, h2[r0:r1], trans_a=True, trans_b=True)      # d logits^T x h

@@ -93,3 +93,16 @@ def test_samplers_follow_the_reference_rules():
     assert set(draws.tolist()) == {0, 1}
     one = _sample_top_p(torch.tensor([[10.0, 0.0, 0.0]]), 0.8, 0.9, g)
     assert one.tolist() == [0]
+
+
+def test_auto_split_k_heuristic(monkeypatch):
+    """Slice count of the deterministic split-K products (ops.auto_split_k) on a 148-SM part: weight gradients of the
+    pretraining step are cut so that one wave of 74 tile slots is (nearly) full, big outputs are left alone."""
+    from gpt2_vision_language_b200 import ops
+    monkeypatch.setattr(ops, "_SM_COUNT", 148)
+    assert ops.auto_split_k(768, 768, 16384) == 8        # 9 tiles -> 72 units
+    assert ops.auto_split_k(3072, 768, 16384) == 2       # 36 tiles -> 72 units
+    assert ops.auto_split_k(512, 768, 50304) == 12       # d h of a 512-row lm_head chunk: 6 tiles -> 72 units
+    assert ops.auto_split_k(16384, 768, 50304) == 1      # 192 tiles already cover the GPU
+    assert ops.auto_split_k(50304, 768, 16384) == 1
+    assert ops.auto_split_k(768, 768, 1024) == 1         # short contraction: not worth a second pass
