@@ -269,7 +269,7 @@ class GemmRecorder:
     def __init__(self, torch):
         from gpt2_vision_language_b200 import ops
         self.torch, self.ops, self.records, self.depth = torch, ops, [], 0
-        self.orig = (ops.gemm, ops.gemm_lnfold, ops.wgrad)
+        self.orig = (ops.gemm, ops.gemm_lnfold, ops.wgrad, ops.gemm_stats)
 
     def _wrap(self, fn, shape_of, kind):
         def timed(*a, **kw):
@@ -296,10 +296,11 @@ class GemmRecorder:
         o.gemm = self._wrap(self.orig[0], gemm_shape, "gemm")
         o.gemm_lnfold = self._wrap(self.orig[1], lambda x, wf, *a, **kw: (x.shape[0], wf.shape[0], x.shape[1]), "lnfold")
         o.wgrad = self._wrap(self.orig[2], lambda dy, x, *a, **kw: (dy.shape[1], x.shape[1], dy.shape[0]), "wgrad")
+        o.gemm_stats = self._wrap(self.orig[3], lambda a_, w, *a, **kw: (a_.shape[0], w.shape[0], a_.shape[1]), "gemm")
         return self
 
     def __exit__(self, *exc):
-        self.ops.gemm, self.ops.gemm_lnfold, self.ops.wgrad = self.orig
+        self.ops.gemm, self.ops.gemm_lnfold, self.ops.wgrad, self.ops.gemm_stats = self.orig
 
 
 def gemm_roofline(torch, step, peaks):

@@ -25,6 +25,10 @@ SIGNATURES = {
     "vlk_row_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "vlk_gemm_bf16_lnfold": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_int, c_void_p],
+    "vlk_gemm_bf16_lnfold_sums": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_float, c_void_p, c_int, c_void_p],
+    "vlk_gemm_bf16_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                            c_int, c_void_p, c_void_p],
     "vlk_colsum_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vlk_transpose_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,

@@ -13,9 +13,11 @@ attention kernel in place; the 14x14/14 patch convolution is an im2col + GEMM wi
 The tower is frozen, so every LayerNorm that feeds a Linear (layer_norm1 -> q/k/v, layer_norm2 -> fc1,
 post_layernorm -> visual_projection: 49 of the 50 norms) is FOLDED into that Linear's weights once
 (``ops.fold_layernorm``): the GEMM runs on the raw residual stream, the per-row mean / rstd come from a
-statistics-only kernel and are applied in the GEMM epilogue.  No normalised copy of the [B*257, 1024]
-activations is ever written or re-read (67 MB of HBM traffic per norm at B=64).  ``VLK_CLIP_NO_LNFOLD=1``
-restores the LayerNorm kernel + plain GEMM pair (cross-check).
+statistics-only kernel — or, from the second norm on, from row sums that the residual GEMM which wrote the
+stream accumulated in its own epilogue — and are applied in the GEMM epilogue.  No normalised copy of the
+[B*257, 1024] activations is ever written or re-read (67 MB of HBM traffic per norm at B=64).
+``VLK_CLIP_NO_LNFOLD=1`` restores the LayerNorm kernel + plain GEMM pair, ``VLK_CLIP_NO_FUSED_STATS=1`` the
+statistics kernel in front of every folded product (cross-checks).
 """
 import os
 
@@ -146,15 +148,31 @@ class ClipVisionTower(nn.Module):
         x = ops.clip_assemble(patch, self.cls, self.pos, B).view(B * 257, H)
         x, _, _ = ops.layernorm_fwd(x, self.pre_ln_w, self.pre_ln_b, self.eps, save_stats=False)
         if self._folded():
+            # the residual GEMMs (out_proj, fc2) also accumulate the row sums of what they write, so the next folded
+            # product needs no pass over x at all; only the very first norm reads its input (vlk_row_stats)
+            fused = H >= 96 and not os.environ.get("VLK_CLIP_NO_FUSED_STATS")
+            sums = torch.zeros((2 * self.n_layers, B * 257, 2), device=x.device, dtype=torch.float32) if fused else None
+            nxt = None                                   # statistics of the current x, when a GEMM produced them
             for i in range(self.n_layers):
                 wq, cq, bq = self._fq[i]
-                qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps, stats=ops.row_stats(x, self.eps)).view(B, 257, 3 * H)
+                if nxt is None:
+                    qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps, stats=ops.row_stats(x, self.eps))
+                else:
+                    qkv = ops.gemm_lnfold(x, wq, bq, cq, self.eps, sums=nxt)
+                qkv = qkv.view(B, 257, 3 * H)
                 a, _ = ops.attention_fwd(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], self.heads, False,
                                          need_lse=False)
-                x = ops.gemm(a.view(B * 257, H), self.out_w[i], bias=self.out_b[i], residual=x)
                 wf, cf, bf_ = self._ff[i]
-                f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu", stats=ops.row_stats(x, self.eps))
-                x = ops.gemm(f, self.fc2_w[i], bias=self.fc2_b[i], residual=x)
+                if fused:
+                    x = ops.gemm_stats(a.view(B * 257, H), self.out_w[i], self.out_b[i], x, sums[2 * i])
+                    f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu", sums=sums[2 * i])
+                    x = ops.gemm_stats(f, self.fc2_w[i], self.fc2_b[i], x, sums[2 * i + 1])
+                    nxt = sums[2 * i + 1]
+                else:
+                    x = ops.gemm(a.view(B * 257, H), self.out_w[i], bias=self.out_b[i], residual=x)
+                    f = ops.gemm_lnfold(x, wf, bf_, cf, self.eps, act="quick_gelu", stats=ops.row_stats(x, self.eps))
+                    x = ops.gemm(f, self.fc2_w[i], bias=self.fc2_b[i], residual=x)
+            self._last_sums = nxt
             return x.view(B, 257, H)
         for i in range(self.n_layers):
             h, _, _ = ops.layernorm_fwd(x, self.ln1_w[i], self.ln1_b[i], self.eps, save_stats=False)
@@ -174,6 +192,10 @@ class ClipVisionTower(nn.Module):
         x = self.hidden_states(pixel_values).view(B * 257, self.hidden)
         if self._folded():
             wp, cp, bp = self._fp
+            if getattr(self, "_last_sums", None) is not None:
+                y = ops.gemm_lnfold(x, wp, bp, cp, self.eps, sums=self._last_sums)
+                self._last_sums = None
+                return y.view(B, 257, self.proj_dim)
             return ops.gemm_lnfold(x, wp, bp, cp, self.eps, stats=ops.row_stats(x, self.eps)).view(B, 257, self.proj_dim)
         y, _, _ = ops.layernorm_fwd(x, self.post_ln_w, self.post_ln_b, self.eps, save_stats=False)
         return ops.gemm(y, self.proj_w).view(B, 257, self.proj_dim)

@@ -45,6 +45,11 @@ struct EpiParams {
     const float* ln_mean;
     const float* ln_rstd;
     const float* ln_colsum;
+    // ... or from the row sums (sum x, sum x^2) that the PRODUCING GEMM accumulated (stats_out of the residual GEMM
+    // that wrote x): mean = s1 / K, rstd = rsqrt(s2 / K - mean^2 + eps)
+    const float* ln_sums;
+    float ln_inv_k, ln_eps;
+    float* stats_out;   // [M][2] fp32, accumulated with atomicAdd: row sums of the bf16-ROUNDED outputs and of their squares
     int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 };
 
@@ -67,8 +72,16 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * ep.alpha;
 
-    if (ep.ln_mean != nullptr) {  // LayerNorm folded into the weights (narrow-tile path)
-        const float mu = __ldg(ep.ln_mean + row), rs = __ldg(ep.ln_rstd + row);
+    if (ep.ln_colsum != nullptr) {  // LayerNorm folded into the weights (narrow-tile path)
+        float mu, rs;
+        if (ep.ln_sums != nullptr) {
+            const float2 s12 = __ldg(reinterpret_cast<const float2*>(ep.ln_sums) + row);
+            mu = s12.x * ep.ln_inv_k;
+            rs = rsqrtf(fmaxf(s12.y * ep.ln_inv_k - mu * mu, 0.f) + ep.ln_eps);
+        } else {
+            mu = __ldg(ep.ln_mean + row);
+            rs = __ldg(ep.ln_rstd + row);
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (i < ncols_valid) v[i] = rs * (v[i] - mu * __ldg(ep.ln_colsum + col0 + i));
@@ -236,7 +249,7 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* 
 // time inside the unrolled loops the kernel was 12.6 k SASS instructions (erff alone is inlined 64 times) and the
 // epilogue warps lost ~15 % of their issue slots to instruction-cache misses (`no_inst`,
 // profiles/r01_ncu_gemm_residual_source_summary.txt).  The dispatcher below picks one compact body per launch.
-template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF>
+template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF, int STATS = 0>
 __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                                 int ncols_warp, int M, int N, int lane, size_t d_off) {
     const int row = row0 + lane;
@@ -245,12 +258,20 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
     const bool has_res = RES < 0 ? (ep.residual != nullptr) : (RES != 0);
     const bool has_scale = SCALE < 0 ? (ep.scale != nullptr) : (SCALE != 0);
     const bool has_aux_out = AUX < 0 ? (ep.aux_out != nullptr) : (AUX != 0);
-    const bool ln_fold = LNF < 0 ? (ep.ln_mean != nullptr) : (LNF != 0);
+    const bool ln_fold = LNF < 0 ? (ep.ln_colsum != nullptr) : (LNF != 0);
     float ln_mu = 0.f, ln_rs = 1.f;
     if (ln_fold && row < M) {
-        ln_mu = __ldg(ep.ln_mean + row);
-        ln_rs = __ldg(ep.ln_rstd + row);
+        if (ep.ln_sums != nullptr) {
+            const float2 s12 = __ldg(reinterpret_cast<const float2*>(ep.ln_sums) + row);
+            ln_mu = s12.x * ep.ln_inv_k;
+            ln_rs = rsqrtf(fmaxf(s12.y * ep.ln_inv_k - ln_mu * ln_mu, 0.f) + ep.ln_eps);
+        } else {
+            ln_mu = __ldg(ep.ln_mean + row);
+            ln_rs = __ldg(ep.ln_rstd + row);
+        }
     }
+    const bool stats = STATS < 0 ? (ep.stats_out != nullptr) : (STATS != 0);
+    float st1 = 0.f, st2 = 0.f;
     const bool aux_direct = dact && has_res;  // both present: aux_in falls back to direct loads
     const float scale = has_scale ? __ldg(ep.scale) : 1.0f;
 #pragma unroll 1
@@ -341,7 +362,17 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
                     float t[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) t[i] = v[q * 8 + i];
-                    *reinterpret_cast<uint4*>(stage_at(buf, lane, h * 4 + q)) = pack8(t);
+                    const uint4 pk = pack8(t);
+                    if (stats && sweep == 1 && q * 8 < hcols) {   // statistics of what the consumer will actually read
+                        float rr[8];
+                        unpack8(pk, rr);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            st1 += rr[i];
+                            st2 = fmaf(rr[i], rr[i], st2);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(stage_at(buf, lane, h * 4 + q)) = pk;
                 }
             }
             __syncwarp();
@@ -349,6 +380,10 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
                              sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
             __syncwarp();
         }
+    }
+    if (stats && row < M) {
+        atomicAdd(ep.stats_out + 2 * static_cast<size_t>(row), st1);
+        atomicAdd(ep.stats_out + 2 * static_cast<size_t>(row) + 1, st2);
     }
 }
 
@@ -375,7 +410,9 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
 #define VLK_EPI_LN(ACT) \
     epilogue_warp_t<ACT, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
-    if (ep.ln_mean != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
+    if (ep.stats_out != nullptr) {  // residual GEMM that also produces the row statistics of its output
+        epilogue_warp_t<0, 0, -1, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+    } else if (ep.ln_colsum != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
         if (ep.act == VLK_ACT_QUICK_GELU) VLK_EPI_LN(VLK_ACT_QUICK_GELU);
         else if (ep.act == VLK_ACT_GELU_TANH) VLK_EPI_LN(VLK_ACT_GELU_TANH);
         else VLK_EPI_LN(VLK_ACT_NONE);
@@ -962,7 +999,8 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
                      int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
                      void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
                      int split_k, long long split_stride, int* split_used, void* stream,
-                     const float* ln_mean = nullptr, const float* ln_rstd = nullptr, const float* ln_colsum = nullptr) {
+                     const float* ln_mean = nullptr, const float* ln_rstd = nullptr, const float* ln_colsum = nullptr,
+                     const float* ln_sums = nullptr, float ln_eps = 0.f, float* stats_out = nullptr) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -1014,6 +1052,10 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     ep.ln_mean = ln_mean;
     ep.ln_rstd = ln_rstd;
     ep.ln_colsum = ln_colsum;
+    ep.ln_sums = ln_sums;
+    ep.ln_inv_k = 1.0f / static_cast<float>(K);
+    ep.ln_eps = ln_eps;
+    ep.stats_out = stats_out;
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
 
@@ -1093,4 +1135,24 @@ extern "C" int vlk_gemm_bf16_lnfold(const void* X, const void* Wf, void* D, int 
                 "vlk_gemm_bf16_lnfold: act=%d", act);
     return gemm_impl(X, Wf, D, M, N, K, ldx, ldw, ldd, 0, 0, bias, nullptr, 0, nullptr, nullptr, 0, nullptr, act, 0, 1.0f,
                      0, 1, 0, nullptr, stream, row_mean, row_rstd, col_sum);
+}
+
+extern "C" int vlk_gemm_bf16_lnfold_sums(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw,
+                                         int ldd, const void* bias, const float* row_sums, float eps,
+                                         const float* col_sum, int act, void* stream) {
+    VLK_REQUIRE(row_sums && col_sum, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16_lnfold_sums: null statistics");
+    VLK_REQUIRE(aligned16(col_sum) && (reinterpret_cast<uintptr_t>(row_sums) & 7u) == 0, VLK_ERR_ALIGNMENT,
+                "vlk_gemm_bf16_lnfold_sums: col_sum must be 16-byte, row_sums 8-byte aligned");
+    VLK_REQUIRE(act == VLK_ACT_NONE || act == VLK_ACT_QUICK_GELU || act == VLK_ACT_GELU_TANH, VLK_ERR_UNSUPPORTED,
+                "vlk_gemm_bf16_lnfold_sums: act=%d", act);
+    return gemm_impl(X, Wf, D, M, N, K, ldx, ldw, ldd, 0, 0, bias, nullptr, 0, nullptr, nullptr, 0, nullptr, act, 0, 1.0f,
+                     0, 1, 0, nullptr, stream, nullptr, nullptr, col_sum, row_sums, eps, nullptr);
+}
+
+extern "C" int vlk_gemm_bf16_stats(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                                   const void* bias, const void* residual, int ldr, float* stats_out, void* stream) {
+    VLK_REQUIRE(stats_out != nullptr, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16_stats: null stats_out");
+    VLK_REQUIRE(N >= 96, VLK_ERR_UNSUPPORTED, "vlk_gemm_bf16_stats: N=%d (needs the staged epilogue, N >= 96)", N);
+    return gemm_impl(A, B, D, M, N, K, lda, ldb, ldd, 0, 0, bias, residual, ldr, nullptr, nullptr, 0, nullptr, VLK_ACT_NONE,
+                     0, 1.0f, 0, 1, 0, nullptr, stream, nullptr, nullptr, nullptr, nullptr, 0.f, stats_out);
 }

@@ -204,15 +204,36 @@ def fold_layernorm(weight, bias, gamma, beta):
     return wf.contiguous(), colsum, biasf.to(BF16).contiguous()
 
 
-def gemm_lnfold(x2d, wf, biasf, colsum, eps=1e-5, act=None, stats=None):
+def gemm_stats(a, w, bias, residual, stats_out):
+    """bf16(a @ w^T + bias + residual), with the row sums (sum, sum of squares) of the rounded result accumulated into
+    ``stats_out`` [M, 2] fp32 (zeroed by the caller) by the same epilogue (vlk_gemm_bf16_stats)."""
+    _need_cuda(a, w, residual)
+    a, w, residual = _bf16c(a), _bf16c(w), _bf16c(residual)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=BF16)
+    check(_lib.load().vlk_gemm_bf16_stats(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), w.stride(0),
+                                          out.stride(0), _p(bias), residual.data_ptr(), residual.stride(0),
+                                          stats_out.data_ptr(), _stream()), "vlk_gemm_bf16_stats")
+    return out
+
+
+def gemm_lnfold(x2d, wf, biasf, colsum, eps=1e-5, act=None, stats=None, sums=None):
     """act(LayerNorm(x) @ W^T + b) computed as rstd * (x @ Wf^T - mean * colsum) + biasf on the RAW x
-    (vlk_gemm_bf16_lnfold); stats = (mean, rstd) may be passed when several products share one input."""
+    (vlk_gemm_bf16_lnfold).  The statistics are either ``stats`` = (mean, rstd) from row_stats (computed here when
+    omitted) or ``sums`` = [M, 2] row sums accumulated by the GEMM that produced x (gemm_stats)."""
     _need_cuda(x2d, wf)
     x2d = _bf16c(x2d)
     M, K = x2d.shape
     N = wf.shape[0]
-    mean, rstd = stats if stats is not None else row_stats(x2d, eps)
     out = torch.empty((M, N), device=x2d.device, dtype=BF16)
+    if sums is not None:
+        check(_lib.load().vlk_gemm_bf16_lnfold_sums(x2d.data_ptr(), wf.data_ptr(), out.data_ptr(), M, N, K, x2d.stride(0),
+                                                    wf.stride(0), out.stride(0), _p(biasf), sums.data_ptr(), float(eps),
+                                                    colsum.data_ptr(), ACT[act] if not isinstance(act, int) else act,
+                                                    _stream()), "vlk_gemm_bf16_lnfold_sums")
+        return out
+    mean, rstd = stats if stats is not None else row_stats(x2d, eps)
     check(_lib.load().vlk_gemm_bf16_lnfold(x2d.data_ptr(), wf.data_ptr(), out.data_ptr(), M, N, K, x2d.stride(0),
                                            wf.stride(0), out.stride(0), _p(biasf), mean.data_ptr(), rstd.data_ptr(),
                                            colsum.data_ptr(), ACT[act] if not isinstance(act, int) else act, _stream()),

@@ -90,6 +90,17 @@ int vlk_row_stats(const void* x, float* mean, float* rstd, int rows, int cols, f
 int vlk_gemm_bf16_lnfold(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw, int ldd,
                          const void* bias, const float* row_mean, const float* row_rstd, const float* col_sum,
                          int act, void* stream);
+/* The same with the statistics supplied as per-row sums: row_sums[m] = (sum_k x[m,k], sum_k x[m,k]^2), fp32 [M][2],
+ * as accumulated by the GEMM that PRODUCED x (vlk_gemm_bf16_stats): mean = s1/K, rstd = rsqrt(s2/K - mean^2 + eps).
+ * With both, a frozen pre-LN transformer block (CLIP: x += out_proj(..); fc1(LN(x))) needs no pass over x between
+ * the residual GEMM and the next product at all. */
+int vlk_gemm_bf16_lnfold_sums(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw, int ldd,
+                              const void* bias, const float* row_sums, float eps, const float* col_sum, int act,
+                              void* stream);
+/* D = bf16(A.B^T + bias + residual) and, in the same epilogue, stats_out[m] += (sum_n D[m,n], sum_n D[m,n]^2) over the
+ * bf16-rounded outputs (fp32 atomics into a caller-zeroed [M][2] buffer).  A [M,K], B [N,K]; N >= 96. */
+int vlk_gemm_bf16_stats(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                        const void* bias, const void* residual, int ldr, float* stats_out, void* stream);
 
 /* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
 int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);

@@ -164,6 +164,38 @@ def test_gemm_with_folded_layernorm(cuda, M, N, K, act):
     assert (out.float() - ref).abs().mean().item() <= 1.5 * (pair.float() - ref).abs().mean().item() + 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(16448, 1024, 1024), (2056, 1024, 4096), (300, 128, 64), (77, 264, 72)])
+def test_residual_gemm_produces_row_statistics(cuda, M, N, K):
+    """vlk_gemm_bf16_stats: same output as the plain residual GEMM, plus (sum, sum of squares) per row of the ROUNDED
+    output; and a folded-LayerNorm product fed with those sums agrees with the one fed by vlk_row_stats."""
+    from gpt2_vision_language_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * 0.05).bfloat16()
+    b = (torch.randn(N, device=cuda, generator=g) * 0.1).bfloat16()
+    res = torch.randn(M, N, device=cuda, generator=g)
+    res[::5] += 4.0
+    res = res.bfloat16()
+    sums = torch.zeros(M, 2, device=cuda)
+    out = ops.gemm_stats(a, w, b, res, sums)
+    assert torch.equal(out, ops.gemm(a, w, bias=b, residual=res))
+    of = out.float()
+    assert torch.allclose(sums[:, 0], of.sum(-1), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(sums[:, 1], (of * of).sum(-1), rtol=1e-4, atol=2e-2)
+    # consumer: LN folded into a following Linear, statistics from the sums vs from a pass over `out`
+    N2 = 256
+    w2 = (torch.randn(N2, N, device=cuda, generator=g) * 0.03).bfloat16()
+    gamma = (1 + 0.2 * torch.randn(N, device=cuda, generator=g)).bfloat16()
+    beta = (0.1 * torch.randn(N, device=cuda, generator=g)).bfloat16()
+    wf, colsum, biasf = ops.fold_layernorm(w2, None, gamma, beta)
+    y_sums = ops.gemm_lnfold(out, wf, biasf, colsum, 1e-5, act="quick_gelu", sums=sums)
+    y_stats = ops.gemm_lnfold(out, wf, biasf, colsum, 1e-5, act="quick_gelu")
+    ref = torch.nn.functional.layer_norm(of, (N,), gamma.float(), beta.float(), 1e-5) @ w2.float().t()
+    ref = ref * torch.sigmoid(1.702 * ref)
+    _check(y_sums, ref, tol=2e-2)
+    assert (y_sums.float() - y_stats.float()).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
 def test_gemm_rejects_bad_args(cuda):
     from gpt2_vision_language_b200 import ops
     a = torch.randn(16, 12, device=cuda).bfloat16()
