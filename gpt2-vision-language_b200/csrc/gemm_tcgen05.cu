@@ -388,6 +388,10 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
 }
 
 
+// SPECIALISE: the 256-wide kernels (every large product of the path) get the compact per-operand-set bodies; the
+// narrow-tile kernels (small problems: decode rows, tiny test shapes) keep one generic body — 20 fewer kernel
+// instantiations to carry six bodies each (build time, library size).
+template <bool SPECIALISE>
 __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                               int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
     if (ep.debug & 1) return;
@@ -410,6 +414,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
 #define VLK_EPI_LN(ACT) \
     epilogue_warp_t<ACT, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
+    if constexpr (!SPECIALISE) {
+        epilogue_warp_t<-1, -1, -1, -1, -1, -1, -1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+        return;
+    }
     if (ep.stats_out != nullptr) {  // residual GEMM that also produces the row statistics of its output
         epilogue_warp_t<0, 0, -1, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
     } else if (ep.ln_colsum != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
@@ -619,7 +627,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
+            epilogue_warp<false>(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
                           static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
@@ -805,7 +813,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
+            epilogue_warp<(BLOCK_N == 256)>(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
                           static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -976,10 +984,14 @@ int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, 
         if (bn == 256) return launch_2cta<256, 5, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
         return launch_2cta<128, 6, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
     }
-    if (cluster == 2) {
+#ifdef VLK_GEMM_MULTICAST_VARIANT   // single-CTA MMA with TMA multicast of B across a CTA pair: measured, never the
+    if (cluster == 2) {             // fastest (profiles/r01_gemm_sweep2.log); compiled only for that comparison
         if (bn == 256) return launch<256, 3, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, sms, stream);
         return launch<128, 5, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, sms, stream);
     }
+#else
+    if (cluster == 2) cluster = 1;
+#endif
     switch (bn) {
         case 256:
             return launch<256, 3, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
@@ -1074,6 +1086,9 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
         int v = atoi(f);
         if (v == 1 || ((v == 2 || v == 3) && bn >= 128 && sms % 2 == 0)) cluster = v;
     }
+#ifndef VLK_GEMM_MULTICAST_VARIANT
+    if (cluster == 2) cluster = 1;   // the multicast pair is not compiled in (see dispatch)
+#endif
 
     CUtensorMap ta, tb;
     int rc;
