@@ -179,7 +179,7 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
     mb, T = args.micro_batch, 1024
     accum = max(1, PRETRAIN_TOKENS_PER_STEP // (mb * T * world))
     step = PretrainStep(model, mb, T, accum, use_graph=not args.no_graph,
-                        overlap_comm=False if os.environ.get("VLK_NO_OVERLAP") else None)
+                        overlap_comm=False if os.environ.get("VLK_NO_OVERLAP") else None, zero1=args.zero1)
     g = torch.Generator().manual_seed(rank)
     x_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
     y_h = torch.randint(0, 50257, (accum, mb, T), generator=g).pin_memory()
@@ -245,7 +245,7 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, out=sys.stdo
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "GPT-2 124M pretraining step, T=1024, AdamW, clip 1.0, grad accumulation",
-                   "tokens_per_step": tokens, "micro_batch": mb, "seq_len": T, "grad_accum_per_rank": accum,
+                   "tokens_per_step": tokens, "micro_batch": mb, "seq_len": T, "grad_accum_per_rank": accum, "zero1": bool(args.zero1),
                    "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "overlap_comm": bool(getattr(step, "overlap", False)),
                    "l2": "no explicit flush: 250 MB of weights + GBs of activations per micro-step >> 126 MB L2"},
         "algorithmic_tflops": tflop / (ms * 1e-3), "frac_of_bf16_sustained_peak": tflop / (ms * 1e-3) / peak / world,
@@ -495,6 +495,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=16, help="pretrain micro-batch (train_gpt2.py:245: B = 16)")
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (the reference's B is per rank)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--zero1", action="store_true", help="pretrain: ZeRO-1 update (reduce-scatter / sharded AdamW / all-gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record).  Everything else that libraries print on the way goes to

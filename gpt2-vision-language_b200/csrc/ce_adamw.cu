@@ -165,17 +165,56 @@ adamw_kernel(const vlk_tensor_desc* __restrict__ table, const float* __restrict_
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, step));
     const float step_size = lr / bc1;
     const float decay = 1.0f - lr * d.weight_decay;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < d.numel;
+    auto update = [&](float gi, float& pi, float& mi, float& vi) {
+        gi *= clip;
+        pi *= decay;
+        mi = beta1 * mi + (1.0f - beta1) * gi;
+        vi = beta2 * vi + (1.0f - beta2) * gi * gi;
+        pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    };
+    // 16-byte accesses on all four streams (14 B/param of HBM traffic in bf16); unaligned views and the tail of a
+    // tensor whose size is not a multiple of the vector width take the scalar loop
+    constexpr int VEC = 16 / sizeof(T);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                           reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
+    const long long nvec = aligned ? d.numel / VEC : 0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float gi = ld1<T>(g, i) * clip;
-        float pi = ld1<T>(p, i) * decay;
-        const float mi = beta1 * ld1<T>(m, i) + (1.0f - beta1) * gi;
-        const float vi = beta2 * ld1<T>(v, i) + (1.0f - beta2) * gi * gi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        pi -= step_size * (mi / denom);
-        st1(p, i, pi);
-        st1(m, i, mi);
-        st1(v, i, vi);
+        const uint4 ug = ldg16(g + i * VEC);
+        const uint4 up = *reinterpret_cast<const uint4*>(p + i * VEC);
+        const uint4 um = *reinterpret_cast<const uint4*>(m + i * VEC);
+        const uint4 uv = *reinterpret_cast<const uint4*>(v + i * VEC);
+        if constexpr (sizeof(T) == 2) {
+            float fg[8], fp[8], fm[8], fv[8];
+            unpack8(ug, fg);
+            unpack8(up, fp);
+            unpack8(um, fm);
+            unpack8(uv, fv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) update(fg[k], fp[k], fm[k], fv[k]);
+            *reinterpret_cast<uint4*>(p + i * VEC) = pack8(fp);
+            *reinterpret_cast<uint4*>(m + i * VEC) = pack8(fm);
+            *reinterpret_cast<uint4*>(v + i * VEC) = pack8(fv);
+        } else {
+            float4 fg = *reinterpret_cast<const float4*>(&ug), fp = *reinterpret_cast<const float4*>(&up);
+            float4 fm = *reinterpret_cast<const float4*>(&um), fv = *reinterpret_cast<const float4*>(&uv);
+            update(fg.x, fp.x, fm.x, fv.x);
+            update(fg.y, fp.y, fm.y, fv.y);
+            update(fg.z, fp.z, fm.z, fv.z);
+            update(fg.w, fp.w, fm.w, fv.w);
+            *reinterpret_cast<float4*>(p + i * VEC) = fp;
+            *reinterpret_cast<float4*>(m + i * VEC) = fm;
+            *reinterpret_cast<float4*>(v + i * VEC) = fv;
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * VEC + threadIdx.x; i < d.numel; i += blockDim.x) {
+            float pi = ld1<T>(p, i), mi = ld1<T>(m, i), vi = ld1<T>(v, i);
+            update(ld1<T>(g, i), pi, mi, vi);
+            st1(p, i, pi);
+            st1(m, i, mi);
+            st1(v, i, vi);
+        }
     }
 }
 

@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    def __init__(self, params, extra_slots=0):
+    def __init__(self, params, extra_slots=0, pad_multiple=1):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -30,6 +30,8 @@ class FlatGradBucket:
             total += (p.numel() + align - 1) // align * align
         self.extra_off = total
         total += (extra_slots + align - 1) // align * align
+        total = (total + pad_multiple - 1) // pad_multiple * pad_multiple   # ZeRO-1: equal, 16-byte aligned shards
+        self.sizes = [p.numel() for p in self.params]
         self.flat = torch.zeros(total, dtype=dtype, device=device)
         self.offsets = {id(p): o for p, o in zip(self.params, offs)}
         for p, o in zip(self.params, offs):
@@ -56,6 +58,33 @@ class FlatGradBucket:
                 dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
                 buf.copy_(tmp / dist.get_world_size(group))
         return self.flat
+
+
+class FlatParamBucket:
+    """The trainable parameters re-pointed into ONE contiguous buffer with exactly the layout of a FlatGradBucket
+    (``p.data`` become views; values are preserved).  Gradient element i and parameter element i then belong to the
+    same weight, which is what lets a rank update an arbitrary [lo, hi) slice (ZeRO-1) and all-gather the result."""
+
+    def __init__(self, grad_bucket):
+        g = grad_bucket
+        self.flat = torch.zeros_like(g.flat)
+        with torch.no_grad():
+            for p in g.params:
+                o = g.offset_of(p)
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+
+
+def shard_segments(offsets, numels, weight_decays, lo, hi):
+    """Intersections of the flat range [lo, hi) with the tensors laid out at ``offsets``:
+    -> [(start, length, weight_decay)] in flat coordinates.  Pure arithmetic (tested on CPU)."""
+    out = []
+    for o, n, wd in zip(offsets, numels, weight_decays):
+        a, b = max(o, lo), min(o + n, hi)
+        if a < b:
+            out.append((a, b - a, wd))
+    return out
 
 
 def broadcast_parameters(module, src=0, group=None):

@@ -127,3 +127,103 @@ class FusedAdamW(torch.optim.Optimizer):
                     self._step_t = st["step"].detach().float().reshape(1).clone()
                 st["step"] = self._step_t
         self._table_key = None
+
+
+class Zero1AdamW:
+    """ZeRO-1 flavour of the fused clip + AdamW for the data-parallel pretraining step: instead of
+    all-reducing the 249 MB gradient bucket and running the full 1.7 GB/step optimizer pass on every rank, the flat
+    gradient is REDUCE-SCATTERED (each rank receives the average of its 1/N slice), the rank updates only that slice of
+    the flat parameter buffer (moments exist for the slice only: optimizer state and traffic / N) and the updated
+    slices are ALL-GATHERED.  Same bytes on the wire as the all-reduce; same arithmetic as FusedAdamW per element
+    (decoupled weight decay per tensor, bias correction, clip by the global norm = all-reduced sum of the slices'
+    squared norms).  The phases are separate methods so they can be driven without a process group (tests)."""
+
+    def __init__(self, grad_bucket, param_bucket, weight_decays, lr=6e-4, betas=(0.9, 0.95), eps=1e-8, rank=0, world=1,
+                 group=None):
+        from .dp import shard_segments
+        g = grad_bucket
+        total = g.flat.numel()
+        if total % (8 * world):
+            raise ValueError("flat bucket must be padded to a multiple of 8 * world (FlatGradBucket(pad_multiple=...))")
+        self.g, self.p, self.rank, self.world, self.group = g, param_bucket, rank, world, group
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.S = total // world
+        self.lo, self.hi = rank * self.S, (rank + 1) * self.S
+        dev, dt = g.flat.device, g.flat.dtype
+        self.gshard = torch.zeros(self.S, device=dev, dtype=dt)
+        self.exp_avg = torch.zeros(self.S, device=dev, dtype=dt)
+        self.exp_avg_sq = torch.zeros(self.S, device=dev, dtype=dt)
+        offs = [g.offset_of(q) for q in g.params]
+        self.segments = shard_segments(offs, g.sizes, weight_decays, self.lo, self.hi)
+        esz = g.flat.element_size()
+        arr = (TensorDesc * max(1, len(self.segments)))()
+        for i, (a, n, wd) in enumerate(self.segments):
+            k = a - self.lo
+            arr[i] = TensorDesc(self.p.flat.data_ptr() + a * esz, self.gshard.data_ptr() + k * esz,
+                                self.exp_avg.data_ptr() + k * esz, self.exp_avg_sq.data_ptr() + k * esz, n, float(wd), 0)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(dev)
+        self.n = len(self.segments)
+        self.max_numel = max((n for _, n, _ in self.segments), default=1)
+        self.fp32 = dt == torch.float32
+        self.norm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_t = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    # ---- phases ------------------------------------------------------------------------------------------
+    def reduce_scatter(self):
+        """gshard <- average over ranks of flat_grad[lo:hi]."""
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_initialized():
+            if dist.get_backend(self.group) == "nccl":
+                dist.reduce_scatter_tensor(self.gshard, self.g.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:   # gloo: no reduce-scatter / AVG / bf16 arithmetic
+                tmp = self.g.flat.float()
+                dist.all_reduce(tmp, group=self.group)
+                self.gshard.copy_(tmp[self.lo:self.hi] / self.world)
+        else:
+            self.gshard.copy_(self.g.flat[self.lo:self.hi])
+
+    @torch.no_grad()
+    def local_sumsq(self):
+        self.norm_sq.zero_()
+        if self.n:
+            check(_lib.load().vlk_grad_sumsq(self.table.data_ptr(), self.n, self.max_numel, int(self.fp32),
+                                             self.norm_sq.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                  "vlk_grad_sumsq")
+        return self.norm_sq
+
+    @torch.no_grad()
+    def apply(self, norm_sq, max_norm):
+        """AdamW on this rank's slice with the clip factor of the GLOBAL norm (norm_sq: 1-element fp32 tensor)."""
+        self.step_t += 1
+        self.lr_t.fill_(float(self.lr))
+        if self.n:
+            b1, b2 = self.betas
+            check(_lib.load().vlk_adamw_step(self.table.data_ptr(), self.n, self.max_numel, int(self.fp32),
+                                             norm_sq.data_ptr() if max_norm > 0 else 0, float(max_norm),
+                                             self.lr_t.data_ptr(), float(b1), float(b2), float(self.eps),
+                                             self.step_t.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                  "vlk_adamw_step")
+
+    def all_gather(self):
+        import torch.distributed as dist
+        if self.world > 1 and dist.is_initialized():
+            shard = self.p.flat[self.lo:self.hi]
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(self.p.flat, shard, group=self.group)
+            else:
+                parts = [torch.empty_like(shard) for _ in range(self.world)]
+                dist.all_gather(parts, shard.clone(), group=self.group)
+                self.p.flat.copy_(torch.cat(parts))
+
+    def step(self, max_norm=1.0):
+        """One optimizer step over the gradients currently in the flat bucket; returns the pre-clip global norm."""
+        import torch.distributed as dist
+        self.reduce_scatter()
+        nsq = self.local_sumsq()
+        if self.world > 1 and dist.is_initialized():
+            dist.all_reduce(nsq, group=self.group)
+        self.apply(nsq, max_norm)
+        self.all_gather()
+        return nsq.sqrt().reshape(())

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from . import ops
 from .caption import pool_clip_197_to_33_avg_with_cls
-from .dp import FlatGradBucket
+from .dp import FlatGradBucket, FlatParamBucket
 
 
 def _gpt_split_forward(model, idx, targets, split):
@@ -283,8 +283,11 @@ class PretrainStep:
     slots) and one update (all-reduce + clip + AdamW)."""
 
     def __init__(self, model, micro_batch=16, seq=1024, grad_accum=32, lr=6e-4, weight_decay=0.1, max_norm=1.0,
-                 use_graph=True, group=None, overlap_comm=None):
-        """overlap_comm (default: on when data parallel): the LAST micro-step's backward is cut in the middle of the
+                 use_graph=True, group=None, overlap_comm=None, zero1=False):
+        """zero1: ZeRO-1 update (optim.Zero1AdamW) — the gradient bucket is reduce-scattered, every rank runs clip +
+        AdamW on its 1/N slice of a flat parameter buffer (moments for that slice only), the slices are all-gathered.
+        The update then runs eagerly (three collectives + two kernels per step); overlap_comm is ignored.
+        overlap_comm (default: on when data parallel): the LAST micro-step's backward is cut in the middle of the
         stack; the all-reduce of layers n/2.. + ln_f (half of the 249 MB) runs on a second stream under the lower
         half of that backward, the rest (layers 0..n/2-1, wte — whose gradient also collects the lm_head's —, wpe)
         follows.  DDP overlaps the same way with 25 MiB buckets (train_gpt2.py:467-468 enables the sync on the last
@@ -299,21 +302,35 @@ class PretrainStep:
         self.y = torch.zeros(micro_batch, seq, device=dev, dtype=torch.int64)
         self.loss = torch.zeros((), device=dev, dtype=torch.float32)
         self.norm = torch.zeros((), device=dev, dtype=torch.float32)
-        self.bucket = FlatGradBucket(model.parameters())
-        self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
+        self.zero1 = bool(zero1)
+        if self.zero1:
+            from .optim import Zero1AdamW
+            world = dist.get_world_size(group) if self._multi_static(group) else 1
+            rank = dist.get_rank(group) if world > 1 else 0
+            self.bucket = FlatGradBucket(model.parameters(), pad_multiple=8 * world)
+            self.pbucket = FlatParamBucket(self.bucket)
+            wds = [weight_decay if p.dim() >= 2 else 0.0 for p in self.bucket.params]   # train_gpt2.py:131-136
+            self.opt = Zero1AdamW(self.bucket, self.pbucket, wds, lr=lr, rank=rank, world=world, group=group)
+        else:
+            self.bucket = FlatGradBucket(model.parameters())
+            self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
         self.g_micro = self.g_update = self.g_last = None
         self._warm = 0
         if overlap_comm is None:
             overlap_comm = self._multi()
-        self.overlap = bool(overlap_comm)
+        self.overlap = bool(overlap_comm) and not self.zero1
         if self.overlap:
             self.split = len(model.transformer.h) // 2
             self.upper = _upper_range(self.bucket, model.transformer.h, self.split)
             self.comm = _CommOverlap()
             self._cut = None
 
+    @staticmethod
+    def _multi_static(group):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
     def _multi(self):
-        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        return self._multi_static(self.group)
 
     def _micro(self):
         _, loss = self.model(self.x, self.y)
@@ -345,15 +362,22 @@ class PretrainStep:
 
     def _exchange(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            self.bucket.all_reduce(self.group)
+            if not self.zero1:                       # ZeRO-1 reduce-scatters inside its update instead
+                self.bucket.all_reduce(self.group)
             dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
             self.loss.div_(dist.get_world_size(self.group))
 
     def _update(self):
+        if self.zero1:
+            self.norm.copy_(self.opt.step(self.max_norm))
+            return
         self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
         self.opt.step()
 
     def set_lr(self, lr):
+        if self.zero1:
+            self.opt.lr = lr
+            return
         for g in self.opt.param_groups:
             g["lr"] = lr
 
@@ -407,8 +431,9 @@ class PretrainStep:
                 with torch.cuda.graph(self.g_last[1], pool=self.g_last[0].pool()):
                     self._last_phase2()
             self.g_update = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_update):
-                self._update()
+            if not self.zero1:                       # the ZeRO-1 update holds collectives: it runs eagerly
+                with torch.cuda.graph(self.g_update):
+                    self._update()
         if self.overlap:
             for i in range(self.grad_accum - 1):
                 self._set_slot(i)
@@ -423,5 +448,8 @@ class PretrainStep:
                 self._set_slot(i)
                 self.g_micro.replay()
             self._exchange()
-        self.g_update.replay()
+        if self.zero1:
+            self._update()
+        else:
+            self.g_update.replay()
         return self.loss

@@ -106,3 +106,28 @@ def test_auto_split_k_heuristic(monkeypatch):
     assert ops.auto_split_k(16384, 768, 50304) == 1      # 192 tiles already cover the GPU
     assert ops.auto_split_k(50304, 768, 16384) == 1
     assert ops.auto_split_k(768, 768, 1024) == 1         # short contraction: not worth a second pass
+
+
+def test_zero1_shard_segments_cover_every_element_once():
+    """dp.shard_segments: the N slices of the flat bucket, intersected with the tensor layout, tile every tensor
+    exactly once and carry that tensor's weight decay."""
+    from gpt2_vision_language_b200.dp import shard_segments
+    numels = [50304 * 8, 1024 * 8, 7, 24, 2304 * 8, 1]
+    wds = [0.1, 0.1, 0.0, 0.0, 0.1, 0.0]
+    offs, total = [], 0
+    for n in numels:
+        offs.append(total)
+        total += (n + 7) // 8 * 8
+    for world in (1, 2, 3, 8):
+        padded = (total + 8 * world - 1) // (8 * world) * (8 * world)
+        S = padded // world
+        cover = torch.zeros(padded, dtype=torch.int32)
+        wd_of = torch.full((padded,), -1.0)
+        for r in range(world):
+            for a, n, wd in shard_segments(offs, numels, wds, r * S, (r + 1) * S):
+                assert r * S <= a and a + n <= (r + 1) * S
+                cover[a:a + n] += 1
+                wd_of[a:a + n] = wd
+        for o, n, wd in zip(offs, numels, wds):
+            assert (cover[o:o + n] == 1).all() and (wd_of[o:o + n] == wd).all()
+        assert int(cover.sum()) == sum(numels)            # padding belongs to no segment

@@ -170,3 +170,63 @@ def test_split_backward_overlap_path_matches_monolithic(cuda, use_graph):
     assert out[True][1] == pytest.approx(out[False][1], rel=2e-2)
     assert (out[True][2] - out[False][2]).abs().max().item() < 2e-2
     assert out[False][0][-1] < out[False][0][0]
+
+
+def test_zero1_update_matches_full_update(cuda):
+    """ZeRO-1 (reduce-scatter / sharded clip+AdamW / all-gather) against the replicated FusedAdamW on one GPU:
+    (a) PretrainStep(zero1=True) at world size 1 reproduces the regular step; (b) three FAKE ranks, each owning a
+    third of the flat bucket, driven phase by phase (the collectives replaced by local copies), end with exactly the
+    parameters of the replicated update — shard boundaries cut through tensors with different weight decay."""
+    from gpt2_vision_language_b200 import gpt2
+    from gpt2_vision_language_b200.dp import FlatGradBucket, FlatParamBucket
+    from gpt2_vision_language_b200.optim import Zero1AdamW
+    from gpt2_vision_language_b200.step import PretrainStep
+    g = load("gpt2_tiny.pt")
+    gen = torch.Generator().manual_seed(3)
+    accum, mb, T = 2, 2, 24
+    xs = torch.randint(0, 256, (accum, mb, T), generator=gen).to(cuda)
+    ys = torch.randint(0, 256, (accum, mb, T), generator=gen).to(cuda)
+
+    def fresh():
+        m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+        m.load_state_dict(g["sd"])
+        return m.to(cuda).to(torch.bfloat16)
+    # (a)
+    out = {}
+    for z in (False, True):
+        m = fresh()
+        st = PretrainStep(m, micro_batch=mb, seq=T, grad_accum=accum, lr=3e-3, use_graph=True, zero1=z)
+        st.load_tokens(xs, ys)
+        losses = [st.run().item() for _ in range(4)]
+        out[z] = (losses, st.norm.item(), torch.cat([p.detach().float().flatten() for p in m.parameters()]))
+    assert out[True][0] == pytest.approx(out[False][0], rel=2e-3)
+    assert out[True][1] == pytest.approx(out[False][1], rel=1e-2)
+    assert (out[True][2] - out[False][2]).abs().max().item() < 1e-2
+    # (b) identical gradients on three fake ranks
+    world = 3
+    ref = fresh()
+    ref_bucket = FlatGradBucket(ref.parameters())
+    ref_opt = ref.configure_optimizers(0.1, 3e-3, "cuda")
+    m = fresh()
+    bucket = FlatGradBucket(m.parameters(), pad_multiple=8 * world)
+    pb = FlatParamBucket(bucket)
+    wds = [0.1 if p.dim() >= 2 else 0.0 for p in bucket.params]
+    ranks = [Zero1AdamW(bucket, pb, wds, lr=3e-3, rank=r, world=world) for r in range(world)]
+    assert len({(z.lo, z.hi) for z in ranks}) == world and sum(len(z.segments) for z in ranks) >= len(bucket.params)
+    for it in range(3):
+        for mod, bk in ((ref, ref_bucket), (m, bucket)):
+            bk.zero()
+            _, loss = mod(xs[it % accum], ys[it % accum])
+            loss.backward()
+        assert torch.equal(bucket.flat[: ref_bucket.flat.numel()], ref_bucket.flat)
+        norm_ref = ref_opt.clip_grad_norm(1.0)
+        ref_opt.step()
+        total = torch.zeros(1, device=cuda)
+        for z in ranks:                       # reduce-scatter of identical gradients = take the slice
+            z.gshard.copy_(bucket.flat[z.lo:z.hi])
+            total += z.local_sumsq()
+        assert total.sqrt().item() == pytest.approx(norm_ref.item(), rel=1e-4)
+        for z in ranks:
+            z.apply(total, 1.0)                # the all-gather is implicit: all fake ranks share the flat buffer
+        for (n1, p1), (n2, p2) in zip(ref.named_parameters(), m.named_parameters()):
+            assert n1 == n2 and torch.equal(p1, p2), n1
