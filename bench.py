@@ -123,7 +123,7 @@ def run_reference(args, out=sys.stdout):
     torch.set_num_threads(cores)
     step_fn = build_cpu_problem(torch, args.workload)
     t1 = time_cpu(torch, step_fn, 1, 1, 1)                       # probe: seconds per sample
-    budget = 150.0
+    budget = float(os.environ.get("VLK_BENCH_CPU_BUDGET_S", "150"))   # seconds of CPU work for the whole run
     B = int(max(1, min(64, budget / max(t1, 1e-3) / (args.steps + args.warmup))))
     dt = time_cpu(torch, step_fn, B, args.steps, args.warmup)
     v = B / dt
