@@ -172,3 +172,40 @@ def load_checkpoint(path, raw_model, optimizer=None, map_location="cpu", strict=
     if optimizer is not None and isinstance(ckpt, dict) and ckpt.get("optimizer") is not None:
         optimizer.load_state_dict(ckpt["optimizer"])
     return int(ckpt.get("step", 0)) + 1 if isinstance(ckpt, dict) else 0
+
+
+class CaptionFeatureDataset:
+    """(x, y, mask, z) items exactly as ``CocoClipFullTokensDataset.__getitem__`` builds them
+    (source/gpt2_linear/data.py:51-63): one of the image's captions is drawn at random (``random.choice``), encoded
+    with ``encode_caption_ids`` and paired with the image's pre-computed CLIP tokens ``z [257, D]`` from the shard
+    cache.  The COCO annotation reader and the tokenizer stay outside (control plane): ``captions[i]`` is the list of
+    already-tokenised captions of image i."""
+
+    def __init__(self, tokens_dir, captions, max_len=32, eot=EOT, seed=None):
+        import random
+        self.features = ClipTokenShards(tokens_dir)
+        if len(self.features) != len(captions):
+            raise AssertionError("index.json length mismatch with the caption list")      # data.py:29
+        self.captions, self.max_len, self.eot = captions, max_len, eot
+        self.rng = random.Random(seed)
+
+    def __len__(self):
+        return len(self.captions)
+
+    def __getitem__(self, idx):
+        x, y, m = encode_caption_ids(self.rng.choice(self.captions[idx]), self.max_len, self.eot)
+        return x, y, m, self.features[idx]
+
+
+def caption_batches(dataset, batch_size, indices=None, pin=True, drop_last=True):
+    """Batches (x [B,T], y [B,T], mask [B,T] bool, z [B,257,D]) as pinned host tensors — what the train loop moves to
+    the device at the top of a step (source/gpt2_linear/train.py:297-303); feed them to ``step.HostBatchFeeder`` /
+    ``pool_clip_197_to_33_avg_with_cls`` or straight to a captioner."""
+    idx = list(range(len(dataset))) if indices is None else list(indices)
+    for s in range(0, len(idx), batch_size):
+        chunk = idx[s:s + batch_size]
+        if len(chunk) < batch_size and drop_last:
+            return
+        items = [dataset[i] for i in chunk]
+        batch = tuple(torch.stack(col) for col in zip(*items))
+        yield tuple(t.pin_memory() for t in batch) if pin and torch.cuda.is_available() else batch

@@ -131,3 +131,33 @@ def test_zero1_shard_segments_cover_every_element_once():
         for o, n, wd in zip(offs, numels, wds):
             assert (cover[o:o + n] == 1).all() and (wd_of[o:o + n] == wd).all()
         assert int(cover.sum()) == sum(numels)            # padding belongs to no segment
+
+
+def test_caption_feature_dataset_items_and_batches(tmp_path):
+    """CocoClipFullTokensDataset.__getitem__ semantics on the shard cache: a random caption of the image, encoded with
+    the reference rule, next to that image's [257, D] tokens; batches stack them."""
+    g = torch.Generator().manual_seed(2)
+    feats = torch.randn(6, 257, 8, generator=g)
+    data.ClipTokenShards.write(str(tmp_path), [feats], rows_per_shard=4, dtype=torch.float32)
+    captions = [[[10 * i + k, 7, 8] + [9] * k for k in range(5)] for i in range(6)]
+    ds = data.CaptionFeatureDataset(str(tmp_path), captions, max_len=8, seed=0)
+    assert len(ds) == 6
+    seen = set()
+    for _ in range(30):
+        x, y, m, z = ds[3]
+        assert torch.equal(z, feats[3]) and x.shape == y.shape == m.shape == (7,)
+        first = int(x[0])
+        assert first in {30 + k for k in range(5)}                    # one of image 3's five captions
+        seen.add(first)
+        L = 3 + (first - 30) + 1                                      # caption length + EOT
+        assert m.sum().item() == max(min(L, 8) - 1, 1) and torch.equal(x[1:], y[:-1])
+    assert len(seen) > 1                                              # random.choice over the captions
+    batches = list(data.caption_batches(ds, 4, pin=False))
+    assert len(batches) == 1                                          # drop_last
+    x, y, m, z = batches[0]
+    assert x.shape == (4, 7) and m.dtype == torch.bool and z.shape == (4, 257, 8) and torch.equal(z, feats[:4])
+    try:
+        data.CaptionFeatureDataset(str(tmp_path), captions[:5])
+        raise SystemExit("length mismatch not detected")
+    except AssertionError:
+        pass
