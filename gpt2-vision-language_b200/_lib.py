@@ -20,6 +20,8 @@ SIGNATURES = {
     "vlk_gemm_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                       c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int,
                       c_int, c_void_p],
+    "vlk_gemm_bf16_tile": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_gemm_bf16_splitk": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_float, c_int, c_int, c_void_p],
     "vlk_row_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
@@ -46,7 +48,9 @@ SIGNATURES = {
                      c_float, c_void_p, ctypes.c_uint, c_void_p],
     "vlk_pool33_l2norm": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_embed_concat_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                             c_void_p],
+                             c_int, c_void_p],
+    "vlk_scalar_pack_digits": [c_void_p, c_void_p, c_int, c_void_p],
+    "vlk_scalar_unpack_digits": [c_void_p, c_void_p, c_int, c_void_p],
     "vlk_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_softmax_ce_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_ce_count": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],

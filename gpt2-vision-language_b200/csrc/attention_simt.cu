@@ -1,14 +1,13 @@
-// Scaled-dot-product attention, head dim 64, on the CUDA cores (fp32 math, online softmax).
-// This is the general kernel family: any Tq/Tk, causal or not, forward AND backward.  It serves the short
-// sequences of the captioning step (T = 31..64, launch-bound, a few GFLOP in total) and every backward pass.
-// The long forward case (CLIP, 257 keys) is served by the tcgen05 kernel in attention_tcgen05.cu.
+// Scaled-dot-product attention FORWARD, head dim 64, on the CUDA cores (fp32 math, online softmax) — the shapes the
+// tensor-core kernels do not take: a few query rows against a long key range (KV-cached decode beyond 64 cached
+// tokens; one warp group per row) and the general streaming kernel for Tq < 64 with Tk > 64.
+// Everything else runs on tcgen05: attention_pair.cu (Tq, Tk <= 64, forward + backward), attention_tcgen05.cu
+// (64 < Tk <= 272, the CLIP tower), attention_flash.cu (longer sequences, forward + backward).
 //
-// Addressing: element (b, t, h, d) of Q lives at q + b*q_bs + t*q_rs + h*64 + d (same for K, V, O and the
-// gradients), so packed c_attn / kv_proj / in_proj outputs are consumed without a head transpose.
-#include <cstdlib>
-#include <cstring>
-
+// Addressing: element (b, t, h, d) of Q lives at q + b*q_bs + t*q_rs + h*64 + d (same for K, V, O), so packed
+// c_attn / kv_proj / in_proj outputs are consumed without a head transpose.
 #include "common.cuh"
+
 
 namespace vlk {
 namespace {
@@ -136,206 +135,6 @@ attn_fwd_simt_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// backward, query side: delta_i = dO_i . O_i ;  dQ_i = scale * sum_j dS_ij K_j
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32)
-attn_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
-                   const bf16* __restrict__ o, const bf16* __restrict__ d_o, const float* __restrict__ lse,
-                   bf16* __restrict__ dq, float* __restrict__ delta, int H, int Tq, int Tk, Addr qa, Addr ka,
-                   Addr va, Addr oa, Addr dqa, int causal, float scale) {
-    __shared__ __align__(16) bf16 sK[TILE * LDS];
-    __shared__ __align__(16) bf16 sV[TILE * LDS];
-    __shared__ __align__(16) float sQ[ROWS_PER_BLOCK][D];
-    __shared__ __align__(16) float sdO[ROWS_PER_BLOCK][D];
-    __shared__ float sP[kWarps][TILE];
-
-    const int b = blockIdx.z, h = blockIdx.y;
-    const int q0 = blockIdx.x * ROWS_PER_BLOCK;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bf16* qb = q + b * qa.bs + h * D;
-    const bf16* kb = k + b * ka.bs + h * D;
-    const bf16* vb = v + b * va.bs + h * D;
-    const bf16* ob = o + b * oa.bs + h * D;
-    const bf16* dob = d_o + b * oa.bs + h * D;
-    const int shift = Tk - Tq;
-
-    for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * D; idx += blockDim.x) {
-        const int r = idx / D, d = idx % D;
-        const bool ok = q0 + r < Tq;
-        sQ[r][d] = ok ? __bfloat162float(qb[static_cast<size_t>(q0 + r) * qa.rs + d]) * scale : 0.f;
-        sdO[r][d] = ok ? __bfloat162float(dob[static_cast<size_t>(q0 + r) * oa.rs + d]) : 0.f;
-    }
-    __syncthreads();
-    constexpr int RPW = ROWS_PER_BLOCK / kWarps;
-    float dl[RPW], ls[RPW], acc0[RPW], acc1[RPW];
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int lr = warp * RPW + r, qi = q0 + lr;
-        acc0[r] = acc1[r] = 0.f;
-        dl[r] = 0.f;
-        ls[r] = 0.f;
-        if (qi < Tq) {
-            const float2 o2 = __bfloat1622float2(reinterpret_cast<const bf162*>(ob + static_cast<size_t>(qi) * oa.rs)[lane]);
-            dl[r] = warp_sum(o2.x * sdO[lr][2 * lane] + o2.y * sdO[lr][2 * lane + 1]);
-            ls[r] = lse[(static_cast<size_t>(b) * H + h) * Tq + qi];
-            if (lane == 0) delta[(static_cast<size_t>(b) * H + h) * Tq + qi] = dl[r];
-        }
-    }
-    int k_end = Tk;
-    if (causal) k_end = min(Tk, q0 + ROWS_PER_BLOCK + shift);
-    for (int kt = 0; kt < k_end; kt += TILE) {
-        __syncthreads();
-        stage_tile(sK, kb + static_cast<size_t>(kt) * ka.rs, ka.rs, min(TILE, Tk - kt));
-        stage_tile(sV, vb + static_cast<size_t>(kt) * va.rs, va.rs, min(TILE, Tk - kt));
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int lr = warp * RPW + r, qi = q0 + lr;
-            if (qi >= Tq) continue;
-            const int lim = causal ? min(Tk, qi + shift + 1) : Tk;
-            if (kt >= lim) continue;
-            float ds[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int j = hh * 32 + lane;
-                ds[hh] = 0.f;
-                if (kt + j < lim) {
-                    const float s = dot64(sQ[lr], sK + j * LDS);
-                    const float p = __expf(s - ls[r]);
-                    const float dp = dot64(sdO[lr], sV + j * LDS);
-                    ds[hh] = p * (dp - dl[r]);
-                }
-            }
-            __syncwarp();
-            sP[warp][lane] = ds[0];
-            sP[warp][32 + lane] = ds[1];
-            __syncwarp();
-            const int jmax = min(TILE, lim - kt);
-            float a0 = acc0[r], a1 = acc1[r];
-            for (int j = 0; j < jmax; ++j) {
-                const float w = sP[warp][j];
-                const uint32_t kw = reinterpret_cast<const uint32_t*>(sK + j * LDS)[lane];
-                const float2 k2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&kw));
-                a0 = fmaf(w, k2.x, a0);
-                a1 = fmaf(w, k2.y, a1);
-            }
-            acc0[r] = a0;
-            acc1[r] = a1;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int qi = q0 + warp * RPW + r;
-        if (qi >= Tq) continue;
-        bf16* row = dq + b * dqa.bs + static_cast<size_t>(qi) * dqa.rs + h * D;
-        reinterpret_cast<bf162*>(row)[lane] = __floats2bfloat162_rn(acc0[r] * scale, acc1[r] * scale);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// backward, key side: dV_j = sum_i P_ij dO_i ;  dK_j = scale * sum_i dS_ij Q_i
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32)
-attn_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
-                    const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
-                    bf16* __restrict__ dk, bf16* __restrict__ dv, int H, int Tq, int Tk, Addr qa, Addr ka, Addr va,
-                    Addr oa, Addr dka, Addr dva, int causal, float scale) {
-    __shared__ __align__(16) bf16 sQ[TILE * LDS];
-    __shared__ __align__(16) bf16 sdO[TILE * LDS];
-    __shared__ __align__(16) float sK[ROWS_PER_BLOCK][D];
-    __shared__ __align__(16) float sV[ROWS_PER_BLOCK][D];
-    __shared__ float sLse[TILE], sDelta[TILE];
-    __shared__ float sP[kWarps][TILE], sDS[kWarps][TILE];
-
-    const int b = blockIdx.z, h = blockIdx.y;
-    const int k0 = blockIdx.x * ROWS_PER_BLOCK;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bf16* qb = q + b * qa.bs + h * D;
-    const bf16* kb = k + b * ka.bs + h * D;
-    const bf16* vb = v + b * va.bs + h * D;
-    const bf16* dob = d_o + b * oa.bs + h * D;
-    const int shift = Tk - Tq;
-
-    for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * D; idx += blockDim.x) {
-        const int r = idx / D, d = idx % D;
-        const bool ok = k0 + r < Tk;
-        sK[r][d] = ok ? __bfloat162float(kb[static_cast<size_t>(k0 + r) * ka.rs + d]) * scale : 0.f;
-        sV[r][d] = ok ? __bfloat162float(vb[static_cast<size_t>(k0 + r) * va.rs + d]) : 0.f;
-    }
-    constexpr int RPW = ROWS_PER_BLOCK / kWarps;
-    float dk0[RPW], dk1[RPW], dv0[RPW], dv1[RPW];
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) dk0[r] = dk1[r] = dv0[r] = dv1[r] = 0.f;
-
-    // causal: key j is seen by queries i >= j - shift
-    int q_begin = 0;
-    if (causal) q_begin = max(0, k0 - shift) / TILE * TILE;
-    for (int qt = q_begin; qt < Tq; qt += TILE) {
-        __syncthreads();
-        stage_tile(sQ, qb + static_cast<size_t>(qt) * qa.rs, qa.rs, min(TILE, Tq - qt));
-        stage_tile(sdO, dob + static_cast<size_t>(qt) * oa.rs, oa.rs, min(TILE, Tq - qt));
-        for (int i = threadIdx.x; i < TILE; i += blockDim.x) {
-            const bool ok = qt + i < Tq;
-            sLse[i] = ok ? lse[(static_cast<size_t>(b) * H + h) * Tq + qt + i] : 0.f;
-            sDelta[i] = ok ? delta[(static_cast<size_t>(b) * H + h) * Tq + qt + i] : 0.f;
-        }
-        __syncthreads();
-        const int imax = min(TILE, Tq - qt);
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int lr = warp * RPW + r, kj = k0 + lr;
-            if (kj >= Tk) continue;
-            const int first = causal ? max(0, kj - shift) : 0;  // first query index that sees key kj
-            if (qt + imax <= first) continue;
-            float pv[2], dsv[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int i = hh * 32 + lane;
-                pv[hh] = 0.f;
-                dsv[hh] = 0.f;
-                if (i < imax && qt + i >= first) {
-                    const float s = dot64(sK[lr], sQ + i * LDS);  // scale folded into sK
-                    const float p = __expf(s - sLse[i]);
-                    const float dp = dot64(sV[lr], sdO + i * LDS);
-                    pv[hh] = p;
-                    dsv[hh] = p * (dp - sDelta[i]);
-                }
-            }
-            __syncwarp();
-            sP[warp][lane] = pv[0];
-            sP[warp][32 + lane] = pv[1];
-            sDS[warp][lane] = dsv[0];
-            sDS[warp][32 + lane] = dsv[1];
-            __syncwarp();
-            float a0 = dk0[r], a1 = dk1[r], c0 = dv0[r], c1 = dv1[r];
-            for (int i = max(0, first - qt); i < imax; ++i) {
-                const float p = sP[warp][i], w = sDS[warp][i];
-                const uint32_t qw = reinterpret_cast<const uint32_t*>(sQ + i * LDS)[lane];
-                const uint32_t gw = reinterpret_cast<const uint32_t*>(sdO + i * LDS)[lane];
-                const float2 q2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&qw));
-                const float2 g2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&gw));
-                a0 = fmaf(w, q2.x, a0);
-                a1 = fmaf(w, q2.y, a1);
-                c0 = fmaf(p, g2.x, c0);
-                c1 = fmaf(p, g2.y, c1);
-            }
-            dk0[r] = a0;
-            dk1[r] = a1;
-            dv0[r] = c0;
-            dv1[r] = c1;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int kj = k0 + warp * RPW + r;
-        if (kj >= Tk) continue;
-        bf16* rk = dk + b * dka.bs + static_cast<size_t>(kj) * dka.rs + h * D;
-        bf16* rv = dv + b * dva.bs + static_cast<size_t>(kj) * dva.rs + h * D;
-        reinterpret_cast<bf162*>(rk)[lane] = __floats2bfloat162_rn(dk0[r] * scale, dk1[r] * scale);
-        reinterpret_cast<bf162*>(rv)[lane] = __floats2bfloat162_rn(dv0[r], dv1[r]);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // forward for a handful of query rows (the 257th CLIP token left over after the 128-row tensor-core blocks):
@@ -472,90 +271,4 @@ int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* l
     VLK_CHECK_LAUNCH("vlk_attn_fwd(simt)");
     return VLK_OK;
 }
-
-bool attn_pair_applicable(int B, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs,
-                          int v_rs, long long o_bs, int o_rs);
-int attn_pair_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                  void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
-                  int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
-                  long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
-                  const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
-bool attn_small_applicable(int Tq, int Tk);
-int attn_small_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                   void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
-                   int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
-                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float dropout_p,
-                   const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
-
-int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
-                   void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
-                   int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
-                   long long dk_bs, int dk_rs, long long dv_bs, int dv_rs, int causal, float scale, float* delta,
-                   cudaStream_t stream);
-
 }  // namespace vlk
-
-using namespace vlk;
-
-extern "C" int vlk_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
-                            const float* lse, void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk,
-                            long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
-                            long long o_bs, int o_rs, long long dq_bs, int dq_rs, long long dk_bs, int dk_rs,
-                            long long dv_bs, int dv_rs, int causal, float scale, float* delta, float dropout_p,
-                            const unsigned long long* seed_state, unsigned int stream_id, void* stream) {
-    VLK_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed_state), VLK_ERR_INVALID_ARG,
-                "vlk_attn_bwd: dropout_p=%f needs a seed state", dropout_p);
-    VLK_REQUIRE(dropout_p == 0.f || attn_small_applicable(Tq, Tk), VLK_ERR_UNSUPPORTED,
-                "vlk_attn_bwd: attention dropout is only implemented for Tq, Tk <= 64 (the Q-Former shapes)");
-    VLK_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv && delta, VLK_ERR_INVALID_ARG,
-                "vlk_attn_bwd: null pointer");
-    VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_bwd: B=%d H=%d Tq=%d Tk=%d", B, H,
-                Tq, Tk);
-    VLK_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && dq_rs % 2 == 0 &&
-                    dk_rs % 2 == 0 && dv_rs % 2 == 0,
-                VLK_ERR_ALIGNMENT, "vlk_attn_bwd: row strides must be multiples of 8 elements");
-    VLK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(d_o), VLK_ERR_ALIGNMENT,
-                "vlk_attn_bwd: 16B alignment");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    {
-        const char* force = getenv("VLK_ATTN_IMPL");
-        if (attn_small_applicable(Tq, Tk) &&
-            (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0)))) {
-            if (!(force && strcmp(force, "small") == 0) &&
-                attn_pair_applicable(B, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs) && dq_rs % 8 == 0 &&
-                dk_rs % 8 == 0 && dv_rs % 8 == 0 && dq_bs % 8 == 0 && dk_bs % 8 == 0 && dv_bs % 8 == 0 && aligned16(dq) &&
-                aligned16(dk) && aligned16(dv))
-                return attn_pair_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
-                                     o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
-                                     seed_state, stream_id, s);
-            return attn_small_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs,
-                                  o_bs, o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, dropout_p,
-                                  seed_state, stream_id, s);
-        }
-    }
-    {
-        // everything longer than the one-CTA-per-head tile runs on the tensor cores (streaming tcgen05 backward)
-        const char* force = getenv("VLK_ATTN_IMPL");
-        const bool aligned = q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && dq_rs % 8 == 0 &&
-                             dk_rs % 8 == 0 && dv_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 &&
-                             o_bs % 8 == 0;
-        if (aligned && !(force && strcmp(force, "simt") == 0))
-            return attn_flash_bwd(q, k, v, o, d_o, lse, dq, dk, dv, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs,
-                                  o_rs, dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs, causal, scale, delta, s);
-    }
-    float* scratch = delta;
-    const dim3 gq((Tq + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
-    attn_bwd_dq_kernel<<<gq, kWarps * 32, 0, s>>>(
-        static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
-        static_cast<const bf16*>(o), static_cast<const bf16*>(d_o), lse, static_cast<bf16*>(dq), scratch, H, Tq, Tk,
-        Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, Addr{dq_bs, dq_rs}, causal, scale);
-    VLK_CHECK_LAUNCH("vlk_attn_bwd(dq)");
-    const dim3 gk((Tk + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, H, B);
-    attn_bwd_dkv_kernel<<<gk, kWarps * 32, 0, s>>>(
-        static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v),
-        static_cast<const bf16*>(d_o), lse, scratch, static_cast<bf16*>(dk), static_cast<bf16*>(dv), H, Tq, Tk,
-        Addr{q_bs, q_rs}, Addr{k_bs, k_rs}, Addr{v_bs, v_rs}, Addr{o_bs, o_rs}, Addr{dk_bs, dk_rs},
-        Addr{dv_bs, dv_rs}, causal, scale);
-    VLK_CHECK_LAUNCH("vlk_attn_bwd(dkv)");
-    return VLK_OK;
-}

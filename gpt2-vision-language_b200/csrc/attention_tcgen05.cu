@@ -1,278 +1,33 @@
 // Attention forward on the tcgen05 tensor cores for mid-length sequences (64 < Tk <= 272: the CLIP ViT-L/14
-// encoder has 257 tokens, 16 heads x 64).  One CTA = 128 query rows of one (batch, head):
+// encoder has 257 tokens, 16 heads x 64) — the persistent, warp-specialised kernel `attn_fwd_tcgen05_v4_kernel`:
 //
-//   TMA:  Q [128 x 64], K [Tk x 64], V [Tk x 64]  -> shared memory (128B swizzle, zero-filled past the sequence)
-//   MMA1: S = Q K^T            (M=128, N=Tk padded to 16, K=64; fp32 in TMEM, 272 columns)
+//   TMA:  Q [128 x 64] per query block, K / V [Tk x 64] once per (batch, head), double-buffered across units
+//         (128B swizzle, zero-filled past the sequence)
+//   MMA1: S = Q K^T            (M=128, N=256; fp32 in TMEM; the 257th key is handled on the CUDA cores)
 //   softmax: thread t owns TMEM lane t = one query row -> no cross-thread reduction at all;
-//            row max, exp2, row sum in registers; un-normalised P written as bf16 into a swizzled K-major
-//            shared-memory tile
-//   MMA2: O = P V              (M=128, N=64, K=Tk; V is fed as an MN-major B operand, i.e. no transpose)
+//            row max, exp2, row sum in registers; un-normalised bf16 P written IN PLACE over the score columns
+//   MMA2: O = P V              (A from TMEM, V as an MN-major B operand, i.e. no transpose)
 //   epilogue: O / rowsum -> bf16 -> global; optional log-sum-exp for the backward pass.
 //
-// The whole key range fits one tile, so there is no online-softmax rescaling here; sequences longer than 272
-// use the streaming kernel in attention_simt.cu.
+// The whole key range fits one tile, so there is no online-softmax rescaling here; longer sequences use the
+// streaming kernel in attention_flash.cu.  The entry point `attn_mid_fwd` is called by attention_api.cu.
 #include <cuda.h>
-#include <cstdlib>
-#include <cstring>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace vlk {
 
-int attn_fwd_simt(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
-                  long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                  int o_rs, int causal, float scale, cudaStream_t stream, int q_row0);
-
-bool attn_pair_applicable(int B, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs,
-                          int v_rs, long long o_bs, int o_rs);
-int attn_pair_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
-                  long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                  int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
-                  unsigned int stream_id, cudaStream_t stream);
-bool attn_small_applicable(int Tq, int Tk);
-int attn_small_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
-                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, float dropout_p, const unsigned long long* seed_state,
-                   unsigned int stream_id, cudaStream_t stream);
-
-int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
-                   long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, cudaStream_t stream);
-
-// bring-up instrumentation: per-phase %globaltimer stamps of the first CTAs (read back by vlk_debug_dump)
+#ifdef VLK_BRINGUP
+// bring-up instrumentation (never compiled into the shipped library): per-phase %globaltimer stamps of the first
+// tiles, read back by vlk_debug_dump
 __device__ long long g_attn_dbg[64 * 16];
-__device__ __forceinline__ void dbg_stamp(int enabled, int slot) {
-    if (enabled && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z < 32 && blockIdx.x == 0) {
-        long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_attn_dbg[blockIdx.z * 16 + slot] = t;
-    }
-}
+#endif
 
 namespace {
 
-constexpr int kMaxKeys = 272;
 constexpr int kQBytes = 128 * 128;                 // 128 rows x 64 bf16
-constexpr int kKVBytes = 35 * 1024;                // >= 272 rows x 128 B, multiple of 1024
-constexpr int kPSlabBytes = 128 * 128;             // 128 rows x 64 keys
-constexpr int kPSlabs = (kMaxKeys + 63) / 64;      // 5
-constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kQBytes;
-constexpr int kOffV = kOffK + kKVBytes;
-constexpr int kOffP = kOffV + kKVBytes;
-constexpr int kOffBar = kOffP + kPSlabs * kPSlabBytes;
-constexpr int kSmemBytes = kOffBar + 64 + 1024;    // barriers + tmem slot + alignment slack
-constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemO = 320;                   // O accumulator columns [320, 384)
 
-struct FwdParams {
-    bf16* o;
-    float* lse;
-    long long o_bs;
-    int o_rs;
-    int H, Tq, Tk, tkp, box_rows, causal;
-    float scale_log2e, scale;
-};
-
-__global__ void __launch_bounds__(128, 1)
-attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                        const __grid_constant__ CUtensorMap tmap_v, FwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + kOffBar);
-    uint64_t* bar_v = bar_qk + 1;
-    uint64_t* bar_s = bar_qk + 2;
-    uint64_t* bar_o = bar_qk + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int tkp = p.tkp;
-    const int n1 = tkp > 256 ? 256 : tkp, n2 = tkp - n1;
-
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&tmap_q);
-        ptx::prefetch_tensormap(&tmap_k);
-        ptx::prefetch_tensormap(&tmap_v);
-        ptx::mbar_init(bar_qk, 1);
-        ptx::mbar_init(bar_v, 1);
-        ptx::mbar_init(bar_s, 1);
-        ptx::mbar_init(bar_o, 1);
-        ptx::fence_barrier_init();
-    }
-    if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    if (threadIdx.x == 0) {
-        const int nbox = tkp / p.box_rows;  // 1 or 2
-        const uint32_t kv_bytes = static_cast<uint32_t>(tkp) * 128u;
-        ptx::mbar_arrive_expect_tx(bar_qk, kQBytes + kv_bytes);
-        ptx::tma_load_3d(smem + kOffQ, &tmap_q, bar_qk, h * 64, q0, b);
-        for (int i = 0; i < nbox; ++i)
-            ptx::tma_load_3d(smem + kOffK + i * p.box_rows * 128, &tmap_k, bar_qk, h * 64, i * p.box_rows, b);
-        ptx::mbar_arrive_expect_tx(bar_v, kv_bytes);
-        for (int i = 0; i < nbox; ++i)
-            ptx::tma_load_3d(smem + kOffV + i * p.box_rows * 128, &tmap_v, bar_v, h * 64, i * p.box_rows, b);
-
-        // ---- S = Q K^T ----
-        ptx::mbar_wait(bar_qk, 0);
-        ptx::tc_fence_after_sync();
-        const uint32_t sq = ptx::smem_u32(smem + kOffQ), sk = ptx::smem_u32(smem + kOffK);
-        const uint32_t idesc1 = ptx::make_idesc_bf16_f32(128, n1, 0, 0);
-        const uint32_t idesc2 = ptx::make_idesc_bf16_f32(128, n2 > 0 ? n2 : 16, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint64_t da = ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024);
-            ptx::umma_bf16_ss(tmem, da, ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc1, k != 0);
-            if (n2 > 0)
-                ptx::umma_bf16_ss(tmem + 256, da, ptx::make_smem_desc_sw128(sk + 256 * 128 + k * 32, 16, 1024), idesc2,
-                                  k != 0);
-        }
-        ptx::umma_commit(bar_s);
-    }
-
-    // ---- softmax: thread = query row = TMEM lane ----
-    ptx::mbar_wait(bar_s, 0);
-    ptx::tc_fence_after_sync();
-    const int row = threadIdx.x;                    // local query row
-    const int qi = q0 + row;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    int lim = p.Tk;                                 // keys [0, lim) are visible to this row
-    if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
-    if (lim < 1) lim = 1;                           // rows past Tq: keep the math finite, result is discarded
-    float m = -INFINITY;
-    for (int c = 0; c < tkp; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(trow + c, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
-    }
-    const float mb = m * p.scale_log2e;
-    float sum = 0.f;
-    uint8_t* prow = smem + kOffP + (row >> 3) * 1024 + (row & 7) * 128;
-    for (int c = 0; c < tkp; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(trow + c, r);
-        ptx::tmem_ld_wait();
-        float e[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            e[i] = (c + i < lim) ? exp2f(__uint_as_float(r[i]) * p.scale_log2e - mb) : 0.f;
-        }
-        // round to bf16 first so that the row sum matches what the tensor core will multiply
-        uint4 lo, hi;
-        {
-            float t0[8], t1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                t0[i] = e[i];
-                t1[i] = e[8 + i];
-            }
-            lo = pack8(t0);
-            hi = pack8(t1);
-            float u0[8], u1[8];
-            unpack8(lo, u0);
-            unpack8(hi, u1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sum += u0[i] + u1[i];
-        }
-        const int slab = c >> 6, chunk = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row
-        uint8_t* base = prow + slab * kPSlabBytes;
-        *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = lo;
-        *reinterpret_cast<uint4*>(base + (((chunk + 1) ^ (row & 7)) << 4)) = hi;
-    }
-    // generic-proxy smem writes -> visible to the tensor core (async proxy), then CTA-wide hand-off
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
-        // ---- O = P V ----
-        ptx::mbar_wait(bar_v, 0);
-        ptx::tc_fence_after_sync();
-        const uint32_t sp = ptx::smem_u32(smem + kOffP), sv = ptx::smem_u32(smem + kOffV);
-        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B (= V) is MN-major
-        const int ksteps = tkp / 16;
-        for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = ptx::make_smem_desc_sw128(sp + (k >> 2) * kPSlabBytes + (k & 3) * 32, 16, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024);
-            ptx::umma_bf16_ss(tmem + kTmemO, da, db, idesc, k != 0);
-        }
-        ptx::umma_commit(bar_o);
-    }
-    ptx::mbar_wait(bar_o, 0);
-    ptx::tc_fence_after_sync();
-    const float inv = 1.0f / sum;
-    if (qi < p.Tq) {
-        bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-            uint32_t r[16];
-            ptx::tmem_ld_32x32b_x16(trow + kTmemO + c, r);
-            ptx::tmem_ld_wait();
-            float t0[8], t1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                t0[i] = __uint_as_float(r[i]) * inv;
-                t1[i] = __uint_as_float(r[8 + i]) * inv;
-            }
-            stg16(orow + c, pack8(t0));
-            stg16(orow + c + 8, pack8(t1));
-        }
-        if (p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
-    } else {
-        // keep the warp converged for the .sync.aligned TMEM loads of its other lanes
-#pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-            uint32_t r[16];
-            ptx::tmem_ld_32x32b_x16(trow + kTmemO + c, r);
-            ptx::tmem_ld_wait();
-        }
-    }
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) {
-        ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, kTmemCols);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// v2: probabilities stay in TENSOR MEMORY.  After the row max, each thread overwrites its own S row in place
-// with bf16 P (two values per 32-bit column, tcgen05.st) and O = P V runs with A read from TMEM.  That removes the
-// 80 KB shared-memory P tile: a CTA needs 84 KB of smem and 256 TMEM columns, so TWO CTAs fit per SM and one
-// CTA's softmax overlaps the other's loads and MMAs.  Keys beyond 256 (CLIP has 257) are not worth a second
-// 256-column accumulator: their scores and their P.V contribution (<= 16 keys) are computed on the CUDA cores.
-//   TMEM columns: S fp32 [0,256) -> P bf16x2 [0,128) in place; O fp32 [128,192) (dead S columns).
-// ------------------------------------------------------------------------------------------------
-constexpr int k2OffQ = 0;                  // 16 KB
-constexpr int k2OffK = 16 * 1024;          // 32 KB  (256 keys)
-constexpr int k2OffKx = 48 * 1024;         //  2 KB  (keys 256..271)
-constexpr int k2OffV = 50 * 1024;          // 32 KB
-constexpr int k2OffVx = 82 * 1024;         //  2 KB
-constexpr int k2OffBar = 84 * 1024;
-constexpr int k2SmemBytes = k2OffBar + 64 + 1024;
-constexpr uint32_t k2TmemCols = 256;
-constexpr uint32_t k2TmemO = 128;
-
-struct Fwd2Params {
-    bf16* o;
-    float* lse;
-    long long o_bs;
-    int o_rs;
-    int H, Tq, Tk, n_main, n_extra, causal;
-    float scale_log2e, scale;
-    int debug;
-};
 
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
@@ -294,247 +49,6 @@ __device__ __forceinline__ float dot_q_kx(const uint8_t* qrow_base, int qr7, con
     }
     return acc;
 }
-
-// 256 threads: two threads per query row (warps w and w+4 share TMEM lane quadrant w&3).  Thread "half" h owns
-// score columns [128h, 128h+128): it reads them, writes its P columns in place inside its OWN column range
-// (keys 0..127 -> TMEM cols [0,64), keys 128..255 -> cols [128,192)) and later normalises O columns [32h, 32h+32)
-// (O lives in cols [192,256), dead score columns of half 1).  Row max / row sum / extra-key probabilities are
-// exchanged through shared memory.
-constexpr int k2OffXchg = k2OffBar + 128;                 // smax[2][128] | ssum[2][128] | spx[16][128] floats
-constexpr int k2XchgBytes = (2 + 2 + 16) * 128 * 4;
-constexpr int k2SmemTotal = k2OffXchg + k2XchgBytes + 1024;
-constexpr uint32_t k2TmemO3 = 192;
-
-__global__ void __launch_bounds__(256, 2)
-attn_fwd_tcgen05_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                           const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_kx,
-                           const __grid_constant__ CUtensorMap tmap_vx, Fwd2Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + k2OffBar);
-    uint64_t* bar_v = bar_qk + 1;
-    uint64_t* bar_s = bar_qk + 2;
-    uint64_t* bar_o = bar_qk + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 4);
-    float* smax = reinterpret_cast<float*>(smem + k2OffXchg);
-    float* ssum = smax + 256;
-    float* spx = ssum + 256;
-
-    const int warp = threadIdx.x >> 5;
-    const int half = threadIdx.x >> 7;
-    const int row = threadIdx.x & 127;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int n_main = p.n_main, n_extra = p.n_extra;
-    dbg_stamp(p.debug, 0);
-
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&tmap_q);
-        ptx::prefetch_tensormap(&tmap_k);
-        ptx::prefetch_tensormap(&tmap_v);
-        ptx::mbar_init(bar_qk, 1);
-        ptx::mbar_init(bar_v, 1);
-        ptx::mbar_init(bar_s, 1);
-        ptx::mbar_init(bar_o, 1);
-        ptx::fence_barrier_init();
-    }
-    if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, k2TmemCols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-    dbg_stamp(p.debug, 1);
-
-    if (threadIdx.x == 0) {
-        const uint32_t kv_bytes = static_cast<uint32_t>(n_main) * 128u + (n_extra > 0 ? 2048u : 0u);
-        ptx::mbar_arrive_expect_tx(bar_qk, kQBytes + kv_bytes);
-        ptx::tma_load_3d(smem + k2OffQ, &tmap_q, bar_qk, h * 64, q0, b);
-        ptx::tma_load_3d(smem + k2OffK, &tmap_k, bar_qk, h * 64, 0, b);
-        if (n_extra > 0) ptx::tma_load_3d(smem + k2OffKx, &tmap_kx, bar_qk, h * 64, 256, b);
-        ptx::mbar_arrive_expect_tx(bar_v, kv_bytes);
-        ptx::tma_load_3d(smem + k2OffV, &tmap_v, bar_v, h * 64, 0, b);
-        if (n_extra > 0) ptx::tma_load_3d(smem + k2OffVx, &tmap_vx, bar_v, h * 64, 256, b);
-
-        ptx::mbar_wait(bar_qk, 0);
-        dbg_stamp(p.debug, 2);
-        ptx::tc_fence_after_sync();
-        const uint32_t sq = ptx::smem_u32(smem + k2OffQ), sk = ptx::smem_u32(smem + k2OffK);
-        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, n_main, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tmem, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc, k != 0);
-        ptx::umma_commit(bar_s);
-    }
-
-    const int qi = q0 + row;
-    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    int lim = p.Tk;
-    if (p.causal) lim = min(p.Tk, qi + (p.Tk - p.Tq) + 1);
-    if (lim < 1) lim = 1;
-    const uint8_t* qrow = smem + k2OffQ + (row >> 3) * 1024 + (row & 7) * 128;
-    // this thread's score columns [dom0, dom1); `full`: end of the prefix that needs no masking.  Warp-uniform on
-    // purpose: the tcgen05.ld/st below are .sync.aligned, every lane must run the same trip counts.
-    const int dom0 = min(half * 128, n_main), dom1 = min(dom0 + 128, n_main);
-    const int lim_min = __reduce_min_sync(0xffffffffu, lim);
-    const int full = dom0 + (max(min(lim_min, dom1) - dom0, 0) & ~31);
-    const uint32_t pcol0 = half * 128;  // P columns of this half start here (in place, inside its own range)
-
-    // scores of the extra keys (CUDA cores; half 0 only), needed for the row max.  They are parked in this
-    // thread's private slots of the exchange buffer (a rolled loop: 16 unrolled copies of the dot product blew
-    // the instruction cache).
-    float m = -INFINITY;
-    if (half == 0 && n_extra > 0) {
-        ptx::mbar_wait(bar_qk, 0);  // Q / Kx are in shared memory
-#pragma unroll 1
-        for (int e = 0; e < n_extra; ++e) {
-            const float sc = (256 + e < lim) ? dot_q_kx(qrow, row & 7, smem + k2OffKx, e) : -INFINITY;
-            spx[e * 128 + row] = sc;
-            m = fmaxf(m, sc);
-        }
-    }
-    dbg_stamp(p.debug, 3);
-    ptx::mbar_wait(bar_s, 0);
-    ptx::tc_fence_after_sync();
-    dbg_stamp(p.debug, 4);
-    for (int c = dom0; c < full; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(trow + c, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-    }
-    for (int c = full; c < dom1; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(trow + c, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (c + i < lim) m = fmaxf(m, __uint_as_float(r[i]));
-    }
-    smax[half * 128 + row] = m;
-    __syncthreads();
-    m = fmaxf(smax[row], smax[128 + row]);
-    const float mb = m * p.scale_log2e;
-    float sum = 0.f;
-    dbg_stamp(p.debug, 5);
-    for (int c = dom0; c < full; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(trow + c, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
-            const float e1 = ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
-            sum += e0 + e1;
-            const bf162 h2 = __floats2bfloat162_rn(e0, e1);
-            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
-        // P columns overwrite score columns of this thread's own range that it has already consumed
-        ptx::tmem_st_32x32b_x16(trow + pcol0 + ((c - dom0) >> 1), pk);
-    }
-    for (int c = full; c < dom1; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(trow + c, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float e0 = (c + 2 * i < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb)) : 0.f;
-            const float e1 =
-                (c + 2 * i + 1 < lim) ? ex2_fast(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb)) : 0.f;
-            sum += e0 + e1;
-            const bf162 h2 = __floats2bfloat162_rn(e0, e1);
-            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-        }
-        ptx::tmem_st_32x32b_x8(trow + pcol0 + ((c - dom0) >> 1), pk);
-    }
-    if (half == 0) {
-#pragma unroll 1
-        for (int e = 0; e < n_extra; ++e) {
-            const float pe = (256 + e < lim) ? ex2_fast(fmaf(spx[e * 128 + row], p.scale_log2e, -mb)) : 0.f;
-            sum += pe;
-            spx[e * 128 + row] = pe;
-        }
-    }
-    ssum[half * 128 + row] = sum;
-    dbg_stamp(p.debug, 6);
-    ptx::tmem_st_wait();
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    dbg_stamp(p.debug, 7);
-
-    if (threadIdx.x == 0) {
-        ptx::mbar_wait(bar_v, 0);
-        ptx::tc_fence_after_sync();
-        const uint32_t sv = ptx::smem_u32(smem + k2OffV);
-        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // A = P (TMEM, K-major), B = V (MN-major)
-        const int ksteps = n_main / 16;
-        for (int k = 0; k < ksteps; ++k) {
-            const uint32_t pa = k < 8 ? k * 8 : 128 + (k - 8) * 8;       // where that key block's P lives
-            ptx::umma_bf16_ts(tmem + k2TmemO3, tmem + pa, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc,
-                              k != 0);
-        }
-        ptx::umma_commit(bar_o);
-    }
-    ptx::mbar_wait(bar_v, 0);  // Vx visible to every thread
-    ptx::mbar_wait(bar_o, 0);
-    ptx::tc_fence_after_sync();
-    dbg_stamp(p.debug, 8);
-    sum = ssum[row] + ssum[128 + row];
-    const float inv = 1.0f / sum;
-    {
-        // this thread normalises and stores O columns [32*half, 32*half + 32) of its row
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(trow + k2TmemO3 + half * 32, r);
-        ptx::tmem_ld_wait();
-        float t[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] = __uint_as_float(r[i]);
-        for (int e = 0; e < n_extra; ++e) {  // rank-1 updates from the extra keys
-            const uint8_t* vrow = smem + k2OffVx + (e >> 3) * 1024 + (e & 7) * 128;
-            const float pe = spx[e * 128 + row];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float v8[8];
-                unpack8(*reinterpret_cast<const uint4*>(vrow + (((half * 4 + q) ^ (e & 7)) << 4)), v8);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t[q * 8 + i] = fmaf(pe, v8[i], t[q * 8 + i]);
-            }
-        }
-        if (qi < p.Tq) {
-            bf16* orow = p.o + b * p.o_bs + static_cast<size_t>(qi) * p.o_rs + h * 64 + half * 32;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float o8[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o8[i] = t[q * 8 + i] * inv;
-                stg16(orow + q * 8, pack8(o8));
-            }
-        }
-    }
-    if (half == 0 && qi < p.Tq && p.lse != nullptr)
-        p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(sum);
-    dbg_stamp(p.debug, 9);
-    ptx::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 1) {
-        ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, k2TmemCols);
-    }
-    dbg_stamp(p.debug, 10);
-}
-
-// ------------------------------------------------------------------------------------------------
-// v4: persistent, warp-specialised pipeline (one CTA per SM).  Work unit = one (batch, head): its K / V tiles are
-// loaded ONCE (double-buffered across units) and shared by all of its 128-row query blocks; two query blocks are in
-// flight at a time, each in its own 256-column TMEM slot with its own 128-thread softmax group, so one block's
-// exp / store phase overlaps the other's MMAs and epilogue and the next unit's TMA loads.
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: group 0   warps 8-11: group 1
-// Per-slot TMEM layout as in v2: S fp32 [0,256) -> P bf16x2 in place [0,128); O fp32 [128,192).
 // ------------------------------------------------------------------------------------------------
 constexpr int k4KVStage = 68 * 1024;                       // K 32 KB | Kx 2 KB | V 32 KB | Vx 2 KB
 constexpr int k4OffQ = 2 * k4KVStage;                      // two Q slots of 16 KB
@@ -564,6 +78,7 @@ struct Fwd4Params {
     int order;
 };
 
+#ifdef VLK_BRINGUP
 __device__ __forceinline__ void dbg4(int enabled, bool who, int g, uint32_t tile, int slot) {
     if (enabled && who && blockIdx.x == 0 && tile >= 2 && tile < 6) {
         long long t;
@@ -571,6 +86,9 @@ __device__ __forceinline__ void dbg4(int enabled, bool who, int g, uint32_t tile
         g_attn_dbg[(g * 4 + (tile - 2)) * 16 + slot] = t;
     }
 }
+#else
+__device__ __forceinline__ void dbg4(int, bool, int, uint32_t, int) {}
+#endif
 
 // swizzled 128-byte row `j` of the K (or V) tile of a stage: keys < 256 in the main tile, the rest in the 16-row box
 __device__ __forceinline__ const uint8_t* kv_row(const uint8_t* main_tile, int j) {
@@ -1058,170 +576,74 @@ int make_tmap3(CUtensorMap* map, const void* base, int W, int T, int B, int rs, 
 }
 
 }  // namespace
-}  // namespace vlk
 
-using namespace vlk;
-
-extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq,
-                            int Tk, long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs,
-                            long long o_bs, int o_rs, int causal, float scale, float dropout_p,
-                            const unsigned long long* seed_state, unsigned int stream_id, void* stream) {
-    VLK_REQUIRE(q && k && v && o, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: null pointer");
-    VLK_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed_state), VLK_ERR_INVALID_ARG,
-                "vlk_attn_fwd: dropout_p=%f needs a seed state", dropout_p);
-    VLK_REQUIRE(dropout_p == 0.f || attn_small_applicable(Tq, Tk), VLK_ERR_UNSUPPORTED,
-                "vlk_attn_fwd: attention dropout is only implemented for Tq, Tk <= 64 (the Q-Former shapes)");
-    VLK_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, VLK_ERR_INVALID_ARG, "vlk_attn_fwd: B=%d H=%d Tq=%d Tk=%d", B, H,
-                Tq, Tk);
-    VLK_REQUIRE(q_rs % 8 == 0 && k_rs % 8 == 0 && v_rs % 8 == 0 && o_rs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 &&
-                    v_bs % 8 == 0 && o_bs % 8 == 0,
-                VLK_ERR_ALIGNMENT, "vlk_attn_fwd: strides must be multiples of 8 elements");
-    VLK_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VLK_ERR_ALIGNMENT,
-                "vlk_attn_fwd: 16B alignment");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const char* force = getenv("VLK_ATTN_IMPL");
-    if (attn_small_applicable(Tq, Tk) &&
-        (dropout_p > 0.f || !(force && (strcmp(force, "simt") == 0 || strcmp(force, "flash") == 0)))) {
-        // two heads per CTA on the tensor cores; VLK_ATTN_IMPL=small keeps the CUDA-core kernel for cross-checks
-        if (!(force && strcmp(force, "small") == 0) &&
-            attn_pair_applicable(B, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs))
-            return attn_pair_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                                 scale, dropout_p, seed_state, stream_id, s);
-        return attn_small_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                              scale, dropout_p, seed_state, stream_id, s);
-    }
-    // long sequences (GPT-2 pretraining, T = 1024): streaming tcgen05 kernel
-    if ((Tk > kMaxKeys && !(force && strcmp(force, "simt") == 0)) || (force && strcmp(force, "flash") == 0))
-        return attn_flash_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                              scale, s);
-    const bool want_tc = force ? (strncmp(force, "tcgen05", 7) == 0) : (Tk > 64);
-    if (!want_tc || Tk > kMaxKeys || Tq < 64 || (force && strcmp(force, "simt") == 0))
-        return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                             scale, s, 0);
-
-    // full 128-row query blocks on the tensor cores; a short tail (e.g. the 257th CLIP token) on the CUDA cores
+// 64 < Tk <= 272, Tq >= 64: full 128-row query blocks on the tensor cores; a remainder of <= 8 rows (the 257th CLIP
+// token) is folded into the same kernel.  All strides in elements, multiples of 8; bases 16-byte aligned.
+int attn_mid_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
+                 long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs,
+                 int causal, float scale, cudaStream_t s) {
     int tail = Tq % 128;
     int tc_rows = Tq - tail;
     if (tail > 8) {  // a longer remainder gets its own (partly empty) 128-row block
         tc_rows = Tq;
         tail = 0;
     }
-    if (!(force && strcmp(force, "tcgen05v1") == 0)) {
-        static bool configured2 = false;
-        if (!configured2) {
-            VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          k2SmemTotal));
-            configured2 = true;
-        }
-        Fwd2Params p2;
-        p2.o = static_cast<bf16*>(o);
-        p2.lse = lse;
-        p2.o_bs = o_bs;
-        p2.o_rs = o_rs;
-        p2.H = H;
-        p2.Tq = Tq;
-        p2.Tk = Tk;
-        p2.n_main = Tk >= 256 ? 256 : (Tk + 15) / 16 * 16;
-        p2.n_extra = Tk > 256 ? Tk - 256 : 0;
-        p2.causal = causal;
-        p2.scale = scale;
-        p2.scale_log2e = scale * 1.4426950408889634f;
-        p2.debug = getenv("VLK_ATTN_DEBUG") != nullptr ? atoi(getenv("VLK_ATTN_DEBUG")) : 0;
-        CUtensorMap tq, tk, tv, tkx, tvx;
-        int rc = make_tmap3(&tq, q, H * 64, Tq, B, q_rs, q_bs, 128);
-        if (rc) return rc;
-        rc = make_tmap3(&tk, k, H * 64, Tk, B, k_rs, k_bs, p2.n_main);
-        if (rc) return rc;
-        rc = make_tmap3(&tv, v, H * 64, Tk, B, v_rs, v_bs, p2.n_main);
-        if (rc) return rc;
-        rc = make_tmap3(&tkx, k, H * 64, Tk, B, k_rs, k_bs, 16);
-        if (rc) return rc;
-        rc = make_tmap3(&tvx, v, H * 64, Tk, B, v_rs, v_bs, 16);
-        if (rc) return rc;
-        if (!(force && strcmp(force, "tcgen05v3") == 0)) {
-            // persistent pipeline: one CTA per SM walks the (batch, head) units
-            static bool configured4 = false;
-            if (!configured4) {
-                VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              k4SmemTotal));
-                configured4 = true;
-            }
-            Fwd4Params p4;
-            p4.o = p2.o;
-            p4.lse = p2.lse;
-            p4.o_bs = o_bs;
-            p4.o_rs = o_rs;
-            p4.B = B;
-            p4.H = H;
-            p4.Tq = Tq;
-            p4.Tk = Tk;
-            p4.n_main = p2.n_main;
-            p4.n_extra = p2.n_extra;
-            p4.causal = causal;
-            p4.nqb = (tc_rows + 127) / 128;
-            p4.scale = scale;
-            p4.scale_log2e = p2.scale_log2e;
-            p4.debug = p2.debug;
-            p4.q = static_cast<const bf16*>(q);
-            p4.q_bs = q_bs;
-            p4.q_rs = q_rs;
-            p4.tail_rows = tail;   // folded into the persistent kernel
-            // measured at B=64, H=16, T=257 (graph-timed): order 0 78.0 us, 1 73.5 us, 2 76.5 us
-            p4.order = 1;
-            if (const char* f = getenv("VLK_ATTN_V4_ORDER")) p4.order = atoi(f);
-            tail = 0;
-            const int sms = device_sm_count();
-            VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
-            const int units = B * H;
-            attn_fwd_tcgen05_v4_kernel<<<units < sms ? units : sms, 384, k4SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p4);
-            VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v4)");
-        } else {
-            const dim3 grid2((tc_rows + 127) / 128, H, B);
-            attn_fwd_tcgen05_v2_kernel<<<grid2, 256, k2SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p2);
-            VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 v3)");
-        }
-        if (tail > 0)
-            return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                                 scale, s, tc_rows);
-        return VLK_OK;
+    static bool configured4 = false;
+    if (!configured4) {
+        VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      k4SmemTotal));
+        configured4 = true;
     }
-    static bool configured = false;
-    if (!configured) {
-        VLK_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
-    }
-    FwdParams p;
-    p.o = static_cast<bf16*>(o);
-    p.lse = lse;
-    p.o_bs = o_bs;
-    p.o_rs = o_rs;
-    p.H = H;
-    p.Tq = Tq;
-    p.Tk = Tk;
-    p.tkp = (Tk + 15) / 16 * 16;
-    p.box_rows = p.tkp > 256 ? p.tkp / 2 : p.tkp;
-    p.causal = causal;
-    p.scale = scale;
-    p.scale_log2e = scale * 1.4426950408889634f;
-    CUtensorMap tq, tk, tv;
+    const int n_main = Tk >= 256 ? 256 : (Tk + 15) / 16 * 16;
+    CUtensorMap tq, tk, tv, tkx, tvx;
     int rc = make_tmap3(&tq, q, H * 64, Tq, B, q_rs, q_bs, 128);
     if (rc) return rc;
-    rc = make_tmap3(&tk, k, H * 64, Tk, B, k_rs, k_bs, p.box_rows);
+    rc = make_tmap3(&tk, k, H * 64, Tk, B, k_rs, k_bs, n_main);
     if (rc) return rc;
-    rc = make_tmap3(&tv, v, H * 64, Tk, B, v_rs, v_bs, p.box_rows);
+    rc = make_tmap3(&tv, v, H * 64, Tk, B, v_rs, v_bs, n_main);
     if (rc) return rc;
-    const dim3 grid((tc_rows + 127) / 128, H, B);
-    attn_fwd_tcgen05_kernel<<<grid, 128, kSmemBytes, s>>>(tq, tk, tv, p);
-    VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05)");
-    if (tail > 0)
-        return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal,
-                             scale, s, tc_rows);
+    rc = make_tmap3(&tkx, k, H * 64, Tk, B, k_rs, k_bs, 16);
+    if (rc) return rc;
+    rc = make_tmap3(&tvx, v, H * 64, Tk, B, v_rs, v_bs, 16);
+    if (rc) return rc;
+    Fwd4Params p4;
+    p4.o = static_cast<bf16*>(o);
+    p4.lse = lse;
+    p4.o_bs = o_bs;
+    p4.o_rs = o_rs;
+    p4.B = B;
+    p4.H = H;
+    p4.Tq = Tq;
+    p4.Tk = Tk;
+    p4.n_main = n_main;
+    p4.n_extra = Tk > 256 ? Tk - 256 : 0;
+    p4.causal = causal;
+    p4.nqb = (tc_rows + 127) / 128;
+    p4.scale = scale;
+    p4.scale_log2e = scale * 1.4426950408889634f;
+    p4.debug = 0;
+    p4.q = static_cast<const bf16*>(q);
+    p4.q_bs = q_bs;
+    p4.q_rs = q_rs;
+    p4.tail_rows = tail;   // folded into the persistent kernel
+    // MMA issue order 1 (scores of the next block before the previous block's P.V), measured at B=64, H=16, T=257
+    // (graph-timed): order 0 78.0 us, 1 73.5 us, 2 76.5 us
+    p4.order = 1;
+    const int sms = device_sm_count();
+    VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
+    const int units = B * H;
+    attn_fwd_tcgen05_v4_kernel<<<units < sms ? units : sms, 384, k4SmemTotal, s>>>(tq, tk, tv, tkx, tvx, p4);
+    VLK_CHECK_LAUNCH("vlk_attn_fwd(tcgen05 mid)");
     return VLK_OK;
 }
 
-// bring-up only (not part of include/vlk.h): copy the attention phase stamps to the host
+}  // namespace vlk
+
+#ifdef VLK_BRINGUP
+// bring-up only (not part of include/vlk.h, not in the shipped library): copy the attention phase stamps to the host
 extern "C" int vlk_debug_dump(long long* host_out, int n) {
     if (n > 64 * 16) n = 64 * 16;
     cudaError_t e = cudaMemcpyFromSymbol(host_out, vlk::g_attn_dbg, sizeof(long long) * n);
     return static_cast<int>(e);
 }
+#endif

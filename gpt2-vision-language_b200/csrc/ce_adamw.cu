@@ -31,8 +31,11 @@ softmax_ce_rows_kernel(bf16* __restrict__ logits, const long long* __restrict__ 
     bf16* r = logits + static_cast<size_t>(row) * ld;
     const long long label = labels[row];
     const int nvec = V / 8;
-    if (label < 0) {  // ignore_index row: zero loss, zero gradient
-        if (threadIdx.x == 0) loss_row[row] = 0.f;
+    if (label == -100 || label < 0 || label >= V) {
+        // ignore_index (-100, F.cross_entropy's default and the value the reference masks with): zero loss, zero
+        // gradient.  Any other label outside [0, V) is a caller bug (torch raises a device assert): the row's loss is
+        // NaN, so the step's loss is NaN instead of a silent read past the cached row.
+        if (threadIdx.x == 0) loss_row[row] = (label == -100) ? 0.f : nanf("");
         if (write_grad) {
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int i = threadIdx.x; i < nvec; i += blockDim.x) stg16(r + i * 8, z);
@@ -84,7 +87,7 @@ __global__ void ce_count_kernel(const long long* __restrict__ labels, const floa
     __shared__ float red[32];
     float c = 0.f;
     for (int i = threadIdx.x; i < rows; i += blockDim.x)
-        c += row_weight ? row_weight[i] : (labels[i] >= 0 ? 1.f : 0.f);
+        c += row_weight ? row_weight[i] : (labels[i] != -100 ? 1.f : 0.f);
     c = block_reduce(c, red, false);
     if (threadIdx.x == 0) out[1] = 1.0f / fmaxf(c, 1.0f);
 }

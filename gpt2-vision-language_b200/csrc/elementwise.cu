@@ -86,7 +86,7 @@ __global__ void pool33_kernel(const void* __restrict__ in_, void* __restrict__ o
 // ---------------------------------------------------------------------------------------------------
 __global__ void embed_concat_kernel(const long long* __restrict__ ids, const bf16* __restrict__ wte,
                                     const bf16* __restrict__ wpe, const bf16* __restrict__ prefix,
-                                    bf16* __restrict__ out, int T, int prefix_len, int C, int pos0) {
+                                    bf16* __restrict__ out, int T, int prefix_len, int C, int pos0, int vocab) {
     const int L = prefix_len + T;
     const int b = blockIdx.x / L, t = blockIdx.x % L;
     bf16* o = out + static_cast<size_t>(blockIdx.x) * C;
@@ -96,6 +96,13 @@ __global__ void embed_concat_kernel(const long long* __restrict__ ids, const bf1
     } else {
         const int tt = t - prefix_len;
         const long long id = ids[static_cast<size_t>(b) * T + tt];
+        if (id < 0 || id >= vocab) {
+            // out-of-vocabulary id: torch's embedding raises a device assert; here the row is poisoned with NaN so the
+            // loss of the step is NaN instead of a silent read outside wte
+            const uint4 nan8 = make_uint4(0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u, 0x7FC07FC0u);
+            for (int col = threadIdx.x * 8; col < C; col += blockDim.x * 8) stg16(o + col, nan8);
+            return;
+        }
         const bf16* e = wte + static_cast<size_t>(id) * C;
         const bf16* p = wpe + static_cast<size_t>(pos0 + tt) * C;
         for (int col = threadIdx.x * 8; col < C; col += blockDim.x * 8) {
@@ -351,6 +358,30 @@ inline int grid_for(long long work_items, int threads, int sms) {
     return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// A scalar riding in the gradient all-reduce: Q8.24 fixed point, 8 base-16 digits, one per bucket slot.
+// Sums of <= 16 digits (< 256) and a division by a power of two are exact in bf16, so the averaged value is
+// recovered exactly (to 2^-24) whatever the reduction order of the collective.
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scalar_pack_digits_kernel(const float* __restrict__ v, T* __restrict__ slots) {
+    const float x = fminf(fmaxf(*v, 0.f), 255.99999f);
+    const unsigned int q = static_cast<unsigned int>(llrintf(x * 16777216.0f));
+    const float d = static_cast<float>((q >> (4 * threadIdx.x)) & 15u);
+    slots[threadIdx.x] = static_cast<T>(d);
+    if (threadIdx.x == 0 && !(*v == *v)) slots[7] = static_cast<T>(nanf(""));   // a NaN loss stays a NaN
+}
+template <typename T>
+__global__ void scalar_unpack_digits_kernel(const T* __restrict__ slots, float* __restrict__ v) {
+    double acc = 0.0, w = 1.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc += static_cast<double>(static_cast<float>(slots[i])) * w;
+        w *= 16.0;
+    }
+    *v = static_cast<float>(acc * (1.0 / 16777216.0));
+}
+
 }  // namespace
 }  // namespace vlk
 
@@ -372,15 +403,15 @@ extern "C" int vlk_pool33_l2norm(const void* in, void* out, int B, int D, int in
 }
 
 extern "C" int vlk_embed_concat_fwd(const long long* ids, const void* wte, const void* wpe, const void* prefix,
-                                    void* out, int B, int T, int prefix_len, int C, int pos0, void* stream) {
+                                    void* out, int B, int T, int prefix_len, int C, int pos0, int vocab, void* stream) {
     VLK_REQUIRE(ids && wte && wpe && out, VLK_ERR_INVALID_ARG, "vlk_embed_concat_fwd: null pointer");
-    VLK_REQUIRE(B > 0 && T > 0 && prefix_len >= 0 && C % 8 == 0, VLK_ERR_INVALID_ARG,
-                "vlk_embed_concat_fwd: B=%d T=%d prefix=%d C=%d", B, T, prefix_len, C);
+    VLK_REQUIRE(B > 0 && T > 0 && prefix_len >= 0 && C % 8 == 0 && vocab > 0, VLK_ERR_INVALID_ARG,
+                "vlk_embed_concat_fwd: B=%d T=%d prefix=%d C=%d vocab=%d", B, T, prefix_len, C, vocab);
     VLK_REQUIRE(prefix_len == 0 || prefix, VLK_ERR_INVALID_ARG, "vlk_embed_concat_fwd: prefix missing");
     const int threads = C / 8 >= 128 ? 128 : ((C / 8 + 31) / 32) * 32;
     embed_concat_kernel<<<B * (prefix_len + T), threads, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, static_cast<const bf16*>(wte), static_cast<const bf16*>(wpe), static_cast<const bf16*>(prefix),
-        static_cast<bf16*>(out), T, prefix_len, C, pos0);
+        static_cast<bf16*>(out), T, prefix_len, C, pos0, vocab);
     VLK_CHECK_LAUNCH("vlk_embed_concat_fwd");
     return VLK_OK;
 }
@@ -499,5 +530,27 @@ extern "C" int vlk_dropout_add_bf16(const void* x, const void* residual, void* y
         static_cast<const bf16*>(x), static_cast<const bf16*>(residual), static_cast<bf16*>(y), n / 8, p, seed_state,
         stream_id);
     VLK_CHECK_LAUNCH("vlk_dropout_add_bf16");
+    return VLK_OK;
+}
+
+extern "C" int vlk_scalar_pack_digits(const float* value, void* slots, int slots_fp32, void* stream) {
+    VLK_REQUIRE(value && slots, VLK_ERR_INVALID_ARG, "vlk_scalar_pack_digits: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (slots_fp32)
+        scalar_pack_digits_kernel<float><<<1, 8, 0, s>>>(value, static_cast<float*>(slots));
+    else
+        scalar_pack_digits_kernel<bf16><<<1, 8, 0, s>>>(value, static_cast<bf16*>(slots));
+    VLK_CHECK_LAUNCH("vlk_scalar_pack_digits");
+    return VLK_OK;
+}
+
+extern "C" int vlk_scalar_unpack_digits(const void* slots, float* value, int slots_fp32, void* stream) {
+    VLK_REQUIRE(value && slots, VLK_ERR_INVALID_ARG, "vlk_scalar_unpack_digits: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (slots_fp32)
+        scalar_unpack_digits_kernel<float><<<1, 1, 0, s>>>(static_cast<const float*>(slots), value);
+    else
+        scalar_unpack_digits_kernel<bf16><<<1, 1, 0, s>>>(static_cast<const bf16*>(slots), value);
+    VLK_CHECK_LAUNCH("vlk_scalar_unpack_digits");
     return VLK_OK;
 }

@@ -50,8 +50,19 @@ struct EpiParams {
     const float* ln_sums;
     float ln_inv_k, ln_eps;
     float* stats_out;   // [M][2] fp32, accumulated with atomicAdd: row sums of the bf16-ROUNDED outputs and of their squares
-    int debug;  // bring-up only (VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
+#ifdef VLK_BRINGUP
+    int debug;  // bring-up builds only (env VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
+#endif
 };
+
+// Work-skipping switches exist in bring-up builds (-DVLK_BRINGUP) only: in the shipped library these fold to `false`.
+#ifdef VLK_BRINGUP
+#define VLK_DBG_SKIP_EPILOGUE(ep) (((ep).debug & 1) != 0)
+#define VLK_DBG_SKIP_LOADS(ep) (((ep).debug & 2) != 0)
+#else
+#define VLK_DBG_SKIP_EPILOGUE(ep) false
+#define VLK_DBG_SKIP_LOADS(ep) false
+#endif
 
 template <int BLOCK_N, int kStages>
 struct SmemLayout {
@@ -227,7 +238,7 @@ __device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int
 // round trip exposed per chunk: +33 % kernel time on the K = 768 / 1024 residual GEMMs, profiles/r01_gemm_short_probe.log.)
 __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* stage, int row0, int n0,
                                                   int ncols_warp, int M, int N, int lane) {
-    if (ep.out_fp32 || ncols_warp < 64 || (ep.debug & 1) || n0 >= N) return;
+    if (ep.out_fp32 || ncols_warp < 64 || VLK_DBG_SKIP_EPILOGUE(ep) || n0 >= N) return;
     int ld;
     const bf16* in = epi_staged_input(ep, ld);
     if (in == nullptr) return;
@@ -394,7 +405,7 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
 template <bool SPECIALISE>
 __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                               int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
-    if (ep.debug & 1) return;
+    if (VLK_DBG_SKIP_EPILOGUE(ep)) return;
     if (ep.out_fp32 || ncols_warp < 64) {
         // fp32 output (split-K slabs) and 32-column slices keep the direct row-per-thread path
         const int row = row0 + lane;
@@ -516,7 +527,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0 && !(ep.debug & 2)) {
+        if (lane == 0 && !VLK_DBG_SKIP_LOADS(ep)) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -582,7 +593,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
+                    if (!VLK_DBG_SKIP_LOADS(ep)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
                     const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
@@ -724,7 +735,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
     if (warp_idx == 0) {
         // ===================================== TMA producer (both CTAs) =========================
-        if (lane == 0 && !(ep.debug & 2)) {
+        if (lane == 0 && !VLK_DBG_SKIP_LOADS(ep)) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -773,7 +784,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!(ep.debug & 2)) ptx::mbar_wait(&full_bar[stage], phase);
+                    if (!VLK_DBG_SKIP_LOADS(ep)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
                     const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t sb = sa + L::kABytes;
@@ -916,10 +927,6 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
     cfg.numAttrs = 1;
     // band height: balance distinct A tiles (128 rows each per CTA) against distinct B tiles (BLOCK_N rows) per wave
     int group = 16 / CLUSTER;
-    if (const char* f = getenv("VLK_GEMM_GROUP")) {
-        const int v = atoi(f);
-        if (v > 0) group = v;
-    }
     if (group > m_units) group = m_units;
     VLK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group, ep));
     VLK_CHECK_LAUNCH("vlk_gemm_bf16");
@@ -953,10 +960,6 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int group = 8;
-    if (const char* f = getenv("VLK_GEMM_GROUP")) {
-        const int v = atoi(f);
-        if (v > 0) group = v;
-    }
     if (group > m_units) group = m_units;
     VLK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group, ep));
     VLK_CHECK_LAUNCH("vlk_gemm_bf16(2cta)");
@@ -1012,7 +1015,8 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
                      void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
                      int split_k, long long split_stride, int* split_used, void* stream,
                      const float* ln_mean = nullptr, const float* ln_rstd = nullptr, const float* ln_colsum = nullptr,
-                     const float* ln_sums = nullptr, float ln_eps = 0.f, float* stats_out = nullptr) {
+                     const float* ln_sums = nullptr, float ln_eps = 0.f, float* stats_out = nullptr,
+                     int bn_override = 0, int pair_override = -1) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -1068,8 +1072,10 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     ep.ln_inv_k = 1.0f / static_cast<float>(K);
     ep.ln_eps = ln_eps;
     ep.stats_out = stats_out;
+#ifdef VLK_BRINGUP
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
+#endif
 
     // Tile selection (measured on B200, profiles/r01_gemm_sweep*.log): the 256-wide tile wins on every shape of
     // this path (fewer, longer tiles amortise the epilogue; N = 768/1024/2304/3072/4096/50304 all tile well), and
@@ -1077,15 +1083,12 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     int bn = N >= 192 ? 256 : (N >= 96 ? 128 : 64);
     int cluster = (M > BLOCK_M && bn >= 128 && sms % 2 == 0) ? 3 : 1;
     (void)tile_cost;
-    if (const char* f = getenv("VLK_GEMM_BN")) {
-        int v = atoi(f);
-        if (v == 256 || v == 128 || v == 64) bn = v;
+    if (bn_override == 256 || bn_override == 128 || bn_override == 64) {   // vlk_gemm_bf16_tile only
+        bn = bn_override;
         if (bn == 64) cluster = 1;
     }
-    if (const char* f = getenv("VLK_GEMM_CLUSTER")) {  // 1 = single CTA, 2 = multicast pair, 3 = cta_group::2 pair
-        int v = atoi(f);
-        if (v == 1 || ((v == 2 || v == 3) && bn >= 128 && sms % 2 == 0)) cluster = v;
-    }
+    if (pair_override == 0) cluster = 1;
+    else if (pair_override == 1 && bn >= 128 && sms % 2 == 0) cluster = 3;
 #ifndef VLK_GEMM_MULTICAST_VARIANT
     if (cluster == 2) cluster = 1;   // the multicast pair is not compiled in (see dispatch)
 #endif
@@ -1116,6 +1119,15 @@ extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N
                              float alpha, int out_fp32, int split_k, void* stream) {
     return gemm_impl(A, B, D, M, N, K, lda, ldb, ldd, transA, transB, bias, residual, ldr, aux_in, aux_out, ld_aux, scale,
                      act, dact, alpha, out_fp32, split_k, 0, nullptr, stream);
+}
+
+extern "C" int vlk_gemm_bf16_tile(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                                  int transA, int transB, const void* bias, const void* residual, int ldr, int act,
+                                  int tile_n, int cta_pair, void* stream) {
+    VLK_REQUIRE(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 256, VLK_ERR_INVALID_ARG,
+                "vlk_gemm_bf16_tile: tile_n=%d (0 = automatic, 64, 128, 256)", tile_n);
+    return gemm_impl(A, B, D, M, N, K, lda, ldb, ldd, transA, transB, bias, residual, ldr, nullptr, nullptr, 0, nullptr, act,
+                     0, 1.0f, 0, 1, 0, nullptr, stream, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, tile_n, cta_pair);
 }
 
 extern "C" int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float* workspace, int M, int N, int K,

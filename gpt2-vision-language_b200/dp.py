@@ -14,8 +14,15 @@ import torch
 import torch.distributed as dist
 
 
+SCALAR_SLOTS = 8          # one fp32 scalar travels as 8 base-16 digits (see FlatGradBucket.pack_scalar)
+
+
 class FlatGradBucket:
-    def __init__(self, params, extra_slots=0, pad_multiple=1):
+    """Layout of ``flat``: [ scalar slots (optional) | gradient of params[0] | params[1] | ... | padding ].
+    The scalar slots sit in FRONT so that both the whole-bucket exchange and the ``[0, k)`` head range of the
+    split-backward path carry them."""
+
+    def __init__(self, params, scalar_slot=False, pad_multiple=1):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -24,19 +31,20 @@ class FlatGradBucket:
             raise ValueError("FlatGradBucket needs a single gradient dtype")
         # 16-byte align every view so the fused optimizer can use vector loads
         align = 16 // torch.empty((), dtype=dtype).element_size()
-        offs, total = [], 0
+        total = (SCALAR_SLOTS + align - 1) // align * align if scalar_slot else 0
+        self.params_off = total
+        offs = []
         for p in self.params:
             offs.append(total)
             total += (p.numel() + align - 1) // align * align
-        self.extra_off = total
-        total += (extra_slots + align - 1) // align * align
+        self.params_end = total
         total = (total + pad_multiple - 1) // pad_multiple * pad_multiple   # ZeRO-1: equal, 16-byte aligned shards
         self.sizes = [p.numel() for p in self.params]
         self.flat = torch.zeros(total, dtype=dtype, device=device)
         self.offsets = {id(p): o for p, o in zip(self.params, offs)}
         for p, o in zip(self.params, offs):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
-        self.extra = self.flat[self.extra_off:self.extra_off + extra_slots]
+        self.scalar = self.flat[:SCALAR_SLOTS] if scalar_slot else None
 
     def offset_of(self, param):
         """Element offset of a parameter's gradient inside the flat buffer (parameters are laid out in
@@ -46,6 +54,40 @@ class FlatGradBucket:
     def zero(self):
         """Replaces optimizer.zero_grad(): one memset; the .grad views stay attached (static addresses)."""
         self.flat.zero_()
+
+    # ---- a scalar (the step's loss) riding in the same collective ---------------------------------------------
+    def pack_scalar(self, value):
+        """Encode a non-negative fp32 scalar (< 256) into the scalar slots as 8 base-16 digits of its Q8.24
+        fixed-point value.  Digits are small integers: their sum over <= 16 ranks (< 256) and the division by a
+        power-of-two world size are EXACT in bf16 / fp32, whatever order the collective adds them in — so the
+        averaged loss (train_gpt2.py:470-471) needs no collective of its own."""
+        if self.scalar is None:
+            raise RuntimeError("bucket was built without a scalar slot")
+        if value.is_cuda:
+            from . import _lib
+            _lib.check(_lib.load().vlk_scalar_pack_digits(value.data_ptr(), self.scalar.data_ptr(),
+                                                          int(self.flat.dtype == torch.float32),
+                                                          torch.cuda.current_stream().cuda_stream), "vlk_scalar_pack_digits")
+        else:   # host restatement for the gloo tests
+            q = int(round(min(max(float(value), 0.0), 255.99999) * (1 << 24)))
+            self.scalar.copy_(torch.tensor([(q >> (4 * i)) & 15 for i in range(SCALAR_SLOTS)], dtype=self.flat.dtype))
+
+    def unpack_scalar(self, out):
+        """Inverse of pack_scalar on the (averaged) digits -> ``out`` (0-d / 1-element fp32 tensor)."""
+        if out.is_cuda:
+            from . import _lib
+            _lib.check(_lib.load().vlk_scalar_unpack_digits(self.scalar.data_ptr(), out.data_ptr(),
+                                                            int(self.flat.dtype == torch.float32),
+                                                            torch.cuda.current_stream().cuda_stream), "vlk_scalar_unpack_digits")
+        else:
+            d = self.scalar.double()
+            out.fill_(float(sum(d[i].item() * 16.0 ** i for i in range(SCALAR_SLOTS)) / (1 << 24)))
+
+    @staticmethod
+    def scalar_rides_along(group=None):
+        """The digit encoding is exact only when the average divides by a power of two."""
+        n = dist.get_world_size(group)
+        return n & (n - 1) == 0 and n <= 16
 
     def all_reduce(self, group=None, lo=0, hi=None):
         """Average elements [lo, hi) over ranks, in place, on the current stream (default: the whole bucket)."""
@@ -58,6 +100,16 @@ class FlatGradBucket:
                 dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
                 buf.copy_(tmp / dist.get_world_size(group))
         return self.flat
+
+
+def average_scalar_(t, group=None):
+    """In-place mean of a small fp32 tensor over ranks (fallback when it cannot ride in the gradient bucket)."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(dist.get_world_size(group))
+    return t
 
 
 class FlatParamBucket:

@@ -96,6 +96,20 @@ class _BlockNoBuffer(Block):
     _attn_cls = _CausalSelfAttentionNoBuffer
 
 
+def _check_config(config):
+    """Shapes the sm_100a kernels are specialised for; anything else fails HERE with a clear message instead of at the
+    first kernel call.  The dataclass default vocab_size=50257 is kept for signature parity with the reference, but —
+    like the reference's own train scripts, which all pass vocab_size=50304 (train_gpt2.py:260, gpt2_linear/train.py:100)
+    — a multiple of 8 is required: the lm_head / cross-entropy kernels move 16-byte (8 x bf16) vectors per vocab row."""
+    if config.vocab_size % 8 != 0:
+        raise ValueError(f"vocab_size={config.vocab_size} is not a multiple of 8: the B200 lm_head / cross-entropy "
+                         f"kernels need 16-byte aligned logit rows; use the padded vocabulary the reference trains "
+                         f"with, GPTConfig(vocab_size=50304)")
+    if config.n_embd % config.n_head != 0 or config.n_embd // config.n_head != 64:
+        raise ValueError(f"n_embd={config.n_embd} / n_head={config.n_head}: the attention kernels are specialised for "
+                         f"head_dim 64 (GPT-2 124M: 768 / 12)")
+
+
 def _init_gpt_weights(root, n_layer):
     """N(0, 0.02) for Linear/Embedding weights, zero biases, residual projections scaled by (2L)^-1/2
     (train_gpt2.py:100-109).  Iterates modules in registration order like nn.Module.apply does, so a given
@@ -142,6 +156,7 @@ class GPT(nn.Module):
 
     def __init__(self, config):
         super().__init__()
+        _check_config(config)
         self.config = config
         self.transformer = nn.ModuleDict(dict(
             wte=nn.Embedding(config.vocab_size, config.n_embd),

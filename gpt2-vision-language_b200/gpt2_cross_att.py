@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from . import ops
 from .caption import pool_clip_197_to_33_avg_with_cls  # noqa: F401  (re-exported)
-from .gpt2 import MLP, CausalSelfAttention, _init_gpt_weights, build_adamw
+from .gpt2 import MLP, CausalSelfAttention, _check_config, _init_gpt_weights, build_adamw
 
 
 @dataclass
@@ -84,6 +84,7 @@ class GPT(nn.Module):
 
     def __init__(self, config):
         super().__init__()
+        _check_config(config)
         self.config = config
         self.transformer = nn.ModuleDict(dict(
             wte=nn.Embedding(config.vocab_size, config.n_embd),

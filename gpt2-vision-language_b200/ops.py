@@ -105,6 +105,23 @@ def gemm(a, b, *, trans_a=False, trans_b=False, bias=None, residual=None, aux_in
     return (out, aux) if aux_out else out
 
 
+def gemm_tile(a, b, *, tile_n=0, cta_pair=-1, trans_a=False, trans_b=False, bias=None, residual=None, act=None):
+    """ops.gemm with an EXPLICIT tile shape (vlk_gemm_bf16_tile): tuning sweeps and per-instantiation regression tests."""
+    _need_cuda(a, b)
+    a, b = _bf16c(a), _bf16c(b)
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    N = b.shape[1] if trans_b else b.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=BF16)
+    if residual is not None:
+        residual = _bf16c(residual)
+    check(_lib.load().vlk_gemm_bf16_tile(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+                                         out.stride(0), int(trans_a), int(trans_b), _p(bias), _p(residual),
+                                         residual.stride(0) if residual is not None else 0,
+                                         ACT[act] if not isinstance(act, int) else act, int(tile_n), int(cta_pair),
+                                         _stream()), "vlk_gemm_bf16_tile")
+    return out
+
+
 _SM_COUNT = None
 
 
@@ -381,7 +398,8 @@ def embed_concat(ids, wte, wpe, prefix=None, pos0=0):
         prefix = _bf16c(prefix).contiguous()
     out = torch.empty((B, P + T, C), device=ids.device, dtype=BF16)
     check(_lib.load().vlk_embed_concat_fwd(ids.data_ptr(), wte.data_ptr(), wpe.data_ptr(), _p(prefix),
-                                           out.data_ptr(), B, T, P, C, int(pos0), _stream()), "vlk_embed_concat_fwd")
+                                           out.data_ptr(), B, T, P, C, int(pos0), int(wte.shape[0]), _stream()),
+          "vlk_embed_concat_fwd")
     return out
 
 
@@ -544,11 +562,37 @@ def layernorm(x, weight, bias, eps=1e-5):
     return LayerNormFn.apply(x, weight, bias, eps)
 
 
+_RESIDUAL_GRAD_INPLACE = False
+
+
+class residual_grad_inplace:
+    """Context manager: inside it, ``ResidualLayerNormFn.backward`` accumulates the LayerNorm input gradient IN PLACE
+    into the incoming residual-stream gradient (one read-modify-write inside the LayerNorm-backward kernel instead of
+    a separate elementwise add per norm).
+
+    Aliasing contract: LinearFn / MLPFn / GatedProjFn hand the residual gradient through unchanged (``dres = dy``, the
+    same tensor), so with the in-place path ONE buffer is mutated all the way down the residual stream.  That is only
+    safe when nobody else reads those gradient tensors: no ``retain_grad()`` / tensor hooks on the residual stream, no
+    ``backward(retain_graph=True)`` run twice, and a tensor passed as ``backward(gradient=G)`` is clobbered.  The step
+    classes (step.CaptionTrainStep / PretrainStep) own every tensor involved and opt in; everywhere else the default
+    out-of-place path keeps autograd's value semantics."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+
+    def __enter__(self):
+        global _RESIDUAL_GRAD_INPLACE
+        self.prev, _RESIDUAL_GRAD_INPLACE = _RESIDUAL_GRAD_INPLACE, self.enabled
+
+    def __exit__(self, *exc):
+        global _RESIDUAL_GRAD_INPLACE
+        _RESIDUAL_GRAD_INPLACE = self.prev
+
+
 class ResidualLayerNormFn(torch.autograd.Function):
     """(x, LayerNorm(x)) for a pre-LN residual block (train_gpt2.py:72-73: ``x = x + f(ln(x))``).  Returning the
     residual stream through the same node lets backward ADD the LayerNorm input gradient straight into the
-    incoming residual gradient inside the LayerNorm-backward kernel (one read-modify-write of dx) instead of
-    autograd launching a separate elementwise add per norm."""
+    incoming residual gradient (in place when ``residual_grad_inplace`` is active, see its aliasing contract)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -569,14 +613,14 @@ class ResidualLayerNormFn(torch.autograd.Function):
         if g_y is None:
             return g_x, None, None, None
         dy2 = _rows(g_y).contiguous()
-        if g_x is not None and g_x.dtype == BF16 and g_x.is_contiguous():
-            # the residual gradient has no reader left but this node (its producers ran earlier in backward)
+        if _RESIDUAL_GRAD_INPLACE and g_x is not None and g_x.dtype == BF16 and g_x.is_contiguous():
+            # opted in: the residual gradient has no reader left but this node (its producers ran earlier in backward)
             acc = g_x.view(-1, g_x.shape[-1])
             _, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, dx=acc, accumulate=True, grads_bf16=True)
             dx = g_x
         else:
             dxl, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, grads_bf16=True)
-            dx = dxl.view(ctx.x_shape) if g_x is None else g_x + dxl.view(ctx.x_shape)
+            dx = dxl.view(ctx.x_shape) if g_x is None else add(g_x, dxl.view(ctx.x_shape)).view(ctx.x_shape)
         return (dx if ctx.needs_input_grad[0] else None,
                 dg if (pg and ctx.needs_input_grad[1]) else None,
                 db if (pg and ctx.needs_input_grad[2]) else None, None)

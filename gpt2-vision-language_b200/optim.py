@@ -5,6 +5,14 @@ Replaces ``torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)`` + ``torch.o
 reference loop's ``param_groups[i]['lr'] = lr`` / ``zero_grad()`` / ``state_dict()`` keep working.  Semantics
 follow torch's AdamW: decoupled weight decay, bias correction, moments stored in the parameter dtype
 (bf16 for the reference's bf16 models), fp32 math in registers.
+
+Two deliberate deviations from torch.optim.AdamW, both enforced rather than silent:
+  * ONE device step counter is shared by all parameters (torch keeps one per parameter).  They are identical as long as
+    every parameter steps every time — which is how the reference trains — so a parameter that joins later (its
+    ``.grad`` was None during earlier steps) raises instead of being bias-corrected with the wrong step;
+  * the learning rate is read by the kernel from a device scalar, so that a captured CUDA graph follows the schedule:
+    ``param_groups[i]['lr'] = x`` takes effect at the next eager ``step()``, or immediately after ``sync_lr()``
+    when the step is replayed from a graph (step.CaptionTrainStep.set_lr does both).
 """
 import ctypes
 
@@ -22,6 +30,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._norm_sq = None
         self._pending_max_norm = 0.0
         self._step_t = None  # ONE device step counter shared by every parameter (they always step together)
+        self._n_steps = 0
 
     # ---------------------------------------------------------------------------------------------
     def _active(self):
@@ -46,9 +55,13 @@ class FusedAdamW(torch.optim.Optimizer):
     def _build_tables(self, active):
         """One device table per (group, dtype); rebuilt only when a pointer changed (e.g. after
         zero_grad(set_to_none=True)).  Under CUDA graphs all pointers are static, so this is a no-op."""
-        key = tuple((id(g), p.data_ptr(), p.grad.data_ptr()) for g, ps in active for p in ps)
+        # weight_decay is baked into the device table: it is part of the key (a scheduler or load_state_dict may change it)
+        key = tuple((id(g), float(g["weight_decay"]), p.data_ptr(), p.grad.data_ptr()) for g, ps in active for p in ps)
         if key == self._table_key:
             return self._tables
+        if self._n_steps > 0 and any(not self.state[p] for _, ps in active for p in ps):
+            raise RuntimeError("FusedAdamW: a parameter received its first gradient after the optimizer had already "
+                               "stepped; all parameters share one step counter (see the module docstring)")
         tables = []
         for g, ps in active:
             for fp32 in (False, True):
@@ -105,9 +118,12 @@ class FusedAdamW(torch.optim.Optimizer):
         stream = torch.cuda.current_stream().cuda_stream
         if tables:
             self._step_t += 1
+            self._n_steps += 1
+        capturing = torch.cuda.is_current_stream_capturing()
         for t in tables:
             g = t["group"]
-            t["lr"].fill_(float(g["lr"]))
+            if not capturing:                       # a captured fill would freeze the learning rate into the graph
+                t["lr"].fill_(float(g["lr"]))
             step_t = self._step_t
             b1, b2 = g["betas"]
             check(lib.vlk_adamw_step(t["dev"].data_ptr(), t["n"], t["max_numel"], int(t["fp32"]),
@@ -117,15 +133,29 @@ class FusedAdamW(torch.optim.Optimizer):
         self._pending_max_norm = 0.0
         return loss
 
+    @torch.no_grad()
+    def sync_lr(self):
+        """Push param_groups[*]['lr'] into the device scalars the (possibly graph-captured) update kernels read."""
+        for t in self._tables or ():
+            t["lr"].fill_(float(t["group"]["lr"]))
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
-        # re-share the step counter (a loaded state has one copy per parameter) and drop cached tables
+        # re-share the step counter (a loaded state has one copy per parameter) and drop cached tables.  torch leaves
+        # 'step' wherever the checkpoint was mapped to (the CPU for data.load_checkpoint's default map_location): the
+        # kernel dereferences it, so it is rebuilt on the PARAMETER's device.
         self._step_t = None
-        for st in self.state.values():
+        for p, st in self.state.items():
             if "step" in st:
                 if self._step_t is None:
-                    self._step_t = st["step"].detach().float().reshape(1).clone()
+                    step = st["step"]
+                    step = step.detach() if torch.is_tensor(step) else torch.tensor(float(step))
+                    self._step_t = step.to(device=p.device, dtype=torch.float32).reshape(1).clone()
                 st["step"] = self._step_t
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st and (st[k].device != p.device or st[k].dtype != p.dtype):
+                    st[k] = st[k].to(device=p.device, dtype=p.dtype)
+        self._n_steps = int(self._step_t.item()) if self._step_t is not None else 0
         self._table_key = None
 
 
@@ -154,6 +184,7 @@ class Zero1AdamW:
         self.exp_avg = torch.zeros(self.S, device=dev, dtype=dt)
         self.exp_avg_sq = torch.zeros(self.S, device=dev, dtype=dt)
         offs = [g.offset_of(q) for q in g.params]
+        # the bucket's scalar slots (offsets < params_off) and tail padding belong to no tensor: never updated
         self.segments = shard_segments(offs, g.sizes, weight_decays, self.lo, self.hi)
         esz = g.flat.element_size()
         arr = (TensorDesc * max(1, len(self.segments)))()
@@ -193,11 +224,16 @@ class Zero1AdamW:
                   "vlk_grad_sumsq")
         return self.norm_sq
 
+    def set_lr(self, lr):
+        self.lr = lr
+        self.lr_t.fill_(float(lr))
+
     @torch.no_grad()
     def apply(self, norm_sq, max_norm):
         """AdamW on this rank's slice with the clip factor of the GLOBAL norm (norm_sq: 1-element fp32 tensor)."""
         self.step_t += 1
-        self.lr_t.fill_(float(self.lr))
+        if not torch.cuda.is_current_stream_capturing():
+            self.lr_t.fill_(float(self.lr))
         if self.n:
             b1, b2 = self.betas
             check(_lib.load().vlk_adamw_step(self.table.data_ptr(), self.n, self.max_numel, int(self.fp32),

@@ -8,12 +8,37 @@ clip_grad_norm_(1.0), set lr, optimizer.step()) with the CLIP ViT-L/14 forward i
 bridge, GPT-2 forward/backward, loss, gradient all-reduce, clip-norm + AdamW — into a CUDA graph, so a step is a
 single graph launch with no host work in between (shapes are static: B x 224 x 224 images, 31-token captions).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .caption import pool_clip_197_to_33_avg_with_cls
-from .dp import FlatGradBucket, FlatParamBucket
+from .dp import FlatGradBucket, FlatParamBucket, average_scalar_
+
+
+def _nccl_in_graph_default():
+    """Collectives are captured INSIDE the step's CUDA graph (one graph launch per step at any world size).
+    VLK_NCCL_OUTSIDE_GRAPH=1 restores the round-1 layout: separate graphs with the collectives launched between them."""
+    return not os.environ.get("VLK_NCCL_OUTSIDE_GRAPH")
+
+
+def _capture(graph, fn, pool=None, with_collectives=False):
+    """Capture fn() into graph.  With collectives inside, every rank first drains its stream and meets at a barrier
+    (no NCCL work may be in flight when capture starts), and the capture only polices the capturing thread — the
+    process group's watchdog thread keeps polling its own events."""
+    kw = {}
+    if pool is not None:
+        kw["pool"] = pool
+    if with_collectives:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        kw["capture_error_mode"] = "thread_local"
+    with torch.cuda.graph(graph, **kw):
+        fn()
+    return graph
 
 
 def _gpt_split_forward(model, idx, targets, split):
@@ -55,8 +80,8 @@ def _upper_range(bucket, blocks, split):
     for blk in blocks[split:]:
         for p in blk.parameters():
             if p.requires_grad:
-                return bucket.offset_of(p), bucket.extra_off
-    return bucket.extra_off, bucket.extra_off
+                return bucket.offset_of(p), bucket.params_end
+    return bucket.params_end, bucket.params_end
 
 
 class _CommOverlap:
@@ -77,7 +102,7 @@ class _CommOverlap:
 
 class CaptionTrainStep:
     def __init__(self, model, clip_tower, kind, batch, text_len=31, lr=1e-3, weight_decay=0.1, max_norm=1.0,
-                 use_graph=True, pixels_dtype=torch.float32, group=None, overlap_comm=None):
+                 use_graph=True, pixels_dtype=torch.float32, group=None, overlap_comm=None, nccl_in_graph=None):
         """kind: 'linear' | 'qformer' (GPT_Caption(patch_tokens, input_ids, labels)) or 'xattn'
         (GPT(idx, z, targets, target_mask)).
         overlap_comm (xattn only; default: on when data parallel): backward is cut in the middle of the stack and
@@ -94,10 +119,12 @@ class CaptionTrainStep:
         self.mask = torch.ones(batch, text_len, device=dev, dtype=torch.bool)
         self.loss = torch.zeros((), device=dev, dtype=torch.float32)
         self.norm = torch.zeros((), device=dev, dtype=torch.float32)
-        self.bucket = FlatGradBucket(model.parameters())
+        # the averaged loss rides in the front slots of the gradient bucket: ONE collective per step
+        self.bucket = FlatGradBucket(model.parameters(), scalar_slot=True)
         self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
         self.graph = None
         self._warm = 0
+        self.nccl_in_graph = _nccl_in_graph_default() if nccl_in_graph is None else bool(nccl_in_graph)
         if overlap_comm is None:
             overlap_comm = self._multi()
         self.overlap = bool(overlap_comm) and kind == "xattn"
@@ -129,21 +156,29 @@ class CaptionTrainStep:
         else:
             labels = self.y.masked_fill(~self.mask, -100)
             _, loss = self.model(z, self.x, labels=labels)
-        loss.backward()
+        with ops.residual_grad_inplace():     # this class owns every gradient tensor of the step
+            loss.backward()
         self.loss.copy_(loss.detach())
 
     def _phase2(self):
         """Lower half of backward, from the cut to the first layer."""
         outs, cuts = self._cut
-        torch.autograd.backward(outs, [c.grad for c in cuts])
+        with ops.residual_grad_inplace():
+            torch.autograd.backward(outs, [c.grad for c in cuts])
         self._cut = None
 
-    def _exchange(self):
-        """The one exchange step of the path: average the flat gradient bucket (and the scalar loss) over ranks."""
+    def _exchange(self, lo=0, hi=None):
+        """The one exchange step of the path: average the flat gradient bucket over ranks — and with it the step's
+        loss (train_gpt2.py:470-471), which travels as exact base-16 digits in the bucket's front slots."""
         if self._multi():
-            self.bucket.all_reduce(self.group)
-            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)   # train_gpt2.py:470-471 (AVG)
-            self.loss.div_(dist.get_world_size(self.group))
+            rides = self.bucket.scalar_rides_along(self.group)
+            if rides:
+                self.bucket.pack_scalar(self.loss)
+            self.bucket.all_reduce(self.group, lo, hi)
+            if rides:
+                self.bucket.unpack_scalar(self.loss)
+            else:
+                average_scalar_(self.loss, self.group)
 
     def _update(self):
         self.norm.copy_(self.opt.clip_grad_norm(self.max_norm))
@@ -159,10 +194,8 @@ class CaptionTrainStep:
 
     def _exchange_lower(self):
         if self._multi():
-            self.bucket.all_reduce(self.group, 0, self.upper[0])
+            self._exchange(0, self.upper[0])
             self.comm.join()
-            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
-            self.loss.div_(dist.get_world_size(self.group))
 
     def _body(self):
         if self.overlap:
@@ -176,8 +209,11 @@ class CaptionTrainStep:
         self._update()
 
     def set_lr(self, lr):
+        """optimizer.param_groups[i]['lr'] = lr (train_gpt2.py:474-475).  The learning rate lives in a device scalar
+        that the captured update reads, so the new value also reaches graph replays."""
         for g in self.opt.param_groups:
             g["lr"] = lr
+        self.opt.sync_lr()
 
     def load_batch(self, pixels, x, y, mask, non_blocking=True):
         """Host (pinned) or device tensors -> the static input buffers."""
@@ -188,8 +224,7 @@ class CaptionTrainStep:
 
     def run(self):
         """One optimizer step on the current contents of the static buffers. Returns the (device) loss tensor.
-        Single GPU: the whole step is one CUDA graph.  Data parallel: two graphs (forward+backward, clip+AdamW)
-        with the NCCL all-reduce launched between them on the same stream — collectives stay outside capture."""
+        The whole step — at any world size, including the gradient all-reduce — is one CUDA graph."""
         if not self.use_graph:
             self._body()
             return self.loss
@@ -203,9 +238,13 @@ class CaptionTrainStep:
                 torch.cuda.current_stream().wait_stream(s)
                 self._warm += 1
                 return self.loss
-            if self.overlap:
+            if not self._multi() or self.nccl_in_graph:
+                # ONE graph for the whole step at any world size: the NCCL collectives (and, with overlap, the fork
+                # onto the comm stream) are captured with the kernels
+                self.graph = _capture(torch.cuda.CUDAGraph(), self._body, with_collectives=self._multi())
+            elif self.overlap:
                 # three graphs: forward + upper backward | lower backward | update; the two halves of the gradient
-                # exchange are launched between them (NCCL stays outside capture), the first one on the comm stream
+                # exchange are launched between them, the first one on the comm stream
                 self.graph = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
                 with torch.cuda.graph(self.graph[0]):
                     self._fwd_phase1()
@@ -213,16 +252,12 @@ class CaptionTrainStep:
                     self._phase2()
                 with torch.cuda.graph(self.graph[2], pool=self.graph[0].pool()):
                     self._update()
-            elif self._multi():
+            else:
                 self.graph = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
                 with torch.cuda.graph(self.graph[0]):
                     self._fwd_bwd()
                 with torch.cuda.graph(self.graph[1]):
                     self._update()
-            else:
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._body()
         if isinstance(self.graph, tuple) and len(self.graph) == 3:
             self.graph[0].replay()
             self._exchange_upper_async()
@@ -283,7 +318,7 @@ class PretrainStep:
     slots) and one update (all-reduce + clip + AdamW)."""
 
     def __init__(self, model, micro_batch=16, seq=1024, grad_accum=32, lr=6e-4, weight_decay=0.1, max_norm=1.0,
-                 use_graph=True, group=None, overlap_comm=None, zero1=False):
+                 use_graph=True, group=None, overlap_comm=None, zero1=False, nccl_in_graph=None):
         """zero1: ZeRO-1 update (optim.Zero1AdamW) — the gradient bucket is reduce-scattered, every rank runs clip +
         AdamW on its 1/N slice of a flat parameter buffer (moments for that slice only), the slices are all-gathered.
         The update then runs eagerly (three collectives + two kernels per step); overlap_comm is ignored.
@@ -307,15 +342,17 @@ class PretrainStep:
             from .optim import Zero1AdamW
             world = dist.get_world_size(group) if self._multi_static(group) else 1
             rank = dist.get_rank(group) if world > 1 else 0
-            self.bucket = FlatGradBucket(model.parameters(), pad_multiple=8 * world)
+            self.bucket = FlatGradBucket(model.parameters(), scalar_slot=True, pad_multiple=8 * world)
             self.pbucket = FlatParamBucket(self.bucket)
             wds = [weight_decay if p.dim() >= 2 else 0.0 for p in self.bucket.params]   # train_gpt2.py:131-136
             self.opt = Zero1AdamW(self.bucket, self.pbucket, wds, lr=lr, rank=rank, world=world, group=group)
         else:
-            self.bucket = FlatGradBucket(model.parameters())
+            self.bucket = FlatGradBucket(model.parameters(), scalar_slot=True)
             self.opt = model.configure_optimizers(weight_decay, lr, "cuda")
-        self.g_micro = self.g_update = self.g_last = None
+        self.g_micro = self.g_update = self.g_last = self.g_tail = None
         self._warm = 0
+        self.nccl_in_graph = _nccl_in_graph_default() if nccl_in_graph is None else bool(nccl_in_graph)
+        self.phase_events = None      # set to [] to record (label, cuda event) pairs of one run() (bench.py)
         if overlap_comm is None:
             overlap_comm = self._multi()
         self.overlap = bool(overlap_comm) and not self.zero1
@@ -334,18 +371,21 @@ class PretrainStep:
 
     def _micro(self):
         _, loss = self.model(self.x, self.y)
-        (loss / self.grad_accum).backward()
+        with ops.residual_grad_inplace():     # this class owns every gradient tensor of the step
+            (loss / self.grad_accum).backward()
         self.loss += loss.detach() / self.grad_accum
 
     def _last_phase1(self):
         loss, outs, cuts = _gpt_split_forward(self.model, self.x, self.y, self.split)
         self._cut = (outs, cuts)
-        (loss / self.grad_accum).backward()
+        with ops.residual_grad_inplace():
+            (loss / self.grad_accum).backward()
         self.loss += loss.detach() / self.grad_accum
 
     def _last_phase2(self):
         outs, cuts = self._cut
-        torch.autograd.backward(outs, [c.grad for c in cuts])
+        with ops.residual_grad_inplace():
+            torch.autograd.backward(outs, [c.grad for c in cuts])
         self._cut = None
 
     def _exchange_upper_async(self):
@@ -355,17 +395,45 @@ class PretrainStep:
 
     def _exchange_lower(self):
         if self._multi():
-            self.bucket.all_reduce(self.group, 0, self.upper[0])
+            self._exchange(0, self.upper[0])
             self.comm.join()
-            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
-            self.loss.div_(dist.get_world_size(self.group))
 
-    def _exchange(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            if not self.zero1:                       # ZeRO-1 reduce-scatters inside its update instead
-                self.bucket.all_reduce(self.group)
-            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
-            self.loss.div_(dist.get_world_size(self.group))
+    def _exchange(self, lo=0, hi=None):
+        """Average the gradient bucket over ranks; the step's mean loss (train_gpt2.py:470-471) rides in its front
+        slots.  ZeRO-1 reduce-scatters the bucket inside its update instead: only the loss is exchanged here."""
+        if not self._multi():
+            return
+        if self.zero1:
+            average_scalar_(self.loss, self.group)
+            return
+        rides = self.bucket.scalar_rides_along(self.group)
+        if rides:
+            self.bucket.pack_scalar(self.loss)
+        self.bucket.all_reduce(self.group, lo, hi)
+        if rides:
+            self.bucket.unpack_scalar(self.loss)
+        else:
+            average_scalar_(self.loss, self.group)
+
+    def _tail(self):
+        """Last micro-step + gradient exchange + update (with overlap: the upper half of the exchange runs on the
+        comm stream under the lower half of the last backward)."""
+        if self.overlap:
+            self._last_phase1()
+            self._exchange_upper_async()
+            self._last_phase2()
+            self._exchange_lower()
+        else:
+            self._micro()
+            self._exchange()
+        self._mark("exchange")
+        self._update()
+
+    def _mark(self, label):
+        if self.phase_events is not None and not torch.cuda.is_current_stream_capturing():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_events.append((label, e))
 
     def _update(self):
         if self.zero1:
@@ -376,10 +444,11 @@ class PretrainStep:
 
     def set_lr(self, lr):
         if self.zero1:
-            self.opt.lr = lr
+            self.opt.set_lr(lr)
             return
         for g in self.opt.param_groups:
             g["lr"] = lr
+        self.opt.sync_lr()
 
     def load_tokens(self, x, y, non_blocking=True):
         """[grad_accum, micro_batch, seq] int64 (host pinned or device)."""
@@ -391,7 +460,11 @@ class PretrainStep:
         self.y.copy_(self.tokens_y[i])
 
     def run(self):
-        """One optimizer step over the grad_accum micro-batches currently in the token buffers."""
+        """One optimizer step over the grad_accum micro-batches currently in the token buffers.
+        Graph layout: ``g_micro`` replayed grad_accum-1 times, then ``g_tail`` = last micro-step + all-reduce +
+        clip + AdamW as ONE graph (collectives captured inside).  With VLK_NCCL_OUTSIDE_GRAPH=1 and several ranks
+        the round-1 layout is used instead (collectives launched between graphs)."""
+        self._mark("start")
         self.bucket.zero()
         self.loss.zero_()
         if not self.use_graph or self._warm < 1:
@@ -399,48 +472,54 @@ class PretrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                for i in range(self.grad_accum - (1 if self.overlap else 0)):
+                for i in range(self.grad_accum - 1):
                     self._set_slot(i)
                     self._micro()
-                if self.overlap:
-                    self._set_slot(self.grad_accum - 1)
-                    self._last_phase1()
-                    self._exchange_upper_async()
-                    self._last_phase2()
-                    self._exchange_lower()
-                else:
-                    self._exchange()
-                self._update()
+                self._set_slot(self.grad_accum - 1)
+                self._tail()
             torch.cuda.current_stream().wait_stream(s)
             self._warm += 1
             return self.loss
-        if self.g_update is None:
+        single_tail = not self._multi() or self.nccl_in_graph
+        if self.g_micro is None and self.g_tail is None and self.g_update is None:
             self._set_slot(0)
             pool = None
-            if not self.overlap or self.grad_accum > 1:
+            if self.grad_accum > 1 or not single_tail:
                 self.g_micro = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.g_micro):      # capture only records; nothing below has run yet
                     self._micro()
                 pool = self.g_micro.pool()
-            if self.overlap:
-                # the last micro-step as two graphs (down to the cut | the rest); they share the micro-step's
-                # memory pool — the three never run concurrently
-                self.g_last = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
-                with torch.cuda.graph(self.g_last[0], pool=pool):
-                    self._last_phase1()
-                with torch.cuda.graph(self.g_last[1], pool=self.g_last[0].pool()):
-                    self._last_phase2()
-            self.g_update = torch.cuda.CUDAGraph()
-            if not self.zero1:                       # the ZeRO-1 update holds collectives: it runs eagerly
-                with torch.cuda.graph(self.g_update):
-                    self._update()
+            if single_tail:
+                self.g_tail = _capture(torch.cuda.CUDAGraph(), self._tail, pool=pool, with_collectives=self._multi())
+            else:
+                if self.overlap:
+                    # the last micro-step as two graphs (down to the cut | the rest); they share the micro-step's
+                    # memory pool — the three never run concurrently
+                    self.g_last = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                    with torch.cuda.graph(self.g_last[0], pool=pool):
+                        self._last_phase1()
+                    with torch.cuda.graph(self.g_last[1], pool=self.g_last[0].pool()):
+                        self._last_phase2()
+                self.g_update = torch.cuda.CUDAGraph()
+                if not self.zero1:                       # the ZeRO-1 update holds collectives: it runs eagerly here
+                    with torch.cuda.graph(self.g_update):
+                        self._update()
+        if single_tail:
+            for i in range(self.grad_accum - 1):
+                self._set_slot(i)
+                self.g_micro.replay()
+            self._mark("micro_steps")
+            self._set_slot(self.grad_accum - 1)
+            self.g_tail.replay()
+            self._mark("tail")
+            return self.loss
         if self.overlap:
             for i in range(self.grad_accum - 1):
                 self._set_slot(i)
                 self.g_micro.replay()
             self._set_slot(self.grad_accum - 1)
             self.g_last[0].replay()
-            self._exchange_upper_async()           # NCCL stays outside graph capture, on the comm stream
+            self._exchange_upper_async()           # NCCL outside graph capture, on the comm stream
             self.g_last[1].replay()
             self._exchange_lower()
         else:
@@ -448,8 +527,10 @@ class PretrainStep:
                 self._set_slot(i)
                 self.g_micro.replay()
             self._exchange()
+        self._mark("exchange")
         if self.zero1:
             self._update()
         else:
             self.g_update.replay()
+        self._mark("update")
         return self.loss

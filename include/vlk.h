@@ -68,6 +68,14 @@ int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
                   void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
                   int split_k, void* stream);
 
+/* The same product with an explicit tile shape instead of the built-in choice (tile_n: 0 = automatic, 64 / 128 / 256
+ * output columns per CTA tile; cta_pair: -1 = automatic, 0 = one CTA per 128-row tile, 1 = cta_group::2 pair on a
+ * 256-row tile).  Every tile shape computes the same result; this entry exists for tuning sweeps and for the
+ * regression tests that exercise each kernel instantiation.  bias / residual / act as in vlk_gemm_bf16. */
+int vlk_gemm_bf16_tile(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                       int transA, int transB, const void* bias, const void* residual, int ldr, int act, int tile_n,
+                       int cta_pair, void* stream);
+
 /* Deterministic split-K product for few-tile / long-K shapes — the weight gradients dW = dy^T . x of nn.Linear
  * (autograd of train_gpt2.py:35,42,56-58: [768..3072] x [768..3072] outputs contracted over B*T = 16,384 rows fill
  * only 9..36 of the 74 tile slots) and d h = d logits . W (K = 50,304):
@@ -159,17 +167,19 @@ int vlk_pool33_l2norm(const void* in, void* out, int B, int D, int in_fp32, int 
  * out[b, prefix_len + t, :] = wte[ids[b,t], :] + wpe[pos0 + t, :];  out[b, 0:prefix_len, :] = prefix[b]
  * (prefix may be NULL with prefix_len == 0).  GPT.forward train_gpt2.py:114-117 and the caption
  * variant gpt2_linear/model.py:187-200 (image prefix gets no position embedding).
- * ids are int64 as produced by the reference data path.
+ * ids are int64 as produced by the reference data path; an id outside [0, vocab) poisons its output row with NaN
+ * (torch's embedding raises a device assert there) instead of reading outside wte.
  */
 int vlk_embed_concat_fwd(const long long* ids, const void* wte, const void* wpe, const void* prefix, void* out,
-                         int B, int T, int prefix_len, int C, int pos0, void* stream);
+                         int B, int T, int prefix_len, int C, int pos0, int vocab, void* stream);
 /* Gradient of the above w.r.t. wte / wpe (fp32 accumulators [V,C], [block,C]); pretraining only. */
 int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte, float* dwpe, int B, int T, int prefix_len,
                   int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Row-wise softmax cross-entropy statistics over materialised bf16 logits [rows, V] (ld in elements):
- *   loss_row[r] = logsumexp(logits[r]) - logits[r, label[r]]   (0 for ignored rows: label < 0)
+ *   loss_row[r] = logsumexp(logits[r]) - logits[r, label[r]]   (0 for ignored rows: label == -100, the
+ *   ignore_index of F.cross_entropy; NaN for any other label outside [0, V) — torch asserts there)
  * and, in place, logits[r,:] <- (softmax(logits[r]) - onehot(label[r])) * grad_scale[r]  when
  * write_grad != 0, where the caller supplies *inv_count (device fp32 scalar = 1/number of valid rows) and
  * an optional per-row fp32 weight (x-attn masked mean, gpt2_cross-att/model.py:176-185).
@@ -179,7 +189,7 @@ int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte, float* dw
  */
 int vlk_softmax_ce_rows(void* logits, const long long* labels, const float* row_weight, float* loss_row,
                         const float* inv_count, int rows, int V, int ld, int write_grad, void* stream);
-/* valid-count + mean: out[0] = sum(loss_row*w)/max(count,1), out[1] = 1/max(count,1), count = #labels>=0
+/* valid-count + mean: out[0] = sum(loss_row*w)/max(count,1), out[1] = 1/max(count,1), count = #labels != -100
  * (or sum of weights when row_weight != NULL). */
 int vlk_ce_count(const long long* labels, const float* row_weight, float* out, int rows, void* stream);
 int vlk_ce_finalize(const float* loss_row, const float* row_weight, float* out, int rows, void* stream);
@@ -229,6 +239,12 @@ int vlk_dropout_add_bf16(const void* x, const void* residual, void* y, long long
 /* gate gradient for the x-attn block (gpt2_cross-att/model.py:101):
  * out[0] += (1 - tanh(gate)^2) * sum(dy * y)  over n elements. */
 int vlk_gate_grad(const void* dy, const void* y, const float* gate, float* out, long long n, void* stream);
+/* A scalar riding in the gradient all-reduce (the averaged loss of train_gpt2.py:470-471 without a collective of its
+ * own): value (device fp32, 0 <= v < 256) <-> 8 slots of the flat gradient bucket (bf16, or fp32 when slots_fp32)
+ * holding the base-16 digits of its Q8.24 fixed-point form.  Digit sums over <= 16 ranks and the division by a
+ * power-of-two world size are exact, so unpack(average(pack(v_r))) = mean(v_r) to 2^-24. */
+int vlk_scalar_pack_digits(const float* value, void* slots, int slots_fp32, void* stream);
+int vlk_scalar_unpack_digits(const void* slots, float* value, int slots_fp32, void* stream);
 /* argmax over the last dim of bf16 [rows, V] -> int64 ids (greedy decode). */
 int vlk_argmax_rows(const void* logits, long long* out, int rows, int V, int ld, void* stream);
 

@@ -182,9 +182,6 @@ attn_case("CLIP B=64 H=16 T=257", 64, 16, 257, False, False)
 attn_case("GPT-2 caption B=64 H=12 T=64 causal", 64, 12, 64, True, True)
 attn_case("pretrain B=16 H=12 T=1024 causal", 16, 12, 1024, True, True)
 attn_case("Q-Former B=64 H=12 T=32", 64, 12, 32, False, True)
-os.environ["VLK_ATTN_IMPL"] = "small"
-attn_case("[CUDA-core kernel] GPT-2 caption B=64 H=12 T=64 causal", 64, 12, 64, True, True)
-os.environ.pop("VLK_ATTN_IMPL")
 
 # ---------------------------------------------------------------- GEMMs of the step
 def gemm_case(name, M, N, K, **kw):
@@ -231,13 +228,21 @@ gemm_case("GPT-2 c_attn caption (bias)", 4096, 2304, 768, use_bias=True)
 gemm_case("GPT-2 attn c_proj caption (bias+residual)", 4096, 768, 768, use_bias=True, use_res=True)
 gemm_case("GPT-2 c_fc caption (bias+gelu)", 4096, 3072, 768, use_bias=True, act="gelu_tanh")
 gemm_case("GPT-2 mlp c_proj caption (bias+residual)", 4096, 768, 3072, use_bias=True, use_res=True)
-for bn, cl in ((256, 1), (128, 1), (128, 3), (64, 1)):
-    os.environ["VLK_GEMM_BN"], os.environ["VLK_GEMM_CLUSTER"] = str(bn), str(cl)
-    gemm_case(f"[bn={bn} cluster={cl}] c_attn", 4096, 2304, 768, use_bias=True)
-    gemm_case(f"[bn={bn} cluster={cl}] attn c_proj", 4096, 768, 768, use_bias=True, use_res=True)
-    gemm_case(f"[bn={bn} cluster={cl}] c_fc", 4096, 3072, 768, use_bias=True, act="gelu_tanh")
-    gemm_case(f"[bn={bn} cluster={cl}] mlp c_proj", 4096, 768, 3072, use_bias=True, use_res=True)
-os.environ.pop("VLK_GEMM_BN"); os.environ.pop("VLK_GEMM_CLUSTER")
+def gemm_tile_case(name, M, N, K, bn, pair, **kw):
+    def mk(i):
+        return (torch.randn(M, K, device=dev).to(BF), torch.randn(N, K, device=dev).to(BF), torch.randn(N, device=dev).to(BF),
+                torch.randn(M, N, device=dev).to(BF))
+    bench(f"gemm [tile_n={bn} pair={pair}] {name} M={M} N={N} K={K}", mk,
+          lambda s: ops.gemm_tile(s[0], s[1], tile_n=bn, cta_pair=pair, bias=s[2],
+                                  residual=s[3] if kw.get("use_res") else None, act=kw.get("act")),
+          flops=2.0 * M * N * K, copies=2)
+
+
+for bn, pair in ((256, 0), (128, 0), (128, 1), (64, 0)):
+    gemm_tile_case("c_attn", 4096, 2304, 768, bn, pair)
+    gemm_tile_case("attn c_proj", 4096, 768, 768, bn, pair, use_res=True)
+    gemm_tile_case("c_fc", 4096, 3072, 768, bn, pair, act="gelu_tanh")
+    gemm_tile_case("mlp c_proj", 4096, 768, 3072, bn, pair, use_res=True)
 
 if not args.once:
     os.makedirs("gpurun_out", exist_ok=True)

@@ -1,5 +1,5 @@
 """The reference arm of bench.py (`--impl reference`: the oracle port of the reference algorithm on the host cores)
-keeps the one-JSON-line contract with the keys the driver reads.  Bounded to one short step here (VLK_BENCH_CPU_BUDGET_S)."""
+keeps the one-JSON-line contract with the keys the driver reads.  Bounded to one short step of a small batch here."""
 import json
 import os
 import subprocess
@@ -9,8 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    env = dict(os.environ, VLK_BENCH_CPU_BUDGET_S="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-batch", "1"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -20,7 +21,13 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["gpu_launches"] == 0 and 1 <= d["config"]["per_step_batch"] <= 64
+    assert d["gpu_launches"] == 0 and d["config"]["per_step_batch"] == 1
+
+
+def test_reference_arm_default_batch_is_a_constant():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.REF_BATCH == 16     # the reference arm's config does not float with the speed of the host CPU
 
 
 def test_reference_arm_nonzero_ranks_exit_quietly():

@@ -48,6 +48,22 @@ def test_token_shard_loader_matches_reference_arithmetic(tmp_path):
     assert not torch.equal(ranks[0], ranks[1])      # ranks read disjoint slices
 
 
+def test_token_shard_loader_matches_reference_dataloaderlite_golden(tmp_path):
+    """Against batches drawn from the reference's OWN DataLoaderLite (train_gpt2.py:148-187 exec'd by
+    oracle/make_golden.py over the same shard files): 70 batches per rank and split, so both train shards roll over
+    and the stream wraps around."""
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataloader_lite.pt"),
+                   weights_only=False)
+    for name, toks in zip(g["names"], g["shards"]):
+        np.save(tmp_path / name, toks.numpy().astype(np.uint16))
+    for (split, rank), ref in g["batches"].items():
+        ld = data.TokenShardLoader(g["B"], g["T"], rank, g["world"], split, str(tmp_path))
+        for i in range(ref["x"].shape[0]):
+            x, y = ld.next_batch()
+            assert torch.equal(x, ref["x"][i].long()) and torch.equal(y, ref["y"][i].long()), (split, rank, i)
+            assert ld.current_shard == int(ref["shard_after"][i]), (split, rank, i)
+
+
 def test_clip_token_shards_roundtrip(tmp_path):
     g = torch.Generator().manual_seed(1)
     batches = [torch.randn(b, 257, 16, generator=g) for b in (5, 3, 7)]

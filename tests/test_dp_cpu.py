@@ -26,8 +26,9 @@ def _worker(rank, world, port, out):
         p.requires_grad_(False)
     mod = torch.nn.Sequential(lin, frozen)
     broadcast_parameters(mod)                     # ... made identical by the one-time broadcast
-    bucket = FlatGradBucket(mod.parameters())
-    assert len(bucket.params) == 2 and lin.weight.grad.data_ptr() == bucket.flat.data_ptr()
+    bucket = FlatGradBucket(mod.parameters(), scalar_slot=True)
+    assert len(bucket.params) == 2 and bucket.params_off == 8
+    assert lin.weight.grad.data_ptr() == bucket.flat[bucket.params_off:].data_ptr()
     bucket.zero()
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(5, 24, generator=g)
@@ -35,10 +36,19 @@ def _worker(rank, world, port, out):
     local = bucket.flat.clone()
     # the exchange in two ranges (the split-backward overlap path reduces the tail of the bucket first) ...
     k = bucket.offset_of(lin.bias)
-    assert 0 < k < bucket.extra_off
-    bucket.all_reduce(lo=k, hi=bucket.extra_off)
+    assert 0 < k < bucket.params_end
+    bucket.all_reduce(lo=k, hi=bucket.params_end)
     assert torch.equal(bucket.flat[:k], local[:k])            # ... leaves the head untouched until its own turn
+    # the step's loss rides in the head range as exact base-16 digits (FlatGradBucket.pack_scalar)
+    loss = torch.tensor(3.25 + 1.0 / 3.0 + rank * 2.7182818)
+    assert bucket.scalar_rides_along()
+    bucket.pack_scalar(loss)
+    local[:8] = bucket.flat[:8]
     bucket.all_reduce(lo=0, hi=k)
+    mean_loss = torch.zeros(())
+    bucket.unpack_scalar(mean_loss)
+    expect = sum(float(torch.tensor(3.25 + 1.0 / 3.0 + r * 2.7182818)) for r in range(world)) / world
+    assert abs(mean_loss.item() - expect) < 2e-7, (mean_loss.item(), expect)
     two_step = bucket.flat.clone()
     bucket.flat.copy_(local)
     bucket.all_reduce()
@@ -64,4 +74,28 @@ def test_flat_bucket_allreduce_world2():
     assert not torch.allclose(l0, l1)                            # different data -> different local grads
     assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-6)          # AVG, like DDP
     assert torch.equal(a0, a1)
-    assert torch.allclose(g0.flatten(), a0[: g0.numel()])        # .grad is a view of the reduced bucket
+    assert torch.allclose(g0.flatten(), a0[8: 8 + g0.numel()])   # .grad is a view of the reduced bucket (after the scalar slots)
+
+
+def test_scalar_digits_survive_bf16_reduction_exactly():
+    """The loss travels through a bf16 AVG all-reduce as 8 base-16 digits: whatever the order of the additions (ring,
+    tree, in-switch) and with every partial sum rounded to bf16, the mean is recovered to the Q8.24 resolution."""
+    from gpt2_vision_language_b200.dp import FlatGradBucket
+    g = torch.Generator().manual_seed(0)
+    for world in (2, 4, 8, 16):
+        for _ in range(20):
+            losses = torch.rand(world, generator=g) * 12.0
+            buckets = []
+            for r in range(world):
+                b = FlatGradBucket([torch.nn.Parameter(torch.zeros(4, dtype=torch.bfloat16))], scalar_slot=True)
+                b.pack_scalar(losses[r])
+                buckets.append(b)
+            order = torch.randperm(world, generator=g).tolist()
+            acc = torch.zeros(8, dtype=torch.bfloat16)
+            for r in order:                                   # bf16 accumulator: rounded after every addition
+                acc = (acc + buckets[r].flat[:8]).to(torch.bfloat16)
+            buckets[0].flat[:8] = (acc / world).to(torch.bfloat16)
+            out = torch.zeros(())
+            buckets[0].unpack_scalar(out)
+            expect = sum(round(float(x) * (1 << 24)) for x in losses) / world / (1 << 24)
+            assert abs(out.item() - expect) < 1e-6, (world, out.item(), expect)

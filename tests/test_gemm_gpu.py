@@ -27,20 +27,19 @@ def _check(out, ref, tol=2e-2):
                                    (1984, 2304, 768), (2112, 768, 768), (300, 64, 192), (77, 264, 72),
                                    (512, 50304, 768)])
 @pytest.mark.parametrize("bn", [None, 256, 128, 64])
-def test_gemm_nt_plain(cuda, M, N, K, bn, monkeypatch):
+def test_gemm_nt_plain(cuda, M, N, K, bn):
     from gpt2_vision_language_b200 import ops
-    if bn is not None:
-        monkeypatch.setenv("VLK_GEMM_BN", str(bn))
-    else:
-        monkeypatch.delenv("VLK_GEMM_BN", raising=False)
     if bn is not None and M * N > 20e6:
         pytest.skip("forced-tile sweep only on small/medium shapes")
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
     b = torch.randn(N, K, device=cuda, generator=g).bfloat16()
-    out = ops.gemm(a, b)
     ref = a.float() @ b.float().t()
-    _check(out, ref)
+    if bn is None:
+        _check(ops.gemm(a, b), ref)
+    else:                      # every tile width, as a CTA pair (cta_group::2) and as single CTAs
+        for pair in ((0, 1) if bn >= 128 else (0,)):
+            _check(ops.gemm_tile(a, b, tile_n=bn, cta_pair=pair), ref)
 
 
 @pytest.mark.parametrize("act", ["gelu_tanh", "gelu_erf", "quick_gelu", None])

@@ -82,6 +82,40 @@ def test_caption_xattn_matches_reference_golden():
         close(sd[n].grad, ref, 5e-4)
 
 
+@pytest.mark.parametrize("case", ["cls_only", "patch_tokens_2d", "truncate_text", "ignored_sample"])
+def test_caption_edge_cases_match_reference_golden(case):
+    """use_cls_only, 2-D patch_tokens, text truncation at block_size and a fully ignored sample
+    (source/gpt2_linear/model.py:178-196, 206-210) — outputs of the reference module itself."""
+    g = load("caption_edge_tiny.pt")[case]
+    sd = leafify(g["sd"], g["grads"].keys())
+    logits, loss = O.caption_linear_forward(sd, g["z"], g["input_ids"], g["labels"], g["cfg"]["n_layer"],
+                                            g["cfg"]["n_head"], use_cls_only=g["kw"].get("use_cls_only", False),
+                                            block_size=g["cfg"]["block_size"])
+    assert logits.shape == g["logits"].shape
+    close(logits.detach(), g["logits"])
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    loss.backward()
+    for n, ref in g["grads"].items():
+        close(sd[n].grad, ref, 5e-4)
+
+
+@pytest.mark.parametrize("case", ["xattn_masked_sample", "xattn_all_masked"])
+def test_xattn_masked_loss_edge_cases_match_reference_golden(case):
+    """Masked-mean CE with a fully masked sample, and with every token masked: 0 / clamp_min(1) = 0 with zero
+    gradients (source/gpt2_cross-att/model.py:176-185)."""
+    g = load("caption_edge_tiny.pt")[case]
+    sd = leafify(g["sd"], g["grads"].keys())
+    logits, loss = O.xattn_forward(sd, g["idx"], g["z"], g["targets"], g["mask"], g["cfg"]["n_layer"], g["cfg"]["n_head"])
+    close(logits.detach(), g["logits"])
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    loss.backward()
+    for n, ref in g["grads"].items():
+        if ref.abs().max() == 0:
+            assert sd[n].grad is None or sd[n].grad.abs().max() == 0
+        else:
+            close(sd[n].grad, ref, 5e-4)
+
+
 def test_clip_matches_hf_golden():
     g = load("clip_tiny.pt")
     px = g["pixels"].float()

@@ -239,3 +239,109 @@ def test_zero1_update_matches_full_update(cuda):
             # same arithmetic per element; only the summation order of the global norm differs (clip factor +-1e-7),
             # which can move a value across a bf16 rounding boundary once in a while
             assert worst < 5e-4 and differ / count < 1e-3, (worst, differ, count)
+
+
+def test_optimizer_resume_from_cpu_mapped_checkpoint(cuda, tmp_path):
+    """save_checkpoint -> load_checkpoint(map_location='cpu') -> load_state_dict -> step(): the step counter the AdamW
+    kernel dereferences must live on the parameters' device again, and the resumed run must continue exactly like the
+    uninterrupted one (reference resume: source/gpt2/train_gpt2.py:319-325)."""
+    from gpt2_vision_language_b200 import data, gpt2
+    g = load("gpt2_tiny.pt")
+
+    def fresh():
+        m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+        m.load_state_dict(g["sd"])
+        return m.to(cuda).to(torch.bfloat16)
+    gen = torch.Generator().manual_seed(9)
+    xs = torch.randint(0, 256, (4, 3, 24), generator=gen).to(cuda)
+    ys = torch.randint(0, 256, (4, 3, 24), generator=gen).to(cuda)
+
+    def one_step(m, opt, i):
+        opt.zero_grad(set_to_none=True)
+        _, loss = m(xs[i], ys[i])
+        loss.backward()
+        opt.clip_grad_norm(1.0)
+        opt.step()
+        return loss.item()
+    a = fresh()
+    opt_a = a.configure_optimizers(0.1, 3e-3, "cuda")
+    for i in range(2):
+        one_step(a, opt_a, i)
+    path = str(tmp_path / "ckpt.pt")
+    data.save_checkpoint(path, a, opt_a, step=2, val_loss=1.0)
+    b = fresh()
+    opt_b = b.configure_optimizers(0.1, 3e-3, "cuda")
+    start = data.load_checkpoint(path, b, opt_b)            # default map_location = 'cpu'
+    assert start == 3
+    assert opt_b._step_t.is_cuda and opt_b._step_t.item() == 2.0
+    la = [one_step(a, opt_a, i) for i in (2, 3)]
+    lb = [one_step(b, opt_b, i) for i in (2, 3)]
+    assert la == pytest.approx(lb, rel=1e-3)
+    wa = torch.cat([p.detach().float().flatten() for p in a.parameters()])
+    wb = torch.cat([p.detach().float().flatten() for p in b.parameters()])
+    assert (wa - wb).abs().max().item() < 2e-3
+
+
+def test_learning_rate_and_weight_decay_changes_reach_the_captured_update(cuda):
+    """param_groups[i]['lr'] = x (train_gpt2.py:474-475) must change what a REPLAYED CUDA graph does, and a changed
+    weight_decay must rebuild the device table it is baked into."""
+    from gpt2_vision_language_b200 import gpt2
+    from gpt2_vision_language_b200.step import PretrainStep
+    g = load("gpt2_tiny.pt")
+    m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+    m.load_state_dict(g["sd"])
+    m = m.to(cuda).to(torch.bfloat16)
+    st = PretrainStep(m, micro_batch=2, seq=24, grad_accum=1, lr=1e-3, use_graph=True)
+    gen = torch.Generator().manual_seed(2)
+    st.load_tokens(torch.randint(0, 256, (1, 2, 24), generator=gen).to(cuda), torch.randint(0, 256, (1, 2, 24), generator=gen).to(cuda))
+    w = m.transformer.h[0].mlp.c_fc.weight
+
+    def delta():
+        before = w.detach().float().clone()
+        st.run()
+        torch.cuda.synchronize()
+        return (w.detach().float() - before).abs().mean().item()
+    for _ in range(3):                       # eager warm-up, capture, first replay
+        delta()
+    d1 = delta()
+    st.set_lr(0.0)
+    before = w.detach().clone()
+    st.run()
+    torch.cuda.synchronize()
+    assert torch.equal(before, w.detach())                     # lr = 0 under graph replay: the weights do not move
+    st.set_lr(4e-3)
+    assert delta() > 2.0 * d1                                  # 4 x lr: Adam's normalised update scales with lr
+    # weight decay is part of the optimizer's device table
+    opt = st.opt
+    keys0 = opt._table_key
+    opt.param_groups[0]["weight_decay"] = 0.5
+    opt.clip_grad_norm(1.0)
+    assert opt._table_key != keys0
+
+
+def test_out_of_range_ids_and_labels_poison_the_loss(cuda):
+    """torch raises device asserts for an out-of-vocabulary token id / label; the B200 path makes the loss NaN instead of
+    reading out of bounds.  Only -100 is the ignore_index."""
+    from gpt2_vision_language_b200 import gpt2, ops
+    g = load("gpt2_tiny.pt")
+    m = gpt2.GPT(gpt2.GPTConfig(**g["cfg"]))
+    m.load_state_dict(g["sd"])
+    m = m.to(cuda).to(torch.bfloat16)
+    idx, tgt = g["idx"].to(cuda), g["targets"].to(cuda)
+    with torch.no_grad():
+        ok = m(idx, tgt)[1].item()
+        bad_label = tgt.clone()
+        bad_label[0, 0] = 256                                   # == vocab_size
+        assert torch.isnan(m(idx, bad_label)[1]).item()
+        neg_label = tgt.clone()
+        neg_label[0, 0] = -5                                    # negative but not ignore_index
+        assert torch.isnan(m(idx, neg_label)[1]).item()
+        ign = tgt.clone()
+        ign[0, :5] = -100
+        v = m(idx, ign)[1].item()
+        assert v == v and abs(v - ok) < 0.5
+        bad_id = idx.clone()
+        bad_id[1, 3] = 999
+        assert torch.isnan(m(bad_id, tgt)[1]).item()
+    rows = ops.cross_entropy_rows(torch.randn(4, 256, device=cuda).bfloat16(), torch.tensor([1, -100, 256, 7], device=cuda))
+    assert rows[1].item() == 0.0 and torch.isnan(rows[2]).item() and rows[0].item() > 0
