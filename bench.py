@@ -274,11 +274,15 @@ def parity_leg(torch, workload, model, clip, clip_sd, step, batch, time_steps=2)
     flat_gpu = torch.cat([g_gpu[n].flatten() for n in names]).double()
     flat_cpu = torch.cat([g_cpu[n].flatten() for n in names]).double()
     cos_all = torch.nn.functional.cosine_similarity(flat_gpu, flat_cpu, dim=0).item()
-    cos_min = min(torch.nn.functional.cosine_similarity(g_gpu[n].flatten().double(), g_cpu[n].flatten().double(), dim=0).item()
-                  for n in names)
+    per = {n: torch.nn.functional.cosine_similarity(g_gpu[n].flatten().double(), g_cpu[n].flatten().double(), dim=0).item()
+           for n in names}
+    worst = min(per, key=per.get)
+    cos_min = per[worst]
+    share = (g_cpu[worst].double().norm() / flat_cpu.norm()).item()
     rel = abs(loss_gpu - loss_cpu) / abs(loss_cpu)
     parity = {"batch": Bc, "loss_gpu": loss_gpu, "loss_oracle": loss_cpu, "rel": rel, "grad_cos": cos_all,
-              "grad_cos_min_tensor": cos_min, "trainable_tensors": len(names),
+              "grad_cos_min_tensor": cos_min, "grad_cos_min_tensor_name": worst,
+              "grad_cos_min_tensor_share_of_grad_norm": share, "trainable_tensors": len(names),
               "ok": bool(rel < 2e-3 and cos_all > 0.999),
               "what": "first-step loss and trainable gradients, pixels -> CLIP ViT-L/14 -> pool -> bridge -> GPT-2 124M -> CE, "
                       "B200 path vs fp32 CPU oracle on the same bf16-rounded weights"}

@@ -37,7 +37,7 @@ SIGNATURES = {
                           c_void_p],
     "vlk_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_int, c_int, c_int, c_void_p],
-    "vlk_sum_copies": [c_void_p, c_int, c_ll, c_void_p, c_int, c_void_p],
+    "vlk_sum_copies": [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
     "vlk_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                      c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float,
                      c_float, c_void_p, ctypes.c_uint, c_void_p],
@@ -52,7 +52,14 @@ SIGNATURES = {
     "vlk_scalar_pack_digits": [c_void_p, c_void_p, c_int, c_void_p],
     "vlk_scalar_unpack_digits": [c_void_p, c_void_p, c_int, c_void_p],
     "vlk_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "vlk_embed_bwd_acc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                          c_void_p],
     "vlk_softmax_ce_rows": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "vlk_lmhead_ce_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],
+    "vlk_lmhead_ce_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                          c_int, c_void_p, c_ll, c_void_p],
+    "vlk_lmhead_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p],
     "vlk_ce_count": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "vlk_ce_finalize": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "vlk_grad_sumsq": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
@@ -67,7 +74,7 @@ SIGNATURES = {
     "vlk_gate_grad": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "vlk_argmax_rows": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"vlk_last_error_string": ctypes.c_char_p, "vlk_launch_count": c_ll}
+_RESTYPES = {"vlk_last_error_string": ctypes.c_char_p, "vlk_launch_count": c_ll, "vlk_lmhead_ce_workspace_bytes": c_ll}
 
 
 class TensorDesc(ctypes.Structure):

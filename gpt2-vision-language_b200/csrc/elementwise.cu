@@ -134,6 +134,70 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Embedding gradient accumulated into bf16 rows without dense [V, C] temporaries (vlk_embed_bwd_acc).
+//   A: first[id] = min position holding that id          B: scratch[first[id_p]] += dout[p]   (fp32 atomics)
+//   C: positions that ARE a first position add their scratch row into dwte[id] (one owner per row: plain RMW),
+//      then restore the workspaces (scratch row = 0, first[id] = INT_MAX)
+//   D: dwpe[t] += sum_b dout[b, t]
+// ---------------------------------------------------------------------------------------------------
+__global__ void embed_first_pos_kernel(const long long* __restrict__ ids, int* __restrict__ first, int n, int vocab) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const long long id = ids[p];
+    if (id >= 0 && id < vocab) atomicMin(first + id, p);
+}
+__global__ void embed_scatter_kernel(const long long* __restrict__ ids, const bf16* __restrict__ dout,
+                                     const int* __restrict__ first, float* __restrict__ scratch, int T, int prefix_len,
+                                     int C, int vocab) {
+    const int p = blockIdx.x, b = p / T, t = p % T;
+    const long long id = ids[p];
+    if (id < 0 || id >= vocab) return;
+    const bf16* g = dout + (static_cast<size_t>(b) * (prefix_len + T) + prefix_len + t) * C;
+    float* dst = scratch + static_cast<size_t>(first[id]) * C;
+    for (int col = threadIdx.x * 8; col < C; col += blockDim.x * 8) {
+        float f[8];
+        unpack8(ldg16(g + col), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + col + i, f[i]);
+    }
+}
+__global__ void embed_flush_kernel(const long long* __restrict__ ids, int* __restrict__ first,
+                                   float* __restrict__ scratch, bf16* __restrict__ dwte, int C, int vocab) {
+    const int p = blockIdx.x;
+    const long long id = ids[p];
+    if (id < 0 || id >= vocab || first[id] != p) return;     // block-uniform
+    float* src = scratch + static_cast<size_t>(p) * C;
+    bf16* dst = dwte + static_cast<size_t>(id) * C;
+    for (int col = threadIdx.x * 8; col < C; col += blockDim.x * 8) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(dst + col), a);
+        const float4 s0 = *reinterpret_cast<const float4*>(src + col), s1 = *reinterpret_cast<const float4*>(src + col + 4);
+        a[0] += s0.x; a[1] += s0.y; a[2] += s0.z; a[3] += s0.w;
+        a[4] += s1.x; a[5] += s1.y; a[6] += s1.z; a[7] += s1.w;
+        stg16(dst + col, pack8(a));
+        *reinterpret_cast<float4*>(src + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(src + col + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) first[id] = 0x7fffffff;
+}
+__global__ void embed_wpe_grad_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dwpe, int B, int T,
+                                      int prefix_len, int C) {
+    const int t = blockIdx.x;
+    for (int col = threadIdx.x * 8; col < C; col += blockDim.x * 8) {
+        float acc[8];
+        unpack8(*reinterpret_cast<const uint4*>(dwpe + static_cast<size_t>(t) * C + col), acc);
+        for (int b = 0; b < B; ++b) {
+            float f[8];
+            unpack8(ldg16(dout + (static_cast<size_t>(b) * (prefix_len + T) + prefix_len + t) * C + col), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+        stg16(dwpe + static_cast<size_t>(t) * C + col, pack8(acc));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // CLIP patch unfold: pixels [B,3,224,224] -> rows [B*256, Kpad], k = c*196 + i*14 + j.
 // One block per (image, patch row); thread x walks one pixel column of the 224-wide stripe.
 // ---------------------------------------------------------------------------------------------------
@@ -423,6 +487,33 @@ extern "C" int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte
     embed_bwd_kernel<<<B * T, 96, 0, static_cast<cudaStream_t>(stream)>>>(ids, static_cast<const bf16*>(dout), dwte,
                                                                          dwpe, T, prefix_len, C);
     VLK_CHECK_LAUNCH("vlk_embed_bwd");
+    return VLK_OK;
+}
+
+extern "C" int vlk_embed_bwd_acc(const long long* ids, const void* dout, void* dwte, void* dwpe, int* first_pos,
+                                 float* scratch, int B, int T, int prefix_len, int C, int vocab, void* stream) {
+    VLK_REQUIRE(ids && dout && (dwte || dwpe), VLK_ERR_INVALID_ARG, "vlk_embed_bwd_acc: null pointer");
+    VLK_REQUIRE(!dwte || (first_pos && scratch), VLK_ERR_INVALID_ARG, "vlk_embed_bwd_acc: workspaces missing");
+    VLK_REQUIRE(B > 0 && T > 0 && C % 8 == 0 && vocab > 0, VLK_ERR_INVALID_ARG, "vlk_embed_bwd_acc: shape");
+    VLK_REQUIRE(aligned16(dout) && (!dwte || aligned16(dwte)) && (!dwpe || aligned16(dwpe)) && (!scratch || aligned16(scratch)),
+                VLK_ERR_ALIGNMENT, "vlk_embed_bwd_acc: 16B alignment");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = B * T;
+    const int threads = C / 8 >= 96 ? 96 : ((C / 8 + 31) / 32) * 32;
+    if (dwte) {
+        embed_first_pos_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, first_pos, n, vocab);
+        VLK_CHECK_LAUNCH("vlk_embed_bwd_acc(first)");
+        embed_scatter_kernel<<<n, threads, 0, s>>>(ids, static_cast<const bf16*>(dout), first_pos, scratch, T, prefix_len, C,
+                                                  vocab);
+        VLK_CHECK_LAUNCH("vlk_embed_bwd_acc(scatter)");
+        embed_flush_kernel<<<n, threads, 0, s>>>(ids, first_pos, scratch, static_cast<bf16*>(dwte), C, vocab);
+        VLK_CHECK_LAUNCH("vlk_embed_bwd_acc(flush)");
+    }
+    if (dwpe) {
+        embed_wpe_grad_kernel<<<T, threads, 0, s>>>(static_cast<const bf16*>(dout), static_cast<bf16*>(dwpe), B, T, prefix_len,
+                                                   C);
+        VLK_CHECK_LAUNCH("vlk_embed_bwd_acc(wpe)");
+    }
     return VLK_OK;
 }
 

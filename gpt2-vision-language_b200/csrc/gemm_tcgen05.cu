@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gemm_internal.cuh"
 #include "ptx.cuh"
 
 namespace vlk {
@@ -50,6 +51,19 @@ struct EpiParams {
     const float* ln_sums;
     float ln_inv_k, ln_eps;
     float* stats_out;   // [M][2] fp32, accumulated with atomicAdd: row sums of the bf16-ROUNDED outputs and of their squares
+    // Fused lm_head + softmax cross-entropy (vlk_lmhead_ce_fwd / _bwd, lmhead_ce.cu).  The accumulator tile holds LOGITS:
+    //   ce_mode 1 (forward): nothing is stored to D; every epilogue warp reduces its 32 rows x (BLOCK_N/2) logits to a
+    //     running (max, sum exp) pair per row -> ce_partial[slice][row], slice = column / (BLOCK_N/2), and the thread
+    //     that meets the row's label column writes that logit to ce_label_logit[row];
+    //   ce_mode 2 (backward): D[m,n] = bf16((exp(logit - ce_lse[m]) - [n + ce_col0 == label[m]]) * ce_row_scale[m]),
+    //     i.e. d loss / d logits of this vocabulary chunk, recomputed instead of read back.
+    int ce_mode;
+    const long long* ce_labels;
+    float2* ce_partial;
+    float* ce_label_logit;
+    const float* ce_lse;
+    const float* ce_row_scale;
+    int ce_col0;
 #ifdef VLK_BRINGUP
     int debug;  // bring-up builds only (env VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
 #endif
@@ -76,6 +90,65 @@ struct SmemLayout {
     static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024B alignment
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ce_mode 2 on 32 logits of one row starting at chunk-local column col0: v <- (softmax - onehot) * row scale.
+__device__ __forceinline__ void ce_grad32(const EpiParams& ep, float (&v)[32], int row, int col0) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float nlse = -__ldg(ep.ce_lse + row) * kLog2e;
+    const float w = __ldg(ep.ce_row_scale + row);
+    const long long hit = ep.ce_labels[row] - ep.ce_col0 - col0;     // index of the label inside these 32 columns
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float p = ex2_approx(fmaf(v[i], kLog2e, nlse));
+        v[i] = (p - (hit == i ? 1.0f : 0.0f)) * w;
+    }
+}
+
+// ce_mode 1: one warp reduces its 32 rows x ncols_warp logits (TMEM) to (max, sum exp) per row and picks the label logit.
+__device__ __forceinline__ void ce_stats_warp(const EpiParams& ep, uint32_t taddr, int row0, int n0, int ncols_warp, int M,
+                                              int N, int lane) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int row = row0 + lane;
+    const long long label = row < M ? ep.ce_labels[row] : -1;
+    float m = -INFINITY, s = 0.f;     // running max (in units of log2: logit * log2e) and sum of 2^(x - m)
+#pragma unroll 1
+    for (int c = 0; c < ncols_warp; c += 32) {
+        const int col0 = n0 + c;
+        if (col0 >= N) break;  // warp-uniform
+        const int ncols = min(32, N - col0);
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r[i]) * ep.alpha;
+            if (i < ncols) cm = fmaxf(cm, v[i]);
+        }
+        const long long hit = label - col0;
+        if (hit >= 0 && hit < ncols) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (hit == i) ep.ce_label_logit[row] = v[i];
+        }
+        const float nm = fmaxf(m, cm * kLog2e);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols) acc += ex2_approx(fmaf(v[i], kLog2e, -nm));
+        s = s * ex2_approx(m - nm) + acc;     // first chunk: m = -inf -> factor 0
+        m = nm;
+    }
+    if (row < M && n0 < N)
+        ep.ce_partial[static_cast<size_t>(n0 / ncols_warp) * M + row] = make_float2(m, s);
+}
+
 // Apply the epilogue to 32 consecutive accumulator columns of one row and store them.
 __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint32_t (&acc)[32], int row, int col0,
                                                  int ncols_valid, size_t d_off) {
@@ -97,6 +170,7 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
         for (int i = 0; i < 32; ++i)
             if (i < ncols_valid) v[i] = rs * (v[i] - mu * __ldg(ep.ln_colsum + col0 + i));
     }
+    if (ep.ce_mode == 2) ce_grad32(ep, v, row, col0);
     if (ep.bias != nullptr) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -260,7 +334,7 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* 
 // time inside the unrolled loops the kernel was 12.6 k SASS instructions (erff alone is inlined 64 times) and the
 // epilogue warps lost ~15 % of their issue slots to instruction-cache misses (`no_inst`,
 // profiles/r01_ncu_gemm_residual_source_summary.txt).  The dispatcher below picks one compact body per launch.
-template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF, int STATS = 0>
+template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF, int STATS = 0, int CE = 0>
 __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                                 int ncols_warp, int M, int N, int lane, size_t d_off) {
     const int row = row0 + lane;
@@ -305,6 +379,9 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
                 const int hc0 = col0 + h * 32;
                 const int hcols = min(32, N - hc0);
+                if (CE != 0) {
+                    if (row < M) ce_grad32(ep, v, row, hc0);
+                }
                 if (ln_fold) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -406,6 +483,10 @@ template <bool SPECIALISE>
 __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
                                               int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
     if (VLK_DBG_SKIP_EPILOGUE(ep)) return;
+    if (ep.ce_mode == 1) {
+        ce_stats_warp(ep, taddr, row0, n0, ncols_warp, M, N, lane);
+        return;
+    }
     if (ep.out_fp32 || ncols_warp < 64) {
         // fp32 output (split-K slabs) and 32-column slices keep the direct row-per-thread path
         const int row = row0 + lane;
@@ -425,6 +506,10 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
 #define VLK_EPI_LN(ACT) \
     epilogue_warp_t<ACT, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
+    if (ep.ce_mode == 2) {   // d logits of a vocabulary chunk: plain staged store of the transformed tile
+        epilogue_warp_t<0, 0, 0, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+        return;
+    }
     if constexpr (!SPECIALISE) {
         epilogue_warp_t<-1, -1, -1, -1, -1, -1, -1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
         return;
@@ -1006,17 +1091,31 @@ int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, 
 }
 
 }  // namespace
+
+int splitk_reduce(const float* ws, int splits, long long slab, void* out, int M, int N, int ldd, int accumulate,
+                  cudaStream_t stream) {
+    const long long work = slab / 8;
+    const int sms = device_sm_count();
+    long long blocks = (work + 255) / 256;
+    if (blocks > sms * 8LL) blocks = sms * 8LL;
+    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(ws, splits, slab, static_cast<bf16*>(out), M, N,
+                                                                            ldd, accumulate);
+    VLK_CHECK_LAUNCH("vlk_gemm_bf16_splitk(reduce)");
+    return VLK_OK;
+}
 }  // namespace vlk
 
 using namespace vlk;
 
-static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
-                     int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
-                     void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
-                     int split_k, long long split_stride, int* split_used, void* stream,
-                     const float* ln_mean = nullptr, const float* ln_rstd = nullptr, const float* ln_colsum = nullptr,
-                     const float* ln_sums = nullptr, float ln_eps = 0.f, float* stats_out = nullptr,
-                     int bn_override = 0, int pair_override = -1) {
+int vlk::gemm_tile_n(int N) { return N >= 192 ? 256 : (N >= 96 ? 128 : 64); }
+
+int vlk::gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                   int transA, int transB, const void* bias, const void* residual, int ldr, const void* aux_in,
+                   void* aux_out, int ld_aux, const float* scale, int act, int dact, float alpha, int out_fp32,
+                   int split_k, long long split_stride, int* split_used, void* stream,
+                   const float* ln_mean, const float* ln_rstd, const float* ln_colsum,
+                   const float* ln_sums, float ln_eps, float* stats_out,
+                   int bn_override, int pair_override, const CeEpilogue* ce) {
     VLK_REQUIRE(A && B && D, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: null operand");
     VLK_REQUIRE(M > 0 && N > 0 && K > 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     VLK_REQUIRE(N % 8 == 0, VLK_ERR_INVALID_ARG, "vlk_gemm_bf16: N=%d must be a multiple of 8", N);
@@ -1072,6 +1171,22 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     ep.ln_inv_k = 1.0f / static_cast<float>(K);
     ep.ln_eps = ln_eps;
     ep.stats_out = stats_out;
+    ep.ce_mode = 0;
+    ep.ce_labels = nullptr;
+    ep.ce_partial = nullptr;
+    ep.ce_label_logit = nullptr;
+    ep.ce_lse = nullptr;
+    ep.ce_row_scale = nullptr;
+    ep.ce_col0 = 0;
+    if (ce != nullptr) {
+        ep.ce_mode = ce->mode;
+        ep.ce_labels = ce->labels;
+        ep.ce_partial = reinterpret_cast<float2*>(ce->partial);
+        ep.ce_label_logit = ce->label_logit;
+        ep.ce_lse = ce->lse;
+        ep.ce_row_scale = ce->row_scale;
+        ep.ce_col0 = ce->col0;
+    }
 #ifdef VLK_BRINGUP
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
@@ -1080,7 +1195,7 @@ static int gemm_impl(const void* A, const void* B, void* D, int M, int N, int K,
     // Tile selection (measured on B200, profiles/r01_gemm_sweep*.log): the 256-wide tile wins on every shape of
     // this path (fewer, longer tiles amortise the epilogue; N = 768/1024/2304/3072/4096/50304 all tile well), and
     // the cta_group::2 pair wins or ties whenever there are at least two 128-row blocks.
-    int bn = N >= 192 ? 256 : (N >= 96 ? 128 : 64);
+    int bn = gemm_tile_n(N);
     int cluster = (M > BLOCK_M && bn >= 128 && sms % 2 == 0) ? 3 : 1;
     (void)tile_cost;
     if (bn_override == 256 || bn_override == 128 || bn_override == 64) {   // vlk_gemm_bf16_tile only
@@ -1143,14 +1258,7 @@ extern "C" int vlk_gemm_bf16_splitk(const void* A, const void* B, void* D, float
     int rc = gemm_impl(A, B, workspace, M, N, K, lda, ldb, N, transA, transB, nullptr, nullptr, 0, nullptr, nullptr, 0,
                        nullptr, VLK_ACT_NONE, 0, alpha, 1, split_k, slab, &used, stream);
     if (rc) return rc;
-    const long long work = slab / 8;
-    const int sms = device_sm_count();
-    long long blocks = (work + 255) / 256;
-    if (blocks > sms * 8LL) blocks = sms * 8LL;
-    splitk_reduce_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        workspace, used, slab, static_cast<bf16*>(D), M, N, ldd, accumulate);
-    VLK_CHECK_LAUNCH("vlk_gemm_bf16_splitk(reduce)");
-    return VLK_OK;
+    return splitk_reduce(workspace, used, slab, D, M, N, ldd, accumulate, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlk_gemm_bf16_lnfold(const void* X, const void* Wf, void* D, int M, int N, int K, int ldx, int ldw, int ldd,

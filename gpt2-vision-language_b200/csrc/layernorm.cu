@@ -280,24 +280,32 @@ extern "C" int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamm
     return VLK_OK;
 }
 
-// dst[i] = sum_c src[c][i]  (fp32 or bf16 destination): final reduction of replicated gradient accumulators
-__global__ void sum_copies_kernel(const float* __restrict__ src, int copies, long long n, float* __restrict__ dst_f32,
-                                  __nv_bfloat16* __restrict__ dst_bf16) {
+// dst[i] = (accumulate ? dst[i] : 0) + sum_c src[c][i]  (fp32 or bf16 destination): final reduction of replicated
+// gradient accumulators, optionally ADDED to an existing gradient (the flat bucket: gradient accumulation over
+// micro-batches without a separate add kernel) and optionally clearing the source so that a persistent accumulator
+// workspace is zero again for its next user.
+__global__ void sum_copies_kernel(float* __restrict__ src, int copies, long long n, float* __restrict__ dst_f32,
+                                  __nv_bfloat16* __restrict__ dst_bf16, int accumulate, int clear_src) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float s = 0.f;
-        for (int c = 0; c < copies; ++c) s += src[c * n + i];
-        if (dst_bf16) dst_bf16[i] = __float2bfloat16(s);
-        else dst_f32[i] = s;
+        for (int c = 0; c < copies; ++c) {
+            s += src[c * n + i];
+            if (clear_src) src[c * n + i] = 0.f;
+        }
+        if (dst_bf16) dst_bf16[i] = __float2bfloat16(accumulate ? s + __bfloat162float(dst_bf16[i]) : s);
+        else dst_f32[i] = accumulate ? s + dst_f32[i] : s;
     }
 }
 
-extern "C" int vlk_sum_copies(const float* src, int copies, long long n, void* dst, int dst_bf16, void* stream) {
+extern "C" int vlk_sum_copies(float* src, int copies, long long n, void* dst, int dst_bf16, int accumulate,
+                              int clear_src, void* stream) {
     VLK_REQUIRE(src && dst && copies > 0 && n > 0, VLK_ERR_INVALID_ARG, "vlk_sum_copies: args");
     long long blocks = (n + 255) / 256;
     if (blocks > 1024) blocks = 1024;
     sum_copies_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, copies, n, dst_bf16 ? nullptr : static_cast<float*>(dst), dst_bf16 ? static_cast<__nv_bfloat16*>(dst) : nullptr);
+        src, copies, n, dst_bf16 ? nullptr : static_cast<float*>(dst), dst_bf16 ? static_cast<__nv_bfloat16*>(dst) : nullptr,
+        accumulate, clear_src);
     VLK_CHECK_LAUNCH("vlk_sum_copies");
     return VLK_OK;
 }

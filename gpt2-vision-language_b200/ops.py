@@ -177,6 +177,51 @@ def colsum(x2d):
     return out
 
 
+def grad_slot(param):
+    """``param.grad`` when a libvlk kernel may ACCUMULATE this parameter's gradient into it in place: a dense bf16 CUDA
+    tensor already attached (gradient accumulation over micro-batches, train_gpt2.py:458-469; the views of
+    dp.FlatGradBucket), and autograd not recording (we are inside backward).  The Function then returns None for that
+    input, so autograd launches no ``grad += new`` kernel of its own.  Otherwise None: the gradient is returned."""
+    if param is None or not param.is_leaf:
+        return None
+    g = param.grad
+    if g is not None and g.dtype == BF16 and g.is_cuda and g.is_contiguous() and g.data_ptr() % 16 == 0 \
+            and not torch.is_grad_enabled():
+        return g
+    return None
+
+
+def sum_copies(src, copies, n, dst, accumulate=False, clear_src=False):
+    """dst[i] (= or +=) sum_c src[c*n + i]; dst fp32 or bf16 (vlk_sum_copies)."""
+    check(_lib.load().vlk_sum_copies(src.data_ptr(), int(copies), int(n), dst.data_ptr(), int(dst.dtype == BF16),
+                                     int(accumulate), int(clear_src), _stream()), "vlk_sum_copies")
+
+
+def bias_grad(dy2, bias):
+    """Bias gradient of nn.Linear = column sums of dy.  Accumulated straight into ``bias.grad`` when possible (returns
+    None), else returned as a bf16 tensor."""
+    s32 = colsum(dy2)
+    g = grad_slot(bias)
+    if g is not None:
+        sum_copies(s32, 1, s32.numel(), g, accumulate=True)
+        return None
+    out = torch.empty(s32.numel(), device=s32.device, dtype=BF16)
+    sum_copies(s32, 1, s32.numel(), out)
+    return out
+
+
+_WORKSPACES = {}
+
+
+def persistent_workspace(key, make):
+    """A process-lifetime device workspace (static address: CUDA-graph friendly) that its users leave in its initial
+    state.  Never created while a stream is capturing — callers fall back to a per-call temporary then."""
+    ws = _WORKSPACES.get(key)
+    if ws is None and not torch.cuda.is_current_stream_capturing():
+        ws = _WORKSPACES[key] = make()
+    return ws
+
+
 def transpose(x2d):
     _need_cuda(x2d)
     x2d = _bf16c(x2d)
@@ -262,27 +307,39 @@ def gemm_lnfold(x2d, wf, biasf, colsum, eps=1e-5, act=None, stats=None, sums=Non
 LN_GRAD_COPIES = 8
 
 
-def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False, grads_bf16=False):
+def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, accumulate=False, grads_bf16=False,
+                  bias=None):
     """-> dx, dgamma, dbeta.  The parameter gradients are accumulated by ~300 blocks into LN_GRAD_COPIES replicas
-    (fewer same-address atomics) that one small kernel sums — into fp32, or bf16 when ``grads_bf16``."""
+    (fewer same-address atomics) that one small kernel sums — into fp32, or bf16 when ``grads_bf16``.  When ``bias`` (the
+    LayerNorm's bias Parameter) is given and both ``weight.grad`` / ``bias.grad`` can take an in-place accumulation
+    (grad_slot), the sums are ADDED into them and None is returned for dgamma / dbeta."""
     rows, cols = x2d.shape
     lib = _lib.load()
     if dx is None:
         assert not accumulate
         dx = torch.empty_like(x2d)
     acc = None
+    persistent = False
     if param_grads:
-        acc = torch.zeros((2, LN_GRAD_COPIES, cols), device=x2d.device, dtype=torch.float32)
+        acc = persistent_workspace(("ln_acc", x2d.device.index, cols),
+                                   lambda: torch.zeros((2, LN_GRAD_COPIES, cols), device=x2d.device, dtype=torch.float32))
+        persistent = acc is not None
+        if acc is None:
+            acc = torch.zeros((2, LN_GRAD_COPIES, cols), device=x2d.device, dtype=torch.float32)
     check(lib.vlk_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                 dx.data_ptr(), _p(acc), acc[1].data_ptr() if acc is not None else 0, rows, cols,
                                 int(accumulate), LN_GRAD_COPIES, _stream()), "vlk_layernorm_bwd")
     dg = db = None
     if param_grads:
-        out = torch.empty((2, cols), device=x2d.device, dtype=BF16 if grads_bf16 else torch.float32)
-        for k in range(2):
-            check(lib.vlk_sum_copies(acc[k].data_ptr(), LN_GRAD_COPIES, cols, out[k].data_ptr(), int(grads_bf16), _stream()),
-                  "vlk_sum_copies")
-        dg, db = out[0], out[1]
+        gw, gb = grad_slot(weight), grad_slot(bias) if bias is not None else None
+        if gw is not None and gb is not None:
+            sum_copies(acc[0], LN_GRAD_COPIES, cols, gw, accumulate=True, clear_src=persistent)
+            sum_copies(acc[1], LN_GRAD_COPIES, cols, gb, accumulate=True, clear_src=persistent)
+        else:
+            out = torch.empty((2, cols), device=x2d.device, dtype=BF16 if grads_bf16 else torch.float32)
+            for k in range(2):
+                sum_copies(acc[k], LN_GRAD_COPIES, cols, out[k], clear_src=persistent)
+            dg, db = out[0], out[1]
     return dx, dg, db
 
 
@@ -464,6 +521,7 @@ class LinearFn(torch.autograd.Function):
         y = gemm(x2, weight, bias=bias, residual=res2)
         ctx.save_for_backward(x2, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_param = bias
         ctx.has_res = residual is not None
         ctx.x_shape = x.shape
         return y.view(*x.shape[:-1], weight.shape[0])
@@ -478,7 +536,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = wgrad(dy2, x2, weight)                                     # dy^T [N,M] x x [M,K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2).to(BF16)
+            db = bias_grad(dy2, ctx.bias_param)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres
@@ -509,6 +567,7 @@ class MLPFn(torch.autograd.Function):
         ctx.act = act
         ctx.x_shape = x.shape
         ctx.has_res = residual is not None
+        ctx.bias_params = (b_fc, b_proj)
         return y.view(x.shape)
 
     @staticmethod
@@ -522,11 +581,11 @@ class MLPFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dwfc = wgrad(du, x2, w_fc)
         if ctx.needs_input_grad[2]:
-            dbfc = colsum(du).to(BF16)
+            dbfc = bias_grad(du, ctx.bias_params[0])
         if ctx.needs_input_grad[3]:
             dwp = wgrad(dy2, h, w_proj)
         if ctx.needs_input_grad[4]:
-            dbp = colsum(dy2).to(BF16)
+            dbp = bias_grad(dy2, ctx.bias_params[1])
         if ctx.has_res and ctx.needs_input_grad[5]:
             dres = dy
         return dx, dwfc, dbfc, dwp, dbp, dres, None
@@ -545,6 +604,7 @@ class LayerNormFn(torch.autograd.Function):
         y, mean, rstd = layernorm_fwd(x2, weight, bias, eps, save_stats=need_bwd)
         if need_bwd:
             ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.bias_param = bias
         ctx.x_shape = x.shape
         return y.view(x.shape)
 
@@ -552,7 +612,8 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, weight, mean, rstd = ctx.saved_tensors
         pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = layernorm_bwd(_rows(dy).contiguous(), x2, weight, mean, rstd, param_grads=pg, grads_bf16=True)
+        dx, dg, db = layernorm_bwd(_rows(dy).contiguous(), x2, weight, mean, rstd, param_grads=pg, grads_bf16=True,
+                                   bias=ctx.bias_param if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else None)
         return (dx.view(ctx.x_shape) if ctx.needs_input_grad[0] else None,
                 dg if (pg and ctx.needs_input_grad[1]) else None,
                 db if (pg and ctx.needs_input_grad[2]) else None, None)
@@ -602,6 +663,7 @@ class ResidualLayerNormFn(torch.autograd.Function):
         y, mean, rstd = layernorm_fwd(x2, weight, bias, eps, save_stats=need_bwd)
         if need_bwd:
             ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.bias_param = bias
         ctx.x_shape = x.shape
         return x.view_as(x), y.view(x.shape)
 
@@ -613,13 +675,15 @@ class ResidualLayerNormFn(torch.autograd.Function):
         if g_y is None:
             return g_x, None, None, None
         dy2 = _rows(g_y).contiguous()
+        bias_p = ctx.bias_param if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2]) else None
         if _RESIDUAL_GRAD_INPLACE and g_x is not None and g_x.dtype == BF16 and g_x.is_contiguous():
             # opted in: the residual gradient has no reader left but this node (its producers ran earlier in backward)
             acc = g_x.view(-1, g_x.shape[-1])
-            _, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, dx=acc, accumulate=True, grads_bf16=True)
+            _, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, dx=acc, accumulate=True, grads_bf16=True,
+                                      bias=bias_p)
             dx = g_x
         else:
-            dxl, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, grads_bf16=True)
+            dxl, dg, db = layernorm_bwd(dy2, x2, weight, mean, rstd, param_grads=pg, grads_bf16=True, bias=bias_p)
             dx = dxl.view(ctx.x_shape) if g_x is None else add(g_x, dxl.view(ctx.x_shape)).view(ctx.x_shape)
         return (dx if ctx.needs_input_grad[0] else None,
                 dg if (pg and ctx.needs_input_grad[1]) else None,
@@ -773,6 +837,7 @@ class EmbedConcatFn(torch.autograd.Function):
         ctx.save_for_backward(ids)
         ctx.P = 0 if prefix is None else prefix.shape[1]
         ctx.wte_shape, ctx.wpe_shape = wte.shape, wpe.shape
+        ctx.params = (wte, wpe)
         return out
 
     @staticmethod
@@ -784,8 +849,27 @@ class EmbedConcatFn(torch.autograd.Function):
         if need_wte or need_wpe:
             B, T = ids.shape
             C = dout.shape[-1]
-            f_wte = torch.zeros(ctx.wte_shape, device=dout.device, dtype=torch.float32) if need_wte else None
-            f_wpe = torch.zeros(ctx.wpe_shape, device=dout.device, dtype=torch.float32) if need_wpe else None
+            wte, wpe = ctx.params
+            V = ctx.wte_shape[0]
+            g_wte = grad_slot(wte) if need_wte else None
+            g_wpe = grad_slot(wpe) if need_wpe else None
+            dev = dout.device
+            first = scratch = None
+            if (not need_wte or g_wte is not None) and (not need_wpe or g_wpe is not None):
+                if need_wte:
+                    first = persistent_workspace(("embed_first", dev.index, V), lambda: torch.full(
+                        (V,), 2 ** 31 - 1, device=dev, dtype=torch.int32))
+                    scratch = persistent_workspace(("embed_scratch", dev.index, B * T, C), lambda: torch.zeros(
+                        (B * T, C), device=dev, dtype=torch.float32))
+                if not need_wte or (first is not None and scratch is not None):
+                    # accumulate straight into the bf16 gradients (the flat bucket): no dense [V, C] temporaries
+                    check(_lib.load().vlk_embed_bwd_acc(ids.data_ptr(), dout.data_ptr(), _p(g_wte), _p(g_wpe[:T] if g_wpe is not None else None),
+                                                        _p(first), _p(scratch), B, T, ctx.P, C, V, _stream()),
+                          "vlk_embed_bwd_acc")
+                    dprefix = dout[:, :ctx.P] if (ctx.P and ctx.needs_input_grad[3]) else None
+                    return None, None, None, dprefix
+            f_wte = torch.zeros(ctx.wte_shape, device=dev, dtype=torch.float32) if need_wte else None
+            f_wpe = torch.zeros(ctx.wpe_shape, device=dev, dtype=torch.float32) if need_wpe else None
             check(_lib.load().vlk_embed_bwd(ids.data_ptr(), dout.data_ptr(), _p(f_wte), _p(f_wpe), B, T, ctx.P, C,
                                             _stream()), "vlk_embed_bwd")
             dwte = f_wte.to(BF16) if need_wte else None
@@ -799,69 +883,83 @@ def embed(ids, wte, wpe, prefix=None):
     return EmbedConcatFn.apply(ids, wte, wpe, prefix)
 
 
-class LMHeadCEFn(torch.autograd.Function):
-    """mean cross-entropy of (h @ W^T) against labels without ever holding the [rows, V] logits:
-    rows are processed in chunks small enough for the chunk's logits to stay L2-resident — lm_head GEMM,
-    in-place softmax-CE (loss + d logits), then the d h (and optional d W) GEMMs consume the chunk.
-    Replaces lm_head + F.cross_entropy at train_gpt2.py:121-124, gpt2_linear/model.py:172,204-210
-    (ignore_index=-100) and the masked mean of gpt2_cross-att/model.py:176-185 (row_weight = mask).
-    The gradient is produced in the forward pass and scaled by the incoming scalar in backward."""
+def _lmhead_ce_forward(h2, weight, labels, rw):
+    """vlk_lmhead_ce_fwd -> (stats [loss, 1/count], loss_row [rows], lse [rows]); no [rows, V] buffer exists."""
+    lib = _lib.load()
+    rows, C = h2.shape
+    V = weight.shape[0]
+    dev = h2.device
+    stats = torch.empty(2, device=dev, dtype=torch.float32)
+    loss_row = torch.empty(rows, device=dev, dtype=torch.float32)
+    lse = torch.empty(rows, device=dev, dtype=torch.float32)
+    nbytes = int(lib.vlk_lmhead_ce_workspace_bytes(rows, C, V, 0, 0, 0))
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    check(lib.vlk_lmhead_ce_fwd(h2.data_ptr(), weight.data_ptr(), labels.data_ptr(), _p(rw), stats.data_ptr(),
+                                loss_row.data_ptr(), lse.data_ptr(), rows, C, V, h2.stride(0), weight.stride(0),
+                                ws.data_ptr(), nbytes, _stream()), "vlk_lmhead_ce_fwd")
+    return stats, loss_row, lse
 
-    CHUNK_ROWS = 2048
-    CHUNK_ROWS_DW = 16384
+
+class LMHeadCEFn(torch.autograd.Function):
+    """Mean cross-entropy of (h @ W^T) against labels with the lm_head fused into the loss (vlk_lmhead_ce_fwd / _bwd):
+    the forward GEMM's epilogue keeps a running (max, sum exp) per row on chip and never stores logits; the backward
+    recomputes the logit tiles of L2-sized vocabulary chunks, turns them into softmax - onehot in the GEMM epilogue and
+    feeds the chunk straight into the d h (and, for a trainable head, d W) products.  No [rows, V] buffer in HBM in
+    either direction.  Replaces lm_head + F.cross_entropy at train_gpt2.py:121-124, gpt2_linear/model.py:172,204-210
+    (ignore_index=-100) and the masked mean of gpt2_cross-att/model.py:176-185 (row_weight = mask).  The incoming
+    scalar gradient (e.g. the 1/grad_accum of train_gpt2.py:464) is folded into the same epilogue."""
+
+    # Backward geometry (row_block, chunk_cols); 0 = the library's automatic choice: 4,096-row blocks x vocabulary chunks
+    # whose d-logits stay L2-resident.  Measured on B200 (scripts/lmhead_ce_ab.py, profiles/r02_lmhead_ce_ab.log):
+    #   frozen head, 1,984 rows:  automatic 473 us | one chunk 383 us | round-1 logits-in-HBM sequence 340 us
+    #   trainable head, 16,384 rows:  automatic 5.50 ms | one block x one chunk 4.37 ms | round-1 sequence 3.88 ms
+    # Recomputing the logit tiles costs one extra 2*rows*V*C product; with a trainable head (3 products become 4) that is
+    # more than the logits' HBM round trip ever cost, so pretraining takes the widest chunks (the d-logits of one
+    # micro-batch exist only inside the backward call, never across the trunk's backward); captioning, where the extra
+    # product is 0.9 % of the step, keeps everything L2-resident.
+    GEOMETRY = (0, 0)                      # frozen head (captioning)
+    GEOMETRY_DW = (1 << 20, 1 << 20)       # trainable head (pretraining): clamped to (rows, V) by the library
 
     @staticmethod
     def forward(ctx, h, weight, labels, row_weight):
         _param_ok(weight)
-        lib = _lib.load()
         h2 = _rows(h)
-        rows, C = h2.shape
-        V = weight.shape[0]
         labels = labels.reshape(-1).contiguous()
-        assert labels.dtype == torch.int64 and labels.numel() == rows
+        assert labels.dtype == torch.int64 and labels.numel() == h2.shape[0]
         rw = row_weight.reshape(-1).float().contiguous() if row_weight is not None else None
-        dev = h2.device
-        stats = torch.zeros(2, device=dev, dtype=torch.float32)           # [loss, 1/count]
-        loss_row = torch.empty(rows, device=dev, dtype=torch.float32)
-        check(lib.vlk_ce_count(labels.data_ptr(), _p(rw), stats.data_ptr(), rows, _stream()), "vlk_ce_count")
-        need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        write_grad = need_dh or need_dw
-        dh = torch.empty_like(h2) if need_dh else None
-        dw = None
-        # frozen lm_head (captioning): 2048-row chunks (206 MB of bf16 logits; the 1,984 text rows of a B=64 step are
-        # one chunk) — 512-row, L2-resident chunks were measured 1.4 % slower on the whole step: four small lm_head /
-        # d h products with K = 50,304 cost more than the logits' round trip through HBM; trainable lm_head
-        # (pretraining): one chunk per micro-batch (1.65 GB of bf16 logits at 16 x 1024 rows), so dW is a single
-        # K = 16,384 product instead of a chain of read-modify-write accumulations
-        chunk = LMHeadCEFn.CHUNK_ROWS if not need_dw else max(LMHeadCEFn.CHUNK_ROWS, LMHeadCEFn.CHUNK_ROWS_DW)
-        if os.environ.get("VLK_CE_CHUNK_ROWS"):
-            chunk = int(os.environ["VLK_CE_CHUNK_ROWS"])
-        logits = torch.empty((min(chunk, rows), V), device=dev, dtype=BF16)
-        for r0 in range(0, rows, chunk):
-            r1 = min(rows, r0 + chunk)
-            lg = logits[: r1 - r0]
-            gemm(h2[r0:r1], weight, out=lg)
-            check(lib.vlk_softmax_ce_rows(lg.data_ptr(), labels[r0:r1].data_ptr(), _p(rw[r0:r1]) if rw is not None else 0,
-                                          loss_row[r0:r1].data_ptr(), stats[1:].data_ptr(), r1 - r0, V, lg.stride(0),
-                                          int(write_grad), _stream()), "vlk_softmax_ce_rows")
-            if need_dh:
-                # d logits [r,V] x W [V,C]: a handful of output tiles with K = V = 50304 -> split the contraction
-                gemm(lg, weight, trans_b=True, out=dh[r0:r1], split_k=auto_split_k(r1 - r0, C, V))
-            if need_dw:
-                if dw is None:
-                    dw = gemm(lg, h2[r0:r1], trans_a=True, trans_b=True)      # d logits^T x h
-                else:
-                    gemm(lg, h2[r0:r1], trans_a=True, trans_b=True, out=dw, residual=dw)
-        check(lib.vlk_ce_finalize(loss_row.data_ptr(), _p(rw), stats.data_ptr(), rows, _stream()), "vlk_ce_finalize")
-        ctx.save_for_backward(dh, dw)
+        stats, _, lse = _lmhead_ce_forward(h2, weight, labels, rw)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(h2, weight, labels, rw, lse, stats)
         ctx.h_shape = h.shape
         return stats[0]
 
     @staticmethod
     def backward(ctx, dloss):
-        dh, dw = ctx.saved_tensors
-        g = dloss.to(BF16)
-        return (dh * g).view(ctx.h_shape) if dh is not None else None, (dw * g) if dw is not None else None, None, None
+        h2, weight, labels, rw, lse, stats = ctx.saved_tensors
+        lib = _lib.load()
+        rows, C = h2.shape
+        V = weight.shape[0]
+        need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dh = torch.empty_like(h2) if need_dh else None
+        dw = dw_ret = None
+        accumulate = 0
+        if need_dw:
+            g = weight.grad if weight.is_leaf else None
+            if g is not None and g.dtype == BF16 and g.is_cuda and g.is_contiguous() and not torch.is_grad_enabled():
+                dw, accumulate = g, 1          # gradient accumulation / flat bucket: summed inside the GEMM (see wgrad)
+            else:
+                dw = dw_ret = torch.empty_like(weight)
+        dl = dloss.detach().reshape(1)
+        if dl.dtype != torch.float32:
+            dl = dl.float()
+        rb, vc = LMHeadCEFn.GEOMETRY_DW if need_dw else LMHeadCEFn.GEOMETRY
+        nbytes = int(lib.vlk_lmhead_ce_workspace_bytes(rows, C, V, 1, rb, vc))
+        ws = torch.empty(nbytes, device=h2.device, dtype=torch.uint8)
+        check(lib.vlk_lmhead_ce_bwd(h2.data_ptr(), weight.data_ptr(), labels.data_ptr(), _p(rw), lse.data_ptr(),
+                                    stats[1:].data_ptr(), dl.data_ptr(), _p(dh), _p(dw), accumulate, rows, C, V,
+                                    h2.stride(0), weight.stride(0), C, weight.stride(0), rb, vc, ws.data_ptr(), nbytes,
+                                    _stream()), "vlk_lmhead_ce_bwd")
+        return dh.view(ctx.h_shape) if dh is not None else None, dw_ret, None, None
 
 
 def lmhead_ce(h, weight, labels, row_weight=None):
@@ -884,17 +982,11 @@ def cross_entropy_rows(logits2d, labels):
 
 
 @torch.no_grad()
-def lmhead_ce_rows(h, weight, labels, chunk=2048):
-    """Per-token losses of (h @ W^T) against labels without holding the [rows, V] logits (evaluation paths:
-    get_most_likely_row at train_gpt2.py:190-202, validation at gpt2_linear/train.py:218-252)."""
+def lmhead_ce_rows(h, weight, labels):
+    """Per-token losses of (h @ W^T) against labels without ever holding logits (evaluation paths:
+    get_most_likely_row at train_gpt2.py:190-202, validation at gpt2_linear/train.py:218-252): the forward half of
+    the fused lm_head + cross-entropy; ignored rows (-100) come back as 0."""
     _param_ok(weight)
     h2 = _rows(h)
-    rows = h2.shape[0]
-    labels = labels.reshape(-1).contiguous()
-    out = torch.empty(rows, device=h2.device, dtype=torch.float32)
-    logits = torch.empty((min(chunk, rows), weight.shape[0]), device=h2.device, dtype=BF16)
-    for r0 in range(0, rows, chunk):
-        r1 = min(rows, r0 + chunk)
-        lg = gemm(h2[r0:r1], weight, out=logits[: r1 - r0])
-        out[r0:r1] = cross_entropy_rows(lg, labels[r0:r1])
-    return out
+    _, loss_row, _ = _lmhead_ce_forward(h2, weight, labels.reshape(-1).contiguous(), None)
+    return loss_row

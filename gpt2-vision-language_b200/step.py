@@ -337,6 +337,7 @@ class PretrainStep:
         self.y = torch.zeros(micro_batch, seq, device=dev, dtype=torch.int64)
         self.loss = torch.zeros((), device=dev, dtype=torch.float32)
         self.norm = torch.zeros((), device=dev, dtype=torch.float32)
+        self.inv_accum = torch.full((), 1.0 / grad_accum, device=dev, dtype=torch.float32)
         self.zero1 = bool(zero1)
         if self.zero1:
             from .optim import Zero1AdamW
@@ -372,15 +373,15 @@ class PretrainStep:
     def _micro(self):
         _, loss = self.model(self.x, self.y)
         with ops.residual_grad_inplace():     # this class owns every gradient tensor of the step
-            (loss / self.grad_accum).backward()
-        self.loss += loss.detach() / self.grad_accum
+            loss.backward(self.inv_accum)     # loss / grad_accum (train_gpt2.py:464): the factor rides in the CE epilogue
+        self.loss.add_(loss.detach(), alpha=1.0 / self.grad_accum)
 
     def _last_phase1(self):
         loss, outs, cuts = _gpt_split_forward(self.model, self.x, self.y, self.split)
         self._cut = (outs, cuts)
         with ops.residual_grad_inplace():
-            (loss / self.grad_accum).backward()
-        self.loss += loss.detach() / self.grad_accum
+            loss.backward(self.inv_accum)
+        self.loss.add_(loss.detach(), alpha=1.0 / self.grad_accum)
 
     def _last_phase2(self):
         outs, cuts = self._cut

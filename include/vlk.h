@@ -130,8 +130,11 @@ int vlk_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
 int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int rows, int cols, int dx_accum, int grad_copies,
                       void* stream);
-/* dst[i] = sum_c src[c*n + i], written as fp32 (dst_bf16 == 0) or bf16. */
-int vlk_sum_copies(const float* src, int copies, long long n, void* dst, int dst_bf16, void* stream);
+/* dst[i] = (accumulate ? dst[i] : 0) + sum_c src[c*n + i], written as fp32 (dst_bf16 == 0) or bf16.  accumulate adds
+ * into an existing gradient (p.grad += g of autograd's AccumulateGrad, without the extra kernel); clear_src zeroes
+ * the replicas after reading them, so a persistent accumulator workspace is clean for its next user. */
+int vlk_sum_copies(float* src, int copies, long long n, void* dst, int dst_bf16, int accumulate, int clear_src,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Scaled-dot-product attention, head dim 64, fp32 softmax (F.scaled_dot_product_attention at
@@ -175,6 +178,13 @@ int vlk_embed_concat_fwd(const long long* ids, const void* wte, const void* wpe,
 /* Gradient of the above w.r.t. wte / wpe (fp32 accumulators [V,C], [block,C]); pretraining only. */
 int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte, float* dwpe, int B, int T, int prefix_len,
                   int C, void* stream);
+/* The same, ACCUMULATED into bf16 gradients (the flat bucket; wte.grad also receives the tied lm_head's dW) without
+ * dense [V, C] temporaries: rows of dout that share a token id are summed in fp32 in scratch[first position of that
+ * id] (fp32 [B*T, C]), then every first position adds its row into dwte[id] once.  first_pos (int32 [V]) and scratch
+ * are caller-owned workspaces that must hold INT32_MAX / zeros on entry and are restored on exit.
+ * dwpe[t] += sum_b dout[b, prefix_len + t].  Either gradient pointer may be NULL. */
+int vlk_embed_bwd_acc(const long long* ids, const void* dout, void* dwte, void* dwpe, int* first_pos, float* scratch,
+                      int B, int T, int prefix_len, int C, int vocab, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Row-wise softmax cross-entropy statistics over materialised bf16 logits [rows, V] (ld in elements):
@@ -189,6 +199,39 @@ int vlk_embed_bwd(const long long* ids, const void* dout, float* dwte, float* dw
  */
 int vlk_softmax_ce_rows(void* logits, const long long* labels, const float* row_weight, float* loss_row,
                         const float* inv_count, int rows, int V, int ld, int write_grad, void* stream);
+/* ---------------------------------------------------------------------------------------------------
+ * Fused lm_head + softmax cross-entropy WITHOUT a [rows, V] logits buffer, forward and backward.
+ * Replaces  logits = lm_head(x); F.cross_entropy(logits.view(-1, V), targets.view(-1))  and its autograd at
+ * train_gpt2.py:121-124, gpt2_linear/model.py:172,204-210 (ignore_index = -100) and the masked mean of
+ * gpt2_cross-att/model.py:176-185 (row_weight = mask).
+ *   h [rows, C] bf16 (row stride ldh), W [V, C] bf16 (the tied wte / lm_head weight, row stride ldw), labels int64
+ *   [rows] (-100 = ignored; any other value outside [0, V) makes that row's loss NaN), row_weight fp32 [rows] or NULL.
+ * fwd: one tcgen05 GEMM whose epilogue reduces every 128-column slice of the logit tile to a running (max, sum exp)
+ *   per row and picks the label logit — nothing of size rows x V is written —, then a merge kernel:
+ *     lse[r] = logsumexp(h[r] . W^T),  loss_row[r] = lse[r] - logit[r, label[r]]  (0 if ignored),
+ *     loss_out[0] = sum_r loss_row[r] * w[r] / max(count, 1),  loss_out[1] = 1 / max(count, 1),
+ *     count = number of non-ignored rows, or sum of row_weight when given.
+ * bwd: walks the vocabulary in chunks whose d-logits [rows, Vc] stay L2-resident; per chunk one GEMM recomputes the
+ *   logit tiles and writes  (exp(logit - lse[r]) - [v == label[r]]) * w[r] * inv_count * dloss  straight from its
+ *   epilogue, then  dh (+)= that . W[chunk]  (deterministic split-K)  and, when dW != NULL (trainable head:
+ *   pretraining),  dW[chunk] = that^T . h  — accumulated into dW when dw_accumulate != 0 (gradient accumulation,
+ *   train_gpt2.py:458-469).  inv_count = &loss_out[1] of the forward; dloss: device fp32 scalar (upstream gradient,
+ *   e.g. 1/grad_accum) or NULL for 1.  dh [rows, C] bf16 is overwritten (may be NULL when only dW is wanted).
+ * row_block / chunk_cols (backward geometry; 0 = automatic): rows per pass over the vocabulary and vocabulary columns
+ *   per chunk.  Automatic = 4,096 rows x the widest chunk whose d-logits fit a 48 MB L2 budget (never a full
+ *   [rows, V] buffer).  DESIGN.md gives the measured cost of that choice against wider chunks.
+ * workspace: vlk_lmhead_ce_workspace_bytes(rows, C, V, backward, row_block, chunk_cols) bytes, 16-byte aligned, caller-owned; contents are
+ *   scratch (nothing is carried from fwd to bwd except lse and loss_out[1]).
+ */
+long long vlk_lmhead_ce_workspace_bytes(int rows, int C, int V, int backward, int row_block, int chunk_cols);
+int vlk_lmhead_ce_fwd(const void* h, const void* W, const long long* labels, const float* row_weight, float* loss_out,
+                      float* loss_row, float* lse, int rows, int C, int V, int ldh, int ldw, void* workspace,
+                      long long workspace_bytes, void* stream);
+int vlk_lmhead_ce_bwd(const void* h, const void* W, const long long* labels, const float* row_weight, const float* lse,
+                      const float* inv_count, const float* dloss, void* dh, void* dW, int dw_accumulate, int rows, int C,
+                      int V, int ldh, int ldw, int lddh, int lddw, int row_block, int chunk_cols, void* workspace,
+                      long long workspace_bytes, void* stream);
+
 /* valid-count + mean: out[0] = sum(loss_row*w)/max(count,1), out[1] = 1/max(count,1), count = #labels != -100
  * (or sum of weights when row_weight != NULL). */
 int vlk_ce_count(const long long* labels, const float* row_weight, float* out, int rows, void* stream);

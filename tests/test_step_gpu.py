@@ -145,7 +145,7 @@ def test_split_backward_overlap_path_matches_monolithic(cuda, use_graph):
     assert (out[True][2] - out[False][2]).abs().max().item() < 2e-2
     if out[True][2].numel():
         lo, hi = st.upper
-        assert 0 < lo < hi == st.bucket.extra_off      # the upper half is a proper, non-empty tail of the bucket
+        assert 0 < lo < hi == st.bucket.params_end     # the upper half is a proper, non-empty tail of the bucket
     # ---- cross-attention captioning step
     g, gc = load("caption_xattn_tiny.pt"), load("clip_tiny.pt")
     B = 2
