@@ -62,7 +62,8 @@ SIGNATURES = {
                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p],
     "vlk_ce_count": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "vlk_ce_finalize": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
-    "vlk_grad_sumsq": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "vlk_grad_sumsq_workspace_floats": [c_int, c_ll],
+    "vlk_grad_sumsq": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],
     "vlk_adamw_step": [c_void_p, c_int, c_ll, c_int, c_void_p, c_float, c_void_p, c_float, c_float, c_float,
                        c_void_p, c_void_p],
     "vlk_im2col_patch14": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -74,7 +75,8 @@ SIGNATURES = {
     "vlk_gate_grad": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "vlk_argmax_rows": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"vlk_last_error_string": ctypes.c_char_p, "vlk_launch_count": c_ll, "vlk_lmhead_ce_workspace_bytes": c_ll}
+_RESTYPES = {"vlk_last_error_string": ctypes.c_char_p, "vlk_launch_count": c_ll, "vlk_lmhead_ce_workspace_bytes": c_ll,
+             "vlk_grad_sumsq_workspace_floats": c_ll}
 
 
 class TensorDesc(ctypes.Structure):

@@ -114,9 +114,12 @@ __device__ __forceinline__ float ld1<float>(const float* p, long long i) { retur
 __device__ __forceinline__ void st1(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
 __device__ __forceinline__ void st1(float* p, long long i, float v) { p[i] = v; }
 
+// Deterministic: every block writes its partial sum to partials[block]; grad_sumsq_finish_kernel adds them in a fixed
+// order.  (With fp32 atomics the ranks of a data-parallel job computed norms that differed in the last bit, their clip
+// factors differed, and the replicas' parameters drifted apart by bf16 ulps — tests/test_dp_gpu2.py.)
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_sumsq_kernel(const vlk_tensor_desc* __restrict__ table, float* __restrict__ norm_sq) {
+grad_sumsq_kernel(const vlk_tensor_desc* __restrict__ table, float* __restrict__ partials) {
     __shared__ float red[32];
     const vlk_tensor_desc d = table[blockIdx.y];
     const T* g = static_cast<const T*>(d.grad);
@@ -145,7 +148,22 @@ grad_sumsq_kernel(const vlk_tensor_desc* __restrict__ table, float* __restrict__
             }
     }
     acc = block_reduce(acc, red, false);
-    if (threadIdx.x == 0 && acc != 0.f) atomicAdd(norm_sq, acc);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// norm_sq[0] += sum of the n partials, in a fixed order: thread t adds partials t, t + 256, ... then a fixed tree.
+__global__ void __launch_bounds__(256) grad_sumsq_finish_kernel(const float* __restrict__ partials, int n,
+                                                                float* __restrict__ norm_sq) {
+    __shared__ float sh[256];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) a += partials[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) norm_sq[0] += sh[0];
 }
 
 template <typename T>
@@ -268,19 +286,28 @@ static int optimizer_grid_x(long long max_numel, int sms, int n_tensors) {
     return static_cast<int>(bx < 1 ? 1 : bx);
 }
 
+extern "C" long long vlk_grad_sumsq_workspace_floats(int n_tensors, long long max_numel) {
+    if (n_tensors <= 0 || max_numel <= 0) return -1;
+    int sms = device_sm_count();
+    if (sms <= 0) sms = 148;
+    return static_cast<long long>(optimizer_grid_x(max_numel, sms, n_tensors)) * n_tensors;
+}
+
 extern "C" int vlk_grad_sumsq(const vlk_tensor_desc* table, int n_tensors, long long max_numel, int dtype_fp32,
-                              float* norm_sq, void* stream) {
-    VLK_REQUIRE(table && norm_sq && n_tensors > 0 && n_tensors <= 65535 && max_numel > 0, VLK_ERR_INVALID_ARG,
+                              float* norm_sq, float* partials, void* stream) {
+    VLK_REQUIRE(table && norm_sq && partials && n_tensors > 0 && n_tensors <= 65535 && max_numel > 0, VLK_ERR_INVALID_ARG,
                 "vlk_grad_sumsq: n_tensors=%d", n_tensors);
     const int sms = device_sm_count();
     VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_grad_sumsq: no sm_100 device");
     const dim3 grid(optimizer_grid_x(max_numel, sms, n_tensors), n_tensors);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype_fp32)
-        grad_sumsq_kernel<float><<<grid, 256, 0, s>>>(table, norm_sq);
+        grad_sumsq_kernel<float><<<grid, 256, 0, s>>>(table, partials);
     else
-        grad_sumsq_kernel<bf16><<<grid, 256, 0, s>>>(table, norm_sq);
+        grad_sumsq_kernel<bf16><<<grid, 256, 0, s>>>(table, partials);
     VLK_CHECK_LAUNCH("vlk_grad_sumsq");
+    grad_sumsq_finish_kernel<<<1, 256, 0, s>>>(partials, static_cast<int>(grid.x * grid.y), norm_sq);
+    VLK_CHECK_LAUNCH("vlk_grad_sumsq(finish)");
     return VLK_OK;
 }
 

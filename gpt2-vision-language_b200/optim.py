@@ -80,9 +80,11 @@ class FusedAdamW(torch.optim.Optimizer):
                                         st["exp_avg_sq"].data_ptr(), p.numel(), float(g["weight_decay"]), 0)
                 host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
                 dev = host.to(sel[0].device, non_blocking=True)
-                tables.append(dict(group=g, params=sel, fp32=fp32, host=host, dev=dev, n=len(sel),
-                                   max_numel=max(p.numel() for p in sel),
-                                   lr=torch.zeros(1, dtype=torch.float32, device=sel[0].device)))
+                max_numel = max(p.numel() for p in sel)
+                nws = int(_lib.load().vlk_grad_sumsq_workspace_floats(len(sel), max_numel))
+                tables.append(dict(group=g, params=sel, fp32=fp32, host=host, dev=dev, n=len(sel), max_numel=max_numel,
+                                   partials=torch.zeros(nws, dtype=torch.float32, device=sel[0].device),
+                                   lr=torch.full((1,), float(g["lr"]), dtype=torch.float32, device=sel[0].device)))
         self._table_key, self._tables = key, tables
         return tables
 
@@ -103,7 +105,7 @@ class FusedAdamW(torch.optim.Optimizer):
         stream = torch.cuda.current_stream().cuda_stream
         for t in tables:
             check(lib.vlk_grad_sumsq(t["dev"].data_ptr(), t["n"], t["max_numel"], int(t["fp32"]),
-                                     self._norm_sq.data_ptr(), stream), "vlk_grad_sumsq")
+                                     self._norm_sq.data_ptr(), t["partials"].data_ptr(), stream), "vlk_grad_sumsq")
         self._pending_max_norm = float(max_norm)
         return self._norm_sq.sqrt().reshape(())
 
@@ -198,6 +200,8 @@ class Zero1AdamW:
         self.max_numel = max((n for _, n, _ in self.segments), default=1)
         self.fp32 = dt == torch.float32
         self.norm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.partials = torch.zeros(max(1, int(_lib.load().vlk_grad_sumsq_workspace_floats(max(self.n, 1), self.max_numel))),
+                                    device=dev, dtype=torch.float32)
         self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
         self.lr_t = torch.zeros(1, device=dev, dtype=torch.float32)
 
@@ -220,8 +224,8 @@ class Zero1AdamW:
         self.norm_sq.zero_()
         if self.n:
             check(_lib.load().vlk_grad_sumsq(self.table.data_ptr(), self.n, self.max_numel, int(self.fp32),
-                                             self.norm_sq.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                  "vlk_grad_sumsq")
+                                             self.norm_sq.data_ptr(), self.partials.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream), "vlk_grad_sumsq")
         return self.norm_sq
 
     def set_lr(self, lr):

@@ -19,9 +19,13 @@ from .dp import FlatGradBucket, FlatParamBucket, average_scalar_
 
 
 def _nccl_in_graph_default():
-    """Collectives are captured INSIDE the step's CUDA graph (one graph launch per step at any world size).
-    VLK_NCCL_OUTSIDE_GRAPH=1 restores the round-1 layout: separate graphs with the collectives launched between them."""
-    return not os.environ.get("VLK_NCCL_OUTSIDE_GRAPH")
+    """Where the gradient all-reduce lives when the step is replayed from CUDA graphs.  Default: BETWEEN the graphs
+    (forward+backward | all-reduce | clip+AdamW), launched eagerly on the same stream.  VLK_NCCL_IN_GRAPH=1 (or
+    nccl_in_graph=True) captures the collectives inside ONE graph per step instead; both layouts are exercised on two
+    GPUs by tests/test_dp_gpu2.py.  Measured at 2 GPUs, same box (profiles/r02/bench_n2_*.json): caption-linear 15.14 ms
+    between graphs vs 15.25 ms in-graph, Q-Former 16.57 vs 16.71, x-attn 16.94 vs 17.06, pretraining 326.4 vs 326.1 —
+    capturing NCCL buys nothing here (the collective is one launch either way), so the simpler layout stays."""
+    return bool(os.environ.get("VLK_NCCL_IN_GRAPH"))
 
 
 def _capture(graph, fn, pool=None, with_collectives=False):

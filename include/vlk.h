@@ -240,7 +240,7 @@ int vlk_ce_finalize(const float* loss_row, const float* row_weight, float* out, 
 /* ---------------------------------------------------------------------------------------------------
  * Fused global-norm clip + AdamW over a table of tensors (clip_grad_norm_ at train_gpt2.py:472 and
  * torch.optim.AdamW(betas, eps, fused) at train_gpt2.py:143).
- *   pass 1  vlk_grad_sumsq: norm_sq[0] += sum over all grads of g^2  (fp32, caller zeroes)
+ *   pass 1  vlk_grad_sumsq: norm_sq[0] += sum over all grads of g^2  (fp32, caller zeroes; deterministic)
  *   pass 2  vlk_adamw_step: clip = min(1, max_norm/(sqrt(norm_sq)+1e-6)); g *= clip; standard decoupled AdamW.
  * The table is a device array of vlk_tensor_desc; params/grads/moments are bf16 or fp32 per `dtype_fp32`.
  * `grads` are left scaled?  No: gradients are read-only here; the clip factor is applied in registers.
@@ -255,8 +255,12 @@ typedef struct vlk_tensor_desc {
     int pad_;
 } vlk_tensor_desc;
 
+/* partials: caller-owned scratch of vlk_grad_sumsq_workspace_floats(n_tensors, max_numel) floats — block partial sums,
+ * added in a fixed order so that every rank of a data-parallel job computes bit-identical norms from identical
+ * (all-reduced) gradients. */
+long long vlk_grad_sumsq_workspace_floats(int n_tensors, long long max_numel);
 int vlk_grad_sumsq(const vlk_tensor_desc* table, int n_tensors, long long max_numel, int dtype_fp32,
-                   float* norm_sq, void* stream);
+                   float* norm_sq, float* partials, void* stream);
 int vlk_adamw_step(const vlk_tensor_desc* table, int n_tensors, long long max_numel, int dtype_fp32,
                    const float* norm_sq, float max_norm, const float* lr, float beta1, float beta2, float eps,
                    const float* step, void* stream);
