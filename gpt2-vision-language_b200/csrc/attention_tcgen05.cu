@@ -12,6 +12,7 @@
 // The whole key range fits one tile, so there is no online-softmax rescaling here; longer sequences use the
 // streaming kernel in attention_flash.cu.  The entry point `attn_mid_fwd` is called by attention_api.cu.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -480,7 +481,11 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
                     ptx::mbar_arrive(&q_empty[g]);   // this slot's Q tile is no longer needed (S done, dots done)
                 }
                 dbg4(p.debug, leader, g, cnt, 5);
-                if (p.tail_rows > 0 && qb == nqb - 1) {
+                // The leftover rows go to group (unit parity), i.e. ALTERNATE between the groups from unit to unit: the phase
+                // stamps of the bring-up build (profiles/r02/attn_clip_phase_stamps.md) show them costing 4.5-5 us per
+                // unit on the CUDA cores; always on the last tile's group they made that group's chain 10 us against
+                // 5 us for the other one, and the MMA issue order couples the two (75.5 -> 65.0 us per CLIP layer).
+                if (p.tail_rows > 0 && (it & 1) == g && qb + 2 >= nqb) {
                     // leftover query rows of this (batch, head), while the tensor core works on this tile's P.V
                     ptx::mbar_wait(&vfull[s], kvpar);
                     float* scr = reinterpret_cast<float*>(smem + k4OffTail) + g * k4TailFloats;
@@ -621,7 +626,11 @@ int attn_mid_fwd(const void* q, const void* k, const void* v, void* o, float* ls
     p4.nqb = (tc_rows + 127) / 128;
     p4.scale = scale;
     p4.scale_log2e = scale * 1.4426950408889634f;
+#ifdef VLK_BRINGUP
+    p4.debug = getenv("VLK_ATTN_DEBUG") != nullptr;
+#else
     p4.debug = 0;
+#endif
     p4.q = static_cast<const bf16*>(q);
     p4.q_bs = q_bs;
     p4.q_rs = q_rs;
