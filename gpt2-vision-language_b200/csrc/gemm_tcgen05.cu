@@ -27,7 +27,6 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
-constexpr int kEpiStageBytes = 8192;  // per epilogue warp: input tile + output tile, each 32 rows x 128 B
 
 struct EpiParams {
     const bf16* bias;
@@ -64,8 +63,10 @@ struct EpiParams {
     const float* ce_lse;
     const float* ce_row_scale;
     int ce_col0;
+    int wide_io;  // every bf16 [M,N] operand of the epilogue (D, residual, aux) has 32-byte aligned rows: 256-bit accesses
 #ifdef VLK_BRINGUP
     int debug;  // bring-up builds only (env VLK_GEMM_DEBUG): 1 = skip epilogue work, 2 = skip TMA loads and full-barrier waits
+    unsigned long long* dbg_out;  // bring-up builds only: per-CTA wait-time breakdown (8 counters), see VLK_DBG_CLOCK
 #endif
 };
 
@@ -73,9 +74,21 @@ struct EpiParams {
 #ifdef VLK_BRINGUP
 #define VLK_DBG_SKIP_EPILOGUE(ep) (((ep).debug & 1) != 0)
 #define VLK_DBG_SKIP_LOADS(ep) (((ep).debug & 2) != 0)
+#define VLK_DBG_LDTM_ONLY(ep) (((ep).debug & 4) != 0)      // epilogue reads the accumulator and drops it
+#define VLK_DBG_NO_GLOBAL_IO(ep) (((ep).debug & 8) != 0)   // epilogue computes but never stores
+// cycle counters of the role threads: T(acc) { statement; } adds the cycles the statement took to acc
+#define VLK_DBG_CLOCK_DECL(name) long long name = 0
+#define VLK_DBG_TIMED(acc, stmt) do { const long long t0__ = clock64(); stmt; acc += clock64() - t0__; } while (0)
+#define VLK_DBG_PUT(ep, slot, val) do { if ((ep).dbg_out) (ep).dbg_out[blockIdx.x * 8 + (slot)] = static_cast<unsigned long long>(val); } while (0)
+unsigned long long* g_gemm_dbg_out = nullptr;
 #else
 #define VLK_DBG_SKIP_EPILOGUE(ep) false
 #define VLK_DBG_SKIP_LOADS(ep) false
+#define VLK_DBG_LDTM_ONLY(ep) false
+#define VLK_DBG_NO_GLOBAL_IO(ep) false
+#define VLK_DBG_CLOCK_DECL(name)
+#define VLK_DBG_TIMED(acc, stmt) do { stmt; } while (0)
+#define VLK_DBG_PUT(ep, slot, val) do { } while (0)
 #endif
 
 template <int BLOCK_N, int kStages>
@@ -83,8 +96,7 @@ struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagingOffset = kStages * kStageBytes;  // kNumEpiWarps x 4 KB epilogue transposers
-    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * kEpiStageBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
     static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024B alignment
@@ -254,49 +266,7 @@ __device__ __forceinline__ void epilogue_store32(const EpiParams& ep, const uint
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Coalescing epilogue.  After tcgen05.ld a thread holds 32 consecutive columns of ONE row, so direct global
-// accesses touch 32 different rows per instruction (32 LSU wavefronts for 512 bytes) and the epilogue becomes
-// LSU-bound — it then throttles the tensor pipe through the TMEM hand-off.  Each epilogue warp therefore owns a
-// 4 KB staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled by row so both access patterns are
-// bank-conflict-free): results are written row-per-thread, then stored with 8 lanes per row, i.e. four full
-// 128-byte lines per instruction.  Residual / activation-gradient inputs take the same route in reverse.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t* stage_at(uint8_t* stage, int row, int chunk) {
-    return stage + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-
-// Coalesced fetch of a 32-row x 64-column bf16 tile into registers (lane = 16-byte chunk lane&7 of rows lane>>3 + 4i),
-// issued well before the values are needed; stage_put() later drops them into the swizzled staging tile.
-__device__ __forceinline__ void tile_prefetch(uint4 (&pre)[8], const bf16* src, int ld, int row0, int col0, int M,
-                                              int ncols, int lane) {
-    const int k = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3);
-        pre[i] = make_uint4(0, 0, 0, 0);
-        if (row0 + r < M && k * 8 < ncols) pre[i] = ldg16(src + static_cast<size_t>(row0 + r) * ld + col0 + k * 8);
-    }
-}
-__device__ __forceinline__ void stage_put(uint8_t* stage, const uint4 (&pre)[8], int lane) {
-    const int k = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stage_at(stage, i * 4 + (lane >> 3), k)) = pre[i];
-}
-
-__device__ __forceinline__ void stage_store_tile(const uint8_t* stage, bf16* dst, int ld, int row0, int col0, int M,
-                                                 int ncols, int lane) {
-    const int k = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3);
-        if (row0 + r < M && k * 8 < ncols)
-            stg16(dst + static_cast<size_t>(row0 + r) * ld + col0 + k * 8,
-                  *reinterpret_cast<const uint4*>(stage_at(const_cast<uint8_t*>(stage), r, k)));
-    }
-}
-
-// Which [M,N] input (if any) travels through the staging tile: the residual, else the activation-gradient input.
+// Which [M,N] input (if any) is read one chunk ahead of its use: the residual, else the activation-gradient input.
 __device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int& ld) {
     if (ep.residual != nullptr) {
         ld = ep.ldr;
@@ -306,46 +276,77 @@ __device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int
     return ep.dact ? ep.aux_in : nullptr;
 }
 
-// Called BEFORE waiting for the accumulator: the epilogue warp is idle while the MMAs of its tile run, so ALL of its
-// staged input (the residual, or the activation-gradient input; up to two 32 x 64 chunks) is fetched under them and
-// parked in the warp's two staging tiles.  (Fetching chunk c+1 only while chunk c was being consumed left a DRAM
-// round trip exposed per chunk: +33 % kernel time on the K = 768 / 1024 residual GEMMs, profiles/r01_gemm_short_probe.log.)
-__device__ __forceinline__ void epilogue_prefetch(const EpiParams& ep, uint8_t* stage, int row0, int n0,
-                                                  int ncols_warp, int M, int N, int lane) {
-    if (ep.out_fp32 || ncols_warp < 64 || VLK_DBG_SKIP_EPILOGUE(ep) || n0 >= N) return;
+// ------------------------------------------------------------------------------------------------
+// Direct epilogue: registers <-> global memory, no shared-memory staging.  After tcgen05.ld a thread holds 32
+// consecutive columns of ONE row = 64 bytes of bf16 = two full 32-byte sectors, written with two 256-bit stores
+// (STG.E.ENL2.256).  The [M,N] inputs (residual, activation-gradient input) are read the same way, one 32-column
+// chunk ahead of its use (the first chunk before the accumulator wait).  Compared with the staged variant above this
+// takes the epilogue's 2 x 64 KB (4 x with a staged input) per tile out of the shared-memory pipe that the tensor
+// core's operand reads and the TMA writes already load to the limit, frees 64 KB for two more pipeline stages, and
+// produces the pre-activation copy (aux_out) in the same pass.
+// ------------------------------------------------------------------------------------------------
+struct EpiPre {
+    uint32_t r[16];  // 32 bf16 of this thread's row
+};
+
+__device__ __forceinline__ void ldg_row32(uint32_t (&r)[16], const bf16* p, int ncols, bool wide) {
+    if (wide && ncols == 32) {
+        ptx::ldg_v8(r, p);
+        ptx::ldg_v8(r + 8, p + 16);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (q * 8 < ncols) u = ldg16(p + q * 8);
+            r[q * 4] = u.x, r[q * 4 + 1] = u.y, r[q * 4 + 2] = u.z, r[q * 4 + 3] = u.w;
+        }
+    }
+}
+__device__ __forceinline__ void stg_row32(bf16* p, const uint32_t (&r)[16], int ncols, bool wide) {
+    if (wide && ncols == 32) {
+        ptx::stg_v8(p, r);
+        ptx::stg_v8(p + 16, r + 8);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q * 8 < ncols) stg16(p + q * 8, make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]));
+    }
+}
+__device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bf162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        r[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const bf162*>(&u)); }
+
+// The first chunk of the staged input, fetched BEFORE the accumulator wait (the warp is idle while its tile's MMAs run).
+__device__ __forceinline__ void epilogue_prefetch_direct(const EpiParams& ep, EpiPre& pre, int row0, int n0, int M, int N,
+                                                         int lane) {
+    if (ep.out_fp32 || ep.ce_mode == 1 || VLK_DBG_SKIP_EPILOGUE(ep) || n0 >= N) return;
     int ld;
     const bf16* in = epi_staged_input(ep, ld);
-    if (in == nullptr) return;
-    uint4 pre0[8], pre1[8];
-    const bool two = ncols_warp > 64 && n0 + 64 < N;
-    tile_prefetch(pre0, in, ld, row0, n0, M, min(64, N - n0), lane);
-    if (two) tile_prefetch(pre1, in, ld, row0, n0 + 64, M, min(64, N - n0 - 64), lane);
-    stage_put(stage, pre0, lane);
-    if (two) stage_put(stage + 4096, pre1, lane);
-    __syncwarp();
+    const int row = row0 + lane;
+    if (in == nullptr || row >= M) return;
+    ldg_row32(pre.r, in + static_cast<size_t>(row) * ld + n0, min(32, N - n0), ep.wide_io != 0);
 }
 
-// One warp, its 32 accumulator rows (TMEM lanes), `ncols_warp` (<= 128) columns starting at global column n0.
-// stage = two 4 KB tiles, one per 64-column chunk; a chunk's tile first holds the staged input, is then updated IN
-// PLACE with the results (row-per-thread: a lane reads and writes only its own row's 16-byte slots) and finally
-// stored with 8 lanes per row.
-//
-// Specialised on the epilogue operands (template value -1 = decided at run time): with every option resolved at run
-// time inside the unrolled loops the kernel was 12.6 k SASS instructions (erff alone is inlined 64 times) and the
-// epilogue warps lost ~15 % of their issue slots to instruction-cache misses (`no_inst`,
-// profiles/r01_ncu_gemm_residual_source_summary.txt).  The dispatcher below picks one compact body per launch.
 template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF, int STATS = 0, int CE = 0>
-__device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
-                                                int ncols_warp, int M, int N, int lane, size_t d_off) {
+__device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& pre, uint32_t taddr, int row0, int n0,
+                                                  int ncols_warp, int M, int N, int lane) {
     const int row = row0 + lane;
+    const bool row_ok = row < M;
     const int act = ACT < 0 ? ep.act : ACT;
     const bool dact = DACT < 0 ? (ep.dact != 0) : (DACT != 0);
     const bool has_res = RES < 0 ? (ep.residual != nullptr) : (RES != 0);
     const bool has_scale = SCALE < 0 ? (ep.scale != nullptr) : (SCALE != 0);
     const bool has_aux_out = AUX < 0 ? (ep.aux_out != nullptr) : (AUX != 0);
     const bool ln_fold = LNF < 0 ? (ep.ln_colsum != nullptr) : (LNF != 0);
+    const bool stats = STATS < 0 ? (ep.stats_out != nullptr) : (STATS != 0);
+    const bool wide = ep.wide_io != 0;
     float ln_mu = 0.f, ln_rs = 1.f;
-    if (ln_fold && row < M) {
+    if (ln_fold && row_ok) {
         if (ep.ln_sums != nullptr) {
             const float2 s12 = __ldg(reinterpret_cast<const float2*>(ep.ln_sums) + row);
             ln_mu = s12.x * ep.ln_inv_k;
@@ -355,140 +356,127 @@ __device__ __forceinline__ void epilogue_warp_t(const EpiParams& ep, uint8_t* st
             ln_rs = __ldg(ep.ln_rstd + row);
         }
     }
-    const bool stats = STATS < 0 ? (ep.stats_out != nullptr) : (STATS != 0);
     float st1 = 0.f, st2 = 0.f;
-    const bool aux_direct = dact && has_res;  // both present: aux_in falls back to direct loads
+    const bool aux_direct = dact && has_res;  // both present: the residual is the prefetched stream, aux_in is read in place
     const float scale = has_scale ? __ldg(ep.scale) : 1.0f;
+    int ld_in = 0;
+    const bf16* in = (has_res || dact) ? epi_staged_input(ep, ld_in) : nullptr;
+    const size_t in_row = static_cast<size_t>(row) * ld_in;
 #pragma unroll 1
-    for (int c = 0; c < ncols_warp; c += 64) {
+    for (int c = 0; c < ncols_warp; c += 32) {
         const int col0 = n0 + c;
         if (col0 >= N) break;  // warp-uniform
-        const int ncols = min(64, N - col0);
-        uint8_t* buf = stage + (c >> 6) * 4096;
-        // sweep 1: the output tile (consumes the staged input); sweep 0 (only with aux_out): the pre-activation tile
-#pragma unroll 1
-        for (int sweep = 1; sweep >= (has_aux_out ? 0 : 1); --sweep) {
+        const int ncols = min(32, N - col0);
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(taddr + c, r);
+        EpiPre nxt;
+        const bool has_next = in != nullptr && c + 32 < ncols_warp && col0 + 32 < N;
+        if (has_next && row_ok) ldg_row32(nxt.r, in + in_row + col0 + 32, min(32, N - col0 - 32), wide);
+        ptx::tmem_ld_wait();
+        if (VLK_DBG_LDTM_ONLY(ep)) continue;
+        float v[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h * 32 >= ncols) break;  // warp-uniform
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c + h * 32, r);
-                ptx::tmem_ld_wait();
-                float v[32];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+        if (CE != 0) {
+            if (row_ok) ce_grad32(ep, v, row, col0);
+        }
+        if (ln_fold) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
-                const int hc0 = col0 + h * 32;
-                const int hcols = min(32, N - hc0);
-                if (CE != 0) {
-                    if (row < M) ce_grad32(ep, v, row, hc0);
-                }
-                if (ln_fold) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (q * 4 < hcols) {
-                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + hc0) + q);
-                            v[q * 4 + 0] = ln_rs * (v[q * 4 + 0] - ln_mu * c4.x);
-                            v[q * 4 + 1] = ln_rs * (v[q * 4 + 1] - ln_mu * c4.y);
-                            v[q * 4 + 2] = ln_rs * (v[q * 4 + 2] - ln_mu * c4.z);
-                            v[q * 4 + 3] = ln_rs * (v[q * 4 + 3] - ln_mu * c4.w);
-                        }
-                    }
-                }
-                if (ep.bias != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q * 8 < hcols) {
-                            float b[8];
-                            unpack8(ldg16(ep.bias + hc0 + q * 8), b);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[q * 8 + i] += b[i];
-                        }
-                    }
-                }
-                if (sweep == 1) {
-                    if (dact) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (q * 8 < hcols) {
-                                float u[8];
-                                if (aux_direct) {
-                                    if (row < M)
-                                        unpack8(ldg16(ep.aux_in + static_cast<size_t>(row) * ep.ld_aux + hc0 + q * 8), u);
-                                    else {
-#pragma unroll
-                                        for (int i = 0; i < 8; ++i) u[i] = 0.f;
-                                    }
-                                } else {
-                                    unpack8(*reinterpret_cast<const uint4*>(stage_at(buf, lane, h * 4 + q)), u);
-                                }
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[q * 8 + i] *= act_grad(act, u[i]);
-                            }
-                        }
-                    } else if (act != VLK_ACT_NONE) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = act_apply(act, v[i]);
-                    }
-                    if (has_scale) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] *= scale;
-                    }
-                    if (has_res) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (q * 8 < hcols) {
-                                float u[8];
-                                unpack8(*reinterpret_cast<const uint4*>(stage_at(buf, lane, h * 4 + q)), u);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[q * 8 + i] += u[i];
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float t[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) t[i] = v[q * 8 + i];
-                    const uint4 pk = pack8(t);
-                    if (stats && sweep == 1 && q * 8 < hcols) {   // statistics of what the consumer will actually read
-                        float rr[8];
-                        unpack8(pk, rr);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            st1 += rr[i];
-                            st2 = fmaf(rr[i], rr[i], st2);
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(stage_at(buf, lane, h * 4 + q)) = pk;
+            for (int q = 0; q < 8; ++q) {
+                if (q * 4 < ncols) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0) + q);
+                    v[q * 4 + 0] = ln_rs * (v[q * 4 + 0] - ln_mu * c4.x);
+                    v[q * 4 + 1] = ln_rs * (v[q * 4 + 1] - ln_mu * c4.y);
+                    v[q * 4 + 2] = ln_rs * (v[q * 4 + 2] - ln_mu * c4.z);
+                    v[q * 4 + 3] = ln_rs * (v[q * 4 + 3] - ln_mu * c4.w);
                 }
             }
-            __syncwarp();
-            stage_store_tile(buf, sweep == 0 ? ep.aux_out : reinterpret_cast<bf16*>(ep.D),
-                             sweep == 0 ? ep.ld_aux : ep.ldd, row0, col0, M, ncols, lane);
-            __syncwarp();
+        }
+        if (ep.bias != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q * 8 < ncols) {
+                    float b[8];
+                    unpack8(ldg16(ep.bias + col0 + q * 8), b);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[q * 8 + i] += b[i];
+                }
+            }
+        }
+        uint32_t pk[16];
+        if (has_aux_out) {  // the pre-activation copy the backward pass needs, from the same registers
+            pack32(v, pk);
+            if (row_ok) stg_row32(ep.aux_out + static_cast<size_t>(row) * ep.ld_aux + col0, pk, ncols, wide);
+        }
+        if (dact) {
+            if (aux_direct) {
+                uint32_t u[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) u[i] = 0;
+                if (row_ok) ldg_row32(u, ep.aux_in + static_cast<size_t>(row) * ep.ld_aux + col0, ncols, wide);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 t = unpack2(u[i]);
+                    v[2 * i] *= act_grad(act, t.x);
+                    v[2 * i + 1] *= act_grad(act, t.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 t = unpack2(pre.r[i]);
+                    v[2 * i] *= act_grad(act, t.x);
+                    v[2 * i + 1] *= act_grad(act, t.y);
+                }
+            }
+        } else if (act != VLK_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = act_apply(act, v[i]);
+        }
+        if (has_scale) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= scale;
+        }
+        if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float2 t = unpack2(pre.r[i]);
+                v[2 * i] += t.x;
+                v[2 * i + 1] += t.y;
+            }
+        }
+        pack32(v, pk);
+        if (stats) {  // statistics of what the consumer will actually read (the rounded values)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (2 * i < ncols) {
+                    const float2 t = unpack2(pk[i]);
+                    st1 += t.x + t.y;
+                    st2 = fmaf(t.x, t.x, fmaf(t.y, t.y, st2));
+                }
+            }
+        }
+        if (row_ok && !(VLK_DBG_NO_GLOBAL_IO(ep) && pk[3] != 0x12345678u))
+            stg_row32(reinterpret_cast<bf16*>(ep.D) + static_cast<size_t>(row) * ep.ldd + col0, pk, ncols, wide);
+        if (has_next) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pre.r[i] = nxt.r[i];
         }
     }
-    if (stats && row < M) {
+    if (stats && row_ok) {
         atomicAdd(ep.stats_out + 2 * static_cast<size_t>(row), st1);
         atomicAdd(ep.stats_out + 2 * static_cast<size_t>(row) + 1, st2);
     }
 }
 
-
-// SPECIALISE: the 256-wide kernels (every large product of the path) get the compact per-operand-set bodies; the
-// narrow-tile kernels (small problems: decode rows, tiny test shapes) keep one generic body — 20 fewer kernel
-// instantiations to carry six bodies each (build time, library size).
 template <bool SPECIALISE>
-__device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stage, uint32_t taddr, int row0, int n0,
-                                              int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
+__device__ __forceinline__ void epilogue_warp_direct(const EpiParams& ep, EpiPre& pre, uint32_t taddr, int row0, int n0,
+                                                     int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
     if (VLK_DBG_SKIP_EPILOGUE(ep)) return;
     if (ep.ce_mode == 1) {
         ce_stats_warp(ep, taddr, row0, n0, ncols_warp, M, N, lane);
         return;
     }
-    if (ep.out_fp32 || ncols_warp < 64) {
-        // fp32 output (split-K slabs) and 32-column slices keep the direct row-per-thread path
+    if (ep.out_fp32) {  // fp32 output (split-K slabs): row-per-thread float4 stores
         const int row = row0 + lane;
 #pragma unroll 1
         for (int c = 0; c < ncols_warp; c += 32) {
@@ -502,20 +490,19 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
         return;
     }
 #define VLK_EPI(ACT, DACT, RES, SCALE, AUX) \
-    epilogue_warp_t<ACT, DACT, RES, SCALE, AUX, 0>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
-#define VLK_EPI_LN(ACT) \
-    epilogue_warp_t<ACT, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off)
+    epilogue_direct_t<ACT, DACT, RES, SCALE, AUX, 0>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane)
+#define VLK_EPI_LN(ACT) epilogue_direct_t<ACT, 0, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
-    if (ep.ce_mode == 2) {   // d logits of a vocabulary chunk: plain staged store of the transformed tile
-        epilogue_warp_t<0, 0, 0, 0, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+    if (ep.ce_mode == 2) {   // d logits of a vocabulary chunk
+        epilogue_direct_t<0, 0, 0, 0, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
         return;
     }
     if constexpr (!SPECIALISE) {
-        epilogue_warp_t<-1, -1, -1, -1, -1, -1, -1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+        epilogue_direct_t<-1, -1, -1, -1, -1, -1, -1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
         return;
     }
     if (ep.stats_out != nullptr) {  // residual GEMM that also produces the row statistics of its output
-        epilogue_warp_t<0, 0, -1, 0, 0, 0, 1>(ep, stage, taddr, row0, n0, ncols_warp, M, N, lane, d_off);
+        epilogue_direct_t<0, 0, -1, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
     } else if (ep.ln_colsum != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
         if (ep.act == VLK_ACT_QUICK_GELU) VLK_EPI_LN(VLK_ACT_QUICK_GELU);
         else if (ep.act == VLK_ACT_GELU_TANH) VLK_EPI_LN(VLK_ACT_GELU_TANH);
@@ -535,6 +522,7 @@ __device__ __forceinline__ void epilogue_warp(const EpiParams& ep, uint8_t* stag
 #undef VLK_EPI
 #undef VLK_EPI_LN
 }
+
 
 // Rasterisation of work units onto the output grid.  A wave of ~148 concurrently running CTAs should touch as few
 // distinct A and B tiles as possible, because what bounds this kernel is unique bytes leaving the L2 (operands
@@ -569,7 +557,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-    const int warp_idx = threadIdx.x >> 5;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
 
     // Work unit = CLUSTER vertically adjacent tiles; cluster c walks units c, c + num_clusters, ...  The last unit
@@ -612,7 +600,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     if (warp_idx == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0 && !VLK_DBG_SKIP_LOADS(ep)) {
+        // The warp walks the loop converged; one elected lane issues (see the MMA issuer below).
+        const bool issuer = ptx::elect_one();
+        if (!VLK_DBG_SKIP_LOADS(ep)) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
@@ -624,6 +614,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
+                    if (issuer) {
                     ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
                     if constexpr (!A_MN) {
                         // box = 64 (k) x 128 (m)
@@ -656,6 +647,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                                        kb * BLOCK_K, kMcastMask);
                         }
                     }
+                    }
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -665,8 +658,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer =======================================
-        if (lane == 0) {
+        // The whole warp walks the loop CONVERGED (every lane polls the barriers) and one elected lane issues, so every
+        // operand of tcgen05.mma is warp-uniform and lives in uniform registers; the shared-memory descriptors are a base
+        // plus a stage / k-step offset in the address field.  Issued from inside `if (lane == 0)` the same loop compiled
+        // to ~25 instructions per MMA (an ELECT / R2UR.BROADCAST loop per operand set): ~600 clk per 64-deep k-block
+        // against the 512 clk the tensor core needs for it — the ISSUE loop, not the tensor pipe, bounded the kernel
+        // (profiles/r02/gemm_issue_loop.md).
+        {
+            const bool issuer = ptx::elect_one();
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // K-major: 16 k-elements = 32 bytes inside the 128B swizzle row, rows grouped by 8 (SBO = 1024 B).
+            // MN-major: 16 k-rows = two 8-row groups of 1024 B (SBO), the next 64-wide MN slab is 8192 B away (LBO).
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            const uint64_t da0 = A_MN ? ptx::make_smem_desc_sw128(smem_base, 8192, 1024)
+                                      : ptx::make_smem_desc_sw128(smem_base, 16, 1024);
+            const uint64_t db0 = B_MN ? ptx::make_smem_desc_sw128(smem_base + L::kABytes, 8192, 1024)
+                                      : ptx::make_smem_desc_sw128(smem_base + L::kABytes, 16, 1024);
+            constexpr uint32_t kStepA = (A_MN ? 2048 : 32) >> 4, kStepB = (B_MN ? 2048 : 32) >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
@@ -680,28 +688,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int kb = kb0; kb < kb1; ++kb) {
                     if (!VLK_DBG_SKIP_LOADS(ep)) ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after_sync();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + L::kABytes;
+                    const uint32_t soff = static_cast<uint32_t>(stage) * (L::kStageBytes >> 4);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // K-major: 16 k-elements = 32 bytes inside the 128B swizzle row, rows grouped by 8
-                        // (SBO = 1024 B).  MN-major: 16 k-rows = two 8-row groups of 1024 B (SBO), the next
-                        // 64-wide MN slab is 8192 B away (LBO).
-                        const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16_ss(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            ptx::umma_bf16_ss(tmem_d, da0 + (soff + k * kStepA), db0 + (soff + k * kStepB), idesc,
+                                              ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        // frees the smem slot (in every CTA that multicasts into it) when these MMAs retire
+                        if constexpr (CLUSTER == 1) ptx::umma_commit(&empty_bar[stage]);
+                        else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);
                     }
-                    // frees the smem slot (in every CTA that multicasts into it) when these MMAs retire
-                    if constexpr (CLUSTER == 1) ptx::umma_commit(&empty_bar[stage]);
-                    else ptx::umma_commit_mcast(&empty_bar[stage], kMcastMask);
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                if (issuer) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else if (warp_idx >= kEpiWarp0) {
@@ -717,14 +721,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
             const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
-            uint8_t* stage = smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes;
-            epilogue_prefetch(ep, stage, row0, n0, kColsPerWarp, M, N, lane);
-            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-            ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp<false>(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
-                          static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
+            EpiPre pre;
+            epilogue_prefetch_direct(ep, pre, row0, n0, M, N, lane);
+            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            ptx::tc_fence_after_sync();
+            epilogue_warp_direct<false>(ep, pre, taddr, row0, n0, kColsPerWarp, M, N, lane,
+                                        static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -760,8 +764,7 @@ struct SmemLayout2 {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagingOffset = kStages * kStageBytes;
-    static constexpr int kBarOffset = kStagingOffset + kNumEpiWarps * kEpiStageBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;
 };
@@ -779,7 +782,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-    const int warp_idx = threadIdx.x >> 5;
+    const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int cta_rank = static_cast<int>(ptx::cluster_ctarank());
     const bool is_leader = cta_rank == 0;
@@ -820,9 +823,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
     if (warp_idx == 0) {
         // ===================================== TMA producer (both CTAs) =========================
-        if (lane == 0 && !VLK_DBG_SKIP_LOADS(ep)) {
+        const bool issuer = ptx::elect_one();
+        if (!VLK_DBG_SKIP_LOADS(ep)) {
             int stage = 0;
             uint32_t phase = 0;
+            VLK_DBG_CLOCK_DECL(c_slot);
             for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
                 int m_unit, n_blk;
                 unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
@@ -830,9 +835,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const int n0 = n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2);
                 const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    VLK_DBG_TIMED(c_slot, ptx::mbar_wait(&empty_bar[stage], phase ^ 1));
                     uint8_t* sa = smem + stage * L::kStageBytes;
                     uint8_t* sb = sa + L::kABytes;
+                    if (issuer) {
                     if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     if constexpr (!A_MN) {
                         ptx::tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
@@ -847,47 +853,71 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         for (int j = 0; j < BLOCK_N / 128; ++j)
                             ptx::tma_load_2d_2sm(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + j * 64, kb * BLOCK_K);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
             }
+            if (issuer) VLK_DBG_PUT(ep, 0, c_slot);
         }
     } else if (warp_idx == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && is_leader) {
+        // Converged warp, one elected lane issues, operands in uniform registers (see the single-CTA kernel).
+        if (is_leader) {
+            const bool issuer = ptx::elect_one();
             constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(2 * BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            const uint32_t smem_base = ptx::smem_u32(smem);
+            const uint64_t da0 = A_MN ? ptx::make_smem_desc_sw128(smem_base, 8192, 1024)
+                                      : ptx::make_smem_desc_sw128(smem_base, 16, 1024);
+            const uint64_t db0 = B_MN ? ptx::make_smem_desc_sw128(smem_base + L::kABytes, 8192, 1024)
+                                      : ptx::make_smem_desc_sw128(smem_base + L::kABytes, 16, 1024);
+            constexpr uint32_t kStepA = (A_MN ? 2048 : 32) >> 4, kStepB = (B_MN ? 2048 : 32) >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
+            VLK_DBG_CLOCK_DECL(c_acc);
+            VLK_DBG_CLOCK_DECL(c_full);
+            VLK_DBG_CLOCK_DECL(c_total);
+#ifdef VLK_BRINGUP
+            c_total = -clock64();
+#endif
             for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
                 const int acc = local_tile & 1;
                 const uint32_t acc_phase = (local_tile >> 1) & 1;
-                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                VLK_DBG_TIMED(c_acc, ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1));
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
                 const int kb0 = (tile / num_out_tiles) * kb_per_split, kb1 = min(kb0 + kb_per_split, total_k_blocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    if (!VLK_DBG_SKIP_LOADS(ep)) ptx::mbar_wait(&full_bar[stage], phase);
+                    if (!VLK_DBG_SKIP_LOADS(ep)) VLK_DBG_TIMED(c_full, ptx::mbar_wait(&full_bar[stage], phase));
                     ptx::tc_fence_after_sync();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + L::kABytes;
+                    const uint32_t soff = static_cast<uint32_t>(stage) * (L::kStageBytes >> 4);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                                 : ptx::make_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        ptx::umma_bf16_ss_2sm(tmem_d, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            ptx::umma_bf16_ss_2sm(tmem_d, da0 + (soff + k * kStepA), db0 + (soff + k * kStepB), idesc,
+                                                  ((kb - kb0) | k) != 0 ? 1u : 0u);
+                        ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
                     }
-                    ptx::umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit_2sm(&tmem_full_bar[acc], 0b11);  // both halves of the accumulator are complete
+                if (issuer) ptx::umma_commit_2sm(&tmem_full_bar[acc], 0b11);  // both halves of the accumulator are complete
+                __syncwarp();
+            }
+#ifdef VLK_BRINGUP
+            c_total += clock64();
+#endif
+            if (issuer) {
+                VLK_DBG_PUT(ep, 1, c_acc);
+                VLK_DBG_PUT(ep, 2, c_full);
+                VLK_DBG_PUT(ep, 3, c_total);
             }
         }
     } else if (warp_idx >= kEpiWarp0) {
@@ -896,6 +926,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int half = (warp_idx - kEpiWarp0) >> 2;
         constexpr int kColsPerWarp = BLOCK_N / 2;
         int local_tile = 0;
+        VLK_DBG_CLOCK_DECL(c_pre);
+        VLK_DBG_CLOCK_DECL(c_wait);
+        VLK_DBG_CLOCK_DECL(c_work);
         for (int tile = unit0; tile < num_tiles; tile += unit_stride, ++local_tile) {
             int m_unit, n_blk;
             unit_to_mn(tile % num_out_tiles, num_m_units, num_n_blocks, group, m_unit, n_blk);
@@ -903,17 +936,22 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int acc = local_tile & 1;
             const uint32_t acc_phase = (local_tile >> 1) & 1;
             const int row0 = m_blk * BLOCK_M + quad * 32, n0 = n_blk * BLOCK_N + half * kColsPerWarp;
-            uint8_t* stage = smem + L::kStagingOffset + (warp_idx - kEpiWarp0) * kEpiStageBytes;
-            epilogue_prefetch(ep, stage, row0, n0, kColsPerWarp, M, N, lane);
-            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-            ptx::tc_fence_after_sync();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
-            epilogue_warp<(BLOCK_N == 256)>(ep, stage, taddr, row0, n0, kColsPerWarp, M, N, lane,
-                          static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
+            EpiPre pre;
+            VLK_DBG_TIMED(c_pre, epilogue_prefetch_direct(ep, pre, row0, n0, M, N, lane));
+            VLK_DBG_TIMED(c_wait, ptx::mbar_wait(&tmem_full_bar[acc], acc_phase));
+            ptx::tc_fence_after_sync();
+            VLK_DBG_TIMED(c_work, epilogue_warp_direct<(BLOCK_N == 256)>(ep, pre, taddr, row0, n0, kColsPerWarp, M, N, lane,
+                          static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles)));
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[acc], 0);  // the leader's barrier
+        }
+        if (warp_idx == kEpiWarp0 && lane == 0) {
+            VLK_DBG_PUT(ep, 4, c_pre);
+            VLK_DBG_PUT(ep, 5, c_wait);
+            VLK_DBG_PUT(ep, 6, c_work);
         }
     }
 
@@ -1069,8 +1107,8 @@ template <bool A_MN, bool B_MN>
 int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int sms, int bn,
              int cluster, cudaStream_t stream) {
     if (cluster == 3) {  // cta_group::2 pair
-        if (bn == 256) return launch_2cta<256, 5, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
-        return launch_2cta<128, 6, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
+        if (bn == 256) return launch_2cta<256, 7, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
+        return launch_2cta<128, 8, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
     }
 #ifdef VLK_GEMM_MULTICAST_VARIANT   // single-CTA MMA with TMA multicast of B across a CTA pair: measured, never the
     if (cluster == 2) {             // fastest (profiles/r01_gemm_sweep2.log); compiled only for that comparison
@@ -1082,11 +1120,11 @@ int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, 
 #endif
     switch (bn) {
         case 256:
-            return launch<256, 3, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
+            return launch<256, 4, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
         case 128:
-            return launch<128, 5, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
+            return launch<128, 6, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
         default:
-            return launch<64, 6, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
+            return launch<64, 8, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, sms, stream);
     }
 }
 
@@ -1178,6 +1216,10 @@ int vlk::gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, i
     ep.ce_lse = nullptr;
     ep.ce_row_scale = nullptr;
     ep.ce_col0 = 0;
+    {
+        auto wide = [](const void* p, int ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & 31u) == 0 && ld % 16 == 0); };
+        ep.wide_io = wide(D, ldd) && wide(residual, ldr) && wide(aux_in, ld_aux) && wide(aux_out, ld_aux);
+    }
     if (ce != nullptr) {
         ep.ce_mode = ce->mode;
         ep.ce_labels = ce->labels;
@@ -1190,6 +1232,7 @@ int vlk::gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, i
 #ifdef VLK_BRINGUP
     ep.debug = 0;
     if (const char* f = getenv("VLK_GEMM_DEBUG")) ep.debug = atoi(f);
+    ep.dbg_out = g_gemm_dbg_out;
 #endif
 
     // Tile selection (measured on B200, profiles/r01_gemm_sweep*.log): the 256-wide tile wins on every shape of
@@ -1227,6 +1270,10 @@ int vlk::gemm_impl(const void* A, const void* B, void* D, int M, int N, int K, i
     if (transA && !transB) return dispatch<true, false>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
     return dispatch<true, true>(ta, tb, M, N, K, ep, sms, bn, cluster, s);
 }
+
+#ifdef VLK_BRINGUP
+extern "C" void vlk_bringup_set_gemm_debug(void* p) { g_gemm_dbg_out = static_cast<unsigned long long*>(p); }
+#endif
 
 extern "C" int vlk_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
                              int transA, int transB, const void* bias, const void* residual, int ldr,

@@ -1,10 +1,15 @@
 #!/bin/bash
-# Bring-up build of the attention kernels (-DVLK_BRINGUP: phase timestamps) -> scripts/probe/libvlk_attn_bringup.so
+# Bring-up build of libvlk (-DVLK_BRINGUP: phase timestamps in the attention kernels, wait-time counters and
+# work-skipping switches in the GEMM) -> scripts/probe/libvlk_bringup.so.  Never loaded by the package.
+# usage: build_bringup.sh [extra nvcc flags, e.g. -DVLK_EXPERIMENT=1] ; output name can be set with OUT=...
 set -e
 cd "$(dirname "$0")/../../gpt2-vision-language_b200/csrc"
-mkdir -p /tmp/build_bringup
-for f in api attention_api attention_flash attention_pair attention_simt attention_tcgen05; do
-  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr -DVLK_BRINGUP -c $f.cu -o /tmp/build_bringup/$f.o 2>/dev/null &
+OUT=${OUT:-libvlk_bringup.so}
+B=/tmp/build_bringup_${OUT%.so}
+mkdir -p $B
+for f in *.cu; do
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr -DVLK_BRINGUP "$@" -c $f -o $B/${f%.cu}.o 2> $B/${f%.cu}.log &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scripts/probe/libvlk_attn_bringup.so /tmp/build_bringup/*.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scripts/probe/$OUT $B/*.o -lcudart
+ln -sf $OUT ../../scripts/probe/libvlk_attn_bringup.so 2>/dev/null || true
