@@ -64,7 +64,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint64_t* bar_o = bar_q + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qb * BQ;
     const int shift = p.Tk - p.Tq;
@@ -116,18 +116,21 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
     for (int j = 0; j < nkb; ++j) {
         const uint32_t par = (j >> 1) & 1;
-        if (threadIdx.x == 0) {
+        if (warp == 0) {   // converged warp, one elected lane issues: MMA operands stay in uniform registers
             if (j == 0) ptx::mbar_wait(bar_q, 0);
             ptx::mbar_wait(&bar_kv[j & 1], par);
             ptx::tc_fence_after_sync();
             const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
-            ptx::umma_commit(bar_s);
-            if (j + 1 < nkb) load_kv(j + 1);  // the other buffer was released by the previous iteration's bar_o wait
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                      ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
+                ptx::umma_commit(bar_s);
+                if (j + 1 < nkb) load_kv(j + 1);  // the other buffer was released by the previous iteration's bar_o wait
+            }
+            __syncwarp();
         }
         ptx::mbar_wait(bar_s, j & 1);
         ptx::tc_fence_after_sync();
@@ -179,14 +182,17 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (warp == 0) {
             ptx::tc_fence_after_sync();
             const uint32_t av = ptx::smem_u32(sKV + (j & 1) * 2 * kTile + kTile);
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-                ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
-            ptx::umma_commit(bar_o);
+                for (int k = 0; k < BK / 16; ++k)
+                    ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
+                ptx::umma_commit(bar_o);
+            }
+            __syncwarp();
         }
         ptx::mbar_wait(bar_o, j & 1);
         ptx::tc_fence_after_sync();
@@ -277,7 +283,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* bar_acc = bar_kv + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int k0 = kb * BK;
     const int shift = p.Tk - p.Tq;
@@ -341,22 +347,25 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             st[row] = qi < p.Tq ? p.lse[stat_base + qi] * 1.4426950408889634f : INFINITY;  // p -> 0 for padded rows
             st[128 + row] = qi < p.Tq ? p.delta[stat_base + qi] : 0.f;
         }
-        if (threadIdx.x == 0) {
+        if (warp == 0) {   // converged warp, one elected lane issues
             if (it == 0) ptx::mbar_wait(bar_kv, 0);
             ptx::mbar_wait(&bar_q[buf], par);
             ptx::tc_fence_after_sync();
             const uint32_t ak = ptx::smem_u32(sK), av = ptx::smem_u32(sV);
             const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQ, 0, 0);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQ, 0, 0);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
-                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(bq + k * 32, 16, 1024), idesc, k != 0);
-                ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(bdo + k * 32, 16, 1024), idesc, k != 0);
+                for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
+                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
+                                      ptx::make_smem_desc_sw128(bq + k * 32, 16, 1024), idesc, k != 0);
+                    ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
+                                      ptx::make_smem_desc_sw128(bdo + k * 32, 16, 1024), idesc, k != 0);
+                }
+                ptx::umma_commit(bar_s);
+                if (i + 1 < nqb) load_q(i + 1);  // other buffer: its last readers (dV/dK MMAs) were waited on via bar_acc
             }
-            ptx::umma_commit(bar_s);
-            if (i + 1 < nqb) load_q(i + 1);  // other buffer: its last readers (dV/dK MMAs) were waited on via bar_acc
+            __syncwarp();
         }
         __syncthreads();  // sStat visible
         ptx::mbar_wait(bar_s, it & 1);
@@ -392,16 +401,19 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (warp == 0) {
             ptx::tc_fence_after_sync();
             const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BQ / 16; ++k) {
-                ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
-                ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
+                for (int k = 0; k < BQ / 16; ++k) {
+                    ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
+                    ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
+                }
+                ptx::umma_commit(bar_acc);
             }
-            ptx::umma_commit(bar_acc);
+            __syncwarp();
         }
         // these MMAs read P^T / dS^T and this Q/dO buffer: wait before either is overwritten
         ptx::mbar_wait(bar_acc, it & 1);
@@ -475,7 +487,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* bar_acc = bar_q + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int q0 = qb * BQ;
     const int shift = p.Tk - p.Tq;
@@ -529,22 +541,25 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
     for (int j = 0; j < nkb; ++j) {
         const uint32_t par = (j >> 1) & 1;
-        if (threadIdx.x == 0) {
+        if (warp == 0) {   // converged warp, one elected lane issues
             if (j == 0) ptx::mbar_wait(bar_q, 0);
             ptx::mbar_wait(&bar_kv[j & 1], par);
             ptx::tc_fence_after_sync();
             const uint32_t aq = ptx::smem_u32(sQ), ado = ptx::smem_u32(sdO);
             const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile), bv = bk + kTile;
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
-                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc, k != 0);
-                ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(bv + k * 32, 16, 1024), idesc, k != 0);
+                for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
+                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                      ptx::make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc, k != 0);
+                    ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
+                                      ptx::make_smem_desc_sw128(bv + k * 32, 16, 1024), idesc, k != 0);
+                }
+                ptx::umma_commit(bar_s);
+                if (j + 1 < nkb) load_kv(j + 1);
             }
-            ptx::umma_commit(bar_s);
-            if (j + 1 < nkb) load_kv(j + 1);
+            __syncwarp();
         }
         ptx::mbar_wait(bar_s, j & 1);
         ptx::tc_fence_after_sync();
@@ -573,14 +588,17 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::tmem_st_wait();
         ptx::tc_fence_before_sync();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (warp == 0) {
             ptx::tc_fence_after_sync();
             const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K_j read MN-major: N = d, K = keys
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K_j read MN-major: N = d, K = keys
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-                ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
-            ptx::umma_commit(bar_acc);
+                for (int k = 0; k < BK / 16; ++k)
+                    ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
+                ptx::umma_commit(bar_acc);
+            }
+            __syncwarp();
         }
         ptx::mbar_wait(bar_acc, j & 1);
         ptx::tc_fence_after_sync();

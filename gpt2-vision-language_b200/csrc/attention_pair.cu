@@ -101,7 +101,7 @@ attn_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* bar_o = bar_in + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 3);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int hh = warp >> 1;                      // which of the two stacked heads this thread's row belongs to
     const int i = threadIdx.x & 63;                // query row inside the head
     const int unit = 2 * blockIdx.x + hh;          // flattened (b, h)
@@ -127,26 +127,32 @@ attn_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 64;
 
-    if (threadIdx.x == 0) {
-        ptx::mbar_arrive_expect_tx(bar_in, 3 * kPairTile);
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_in, 3 * kPairTile);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int u = 2 * blockIdx.x + t;
-            const bool ok = u < p.B * p.H;
-            const int bb = ok ? u / p.H : p.B, hx = ok ? u % p.H : 0;  // batch index B is out of bounds: zero fill
-            ptx::tma_load_3d(sQ + t * kHalfTile, &tmap_q, bar_in, hx * 64, 0, bb);
-            ptx::tma_load_3d(sK + t * kHalfTile, &tmap_k, bar_in, hx * 64, 0, bb);
-            ptx::tma_load_3d(sV + t * kHalfTile, &tmap_v, bar_in, hx * 64, 0, bb);
+            for (int t = 0; t < 2; ++t) {
+                const int u = 2 * blockIdx.x + t;
+                const bool ok = u < p.B * p.H;
+                const int bb = ok ? u / p.H : p.B, hx = ok ? u % p.H : 0;  // batch index B is out of bounds: zero fill
+                ptx::tma_load_3d(sQ + t * kHalfTile, &tmap_q, bar_in, hx * 64, 0, bb);
+                ptx::tma_load_3d(sK + t * kHalfTile, &tmap_k, bar_in, hx * 64, 0, bb);
+                ptx::tma_load_3d(sV + t * kHalfTile, &tmap_v, bar_in, hx * 64, 0, bb);
+            }
         }
+        __syncwarp();
         ptx::mbar_wait(bar_in, 0);
         ptx::tc_fence_after_sync();
         const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sK);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128, 0, 0);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
-        ptx::umma_commit(bar_s);
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_s);
+        }
+        __syncwarp();
     }
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const int shift = p.Tk - p.Tq;
@@ -208,14 +214,17 @@ attn_pair_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     ptx::tmem_st_wait();
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
         ptx::tc_fence_after_sync();
         const uint32_t av = ptx::smem_u32(sV);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // V [key x 64] read MN-major
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
-        ptx::umma_commit(bar_o);
+            for (int k = 0; k < 8; ++k)
+                ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_o);
+        }
+        __syncwarp();
     }
     ptx::mbar_wait(bar_o, 0);
     ptx::tc_fence_after_sync();
@@ -257,7 +266,7 @@ attn_pair_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* bar_acc = bar_in + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 3);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int hh = warp >> 1;
     const int i = threadIdx.x & 63;               // this thread's row inside its head: key row in phase A, query row in B
     const int unit = 2 * blockIdx.x + hh;
@@ -315,19 +324,22 @@ attn_pair_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         sLse[threadIdx.x] = ls;
         sDelta[threadIdx.x] = d;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
         ptx::mbar_wait(bar_in, 0);
         ptx::tc_fence_after_sync();
         const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sK), av = ptx::smem_u32(sV), ado = ptx::smem_u32(sdO);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128, 0, 0);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
-            ptx::umma_bf16_ss(tR0, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024), idesc, k != 0);
-            ptx::umma_bf16_ss(tR1, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024), idesc, k != 0);
+            for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
+                ptx::umma_bf16_ss(tR0, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024), idesc, k != 0);
+                ptx::umma_bf16_ss(tR1, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024), idesc, k != 0);
+            }
+            ptx::umma_commit(bar_s);
         }
-        ptx::umma_commit(bar_s);
+        __syncwarp();
     }
     __syncthreads();  // sLse / sDelta visible
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
@@ -378,16 +390,19 @@ attn_pair_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     ptx::tmem_st_wait();
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
         ptx::tc_fence_after_sync();
         const uint32_t bq = ptx::smem_u32(sQ), bdo = ptx::smem_u32(sdO);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            ptx::umma_bf16_ts(tR0 + 64, tR0 + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
-            ptx::umma_bf16_ts(tR1 + 64, tR1 + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
+            for (int k = 0; k < 8; ++k) {
+                ptx::umma_bf16_ts(tR0 + 64, tR0 + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
+                ptx::umma_bf16_ts(tR1 + 64, tR1 + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
+            }
+            ptx::umma_commit(bar_acc);
         }
-        ptx::umma_commit(bar_acc);
+        __syncwarp();
     }
     ptx::mbar_wait(bar_acc, 0);
     ptx::tc_fence_after_sync();
@@ -408,18 +423,21 @@ attn_pair_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();  // every TMEM read of phase A is done before phase B's MMAs overwrite R0 / R1
 
     // ---------------- phase B: thread = query row qi = i ----------------
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
         ptx::tc_fence_after_sync();
         const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sK), av = ptx::smem_u32(sV), ado = ptx::smem_u32(sdO);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 128, 0, 0);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
-            ptx::umma_bf16_ss(tR0, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
-            ptx::umma_bf16_ss(tR1, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
-                              ptx::make_smem_desc_sw128(av + k * 32, 16, 1024), idesc, k != 0);
+            for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
+                ptx::umma_bf16_ss(tR0, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
+                ptx::umma_bf16_ss(tR1, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(av + k * 32, 16, 1024), idesc, k != 0);
+            }
+            ptx::umma_commit(bar_s);
         }
-        ptx::umma_commit(bar_s);
+        __syncwarp();
     }
     ptx::mbar_wait(bar_s, 1);
     ptx::tc_fence_after_sync();
@@ -458,14 +476,17 @@ attn_pair_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     ptx::tmem_st_wait();
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // converged warp, one elected lane issues (MMA operands in uniform registers)
         ptx::tc_fence_after_sync();
         const uint32_t bk = ptx::smem_u32(sK);
         const uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K [key x 64] read MN-major
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            ptx::umma_bf16_ts(tR0, tR1 + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
-        ptx::umma_commit(bar_acc);
+            for (int k = 0; k < 8; ++k)
+                ptx::umma_bf16_ts(tR0, tR1 + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_acc);
+        }
+        __syncwarp();
     }
     ptx::mbar_wait(bar_acc, 1);
     ptx::tc_fence_after_sync();

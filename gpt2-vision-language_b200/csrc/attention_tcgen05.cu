@@ -73,10 +73,6 @@ struct Fwd4Params {
     const bf16* q;
     long long q_bs;
     int q_rs, tail_rows;
-    // MMA issue order: 0 = wait for the previous tile's probabilities before producing the next tile's scores (the two
-    // groups' exp phases never overlap); 1 = scores first, so both groups run their softmax concurrently (two warps
-    // per scheduler hide each other's TMEM / MUFU latencies)
-    int order;
 };
 
 #ifdef VLK_BRINGUP
@@ -187,7 +183,7 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     uint64_t* s_free = bars + 16;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp: uniform for the compiler
     const int n_main = p.n_main, n_extra = p.n_extra, nqb = p.nqb;
     const int num_units = p.B * p.H;
 
@@ -220,135 +216,104 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        if (lane == 0) {
-            uint32_t qcnt[2] = {0, 0};
-            int it = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
-                const int b = u / p.H, h = u % p.H, s = it & 1;
-                uint8_t* st = smem + s * k4KVStage;
-                ptx::mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
+        // converged warp; one elected lane issues (TMA operands stay in uniform registers)
+        const bool issuer = ptx::elect_one();
+        uint32_t qcnt0 = 0, qcnt1 = 0;
+        int it = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+            const int b = u / p.H, h = u % p.H, s = it & 1;
+            uint8_t* st = smem + s * k4KVStage;
+            ptx::mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
+            if (issuer) {
                 ptx::mbar_arrive_expect_tx(&kfull[s], kv_bytes);
                 ptx::tma_load_3d(st, &tmap_k, &kfull[s], h * 64, 0, b);
                 if (n_extra > 0) ptx::tma_load_3d(st + 32 * 1024, &tmap_kx, &kfull[s], h * 64, 256, b);
                 ptx::mbar_arrive_expect_tx(&vfull[s], kv_bytes);
                 ptx::tma_load_3d(st + 34 * 1024, &tmap_v, &vfull[s], h * 64, 0, b);
                 if (n_extra > 0) ptx::tma_load_3d(st + 66 * 1024, &tmap_vx, &vfull[s], h * 64, 256, b);
-                for (int qb = 0; qb < nqb; ++qb) {
-                    const int g = qb & 1;
-                    ptx::mbar_wait(&q_empty[g], (qcnt[g] & 1) ^ 1);
+            }
+            __syncwarp();
+            for (int qb = 0; qb < nqb; ++qb) {
+                const int g = qb & 1;
+                const uint32_t qc = g ? qcnt1 : qcnt0;
+                ptx::mbar_wait(&q_empty[g], (qc & 1) ^ 1);
+                if (issuer) {
                     ptx::mbar_arrive_expect_tx(&q_full[g], kQBytes);
                     ptx::tma_load_3d(smem + k4OffQ + g * 16 * 1024, &tmap_q, &q_full[g], h * 64, qb * 128, b);
-                    ++qcnt[g];
                 }
+                __syncwarp();
+                if (g) ++qcnt1; else ++qcnt0;
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
-        // Ping-pong schedule over the flat tile sequence t = 0, 1, 2, ... (slot = query block & 1):
-        //     wait softmax(t-1) done  ->  issue S(t)  ->  issue P.V(t-1)
-        // so the exp-heavy (MUFU-bound) phase of tile t never overlaps that of tile t-1; instead it runs under
-        // the P.V product, normalisation and stores of tile t-1 in the other group.
-        if (lane == 0) {
-            uint32_t cnt_s[2] = {0, 0}, cnt_o[2] = {0, 0};
-            const uint32_t idesc_s = ptx::make_idesc_bf16_f32(128, n_main, 0, 0);
-            const uint32_t idesc_o = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
-            const int ksteps = n_main / 16;
-            int prev_g = -1, prev_s = 0, prev_last = 0;
-            uint32_t prev_kvpar = 0;
-            auto issue_pv = [&]() {
-                // P.V of the previous tile (its softmax was already waited for)
-                const uint32_t sv = ptx::smem_u32(smem + prev_s * k4KVStage) + 34 * 1024;
-                ptx::mbar_wait(&vfull[prev_s], prev_kvpar);
-                ptx::tc_fence_after_sync();
-                for (int k = 0; k < ksteps; ++k)
-                    ptx::umma_bf16_ts(tmem + prev_g * 256 + 128, tmem + prev_g * 256 + k * 8,
-                                      ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc_o, k != 0);
-                ptx::umma_commit(&o_ready[prev_g]);
-                ++cnt_o[prev_g];
-                if (prev_last) ptx::umma_commit(&kv_empty[prev_s]);  // every MMA of that unit has been issued
-            };
-            int it = 0;
-            for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
-                const int s = it & 1;
-                const uint32_t kvpar = (it >> 1) & 1;
-                const uint32_t sk = ptx::smem_u32(smem + s * k4KVStage);
-                ptx::mbar_wait(&kfull[s], kvpar);
-                for (int qb = 0; qb < nqb; ++qb) {
-                    const int g = qb & 1;
-                    // only when the previous tile's probabilities are complete may the next tile's scores be produced
-                    // (keeps the two groups' exp phases from overlapping); S(t) goes first because it is on the
-                    // critical path, P.V(t-1) right behind it
-                    const uint32_t par = cnt_s[g] & 1;
-                    if (p.order != 0) {
-                        auto issue_s = [&]() {
-                            ptx::tc_fence_after_sync();
-                            const uint32_t sq1 = ptx::smem_u32(smem + k4OffQ + g * 16 * 1024);
+        // Flat tile sequence t = 0, 1, 2, ... (slot = query block & 1):  issue S(t), then P.V(t-1) as soon as its
+        // probabilities are complete — both groups run their softmax concurrently (two warps per scheduler hide each
+        // other's TMEM / MUFU latencies; measured against "P.V(t-1) first": 73.5 vs 78.0 us per CLIP layer).
+        // The warp walks the loop CONVERGED and one elected lane issues: every tcgen05.mma operand is then warp-uniform
+        // and lives in uniform registers (issued from inside `if (lane == 0)` each MMA cost an ELECT / R2UR loop of ~25
+        // instructions, 20 MMAs per tile).
+        const bool issuer = ptx::elect_one();
+        uint32_t cnt_s0 = 0, cnt_s1 = 0, cnt_o0 = 0, cnt_o1 = 0;
+        const uint32_t idesc_s = ptx::make_idesc_bf16_f32(128, n_main, 0, 0);
+        constexpr uint32_t idesc_o = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+        const int ksteps = n_main / 16;
+        int prev_g = -1, prev_s = 0, prev_last = 0;
+        uint32_t prev_kvpar = 0;
+        auto issue_pv = [&]() {
+            // P.V of the previous tile, once its probabilities are complete
+            ptx::mbar_wait(&p_ready[prev_g], (prev_g ? cnt_o1 : cnt_o0) & 1);
+            const uint32_t sv = ptx::smem_u32(smem + prev_s * k4KVStage) + 34 * 1024;
+            ptx::mbar_wait(&vfull[prev_s], prev_kvpar);
+            ptx::tc_fence_after_sync();
+            const uint32_t t_o = tmem + prev_g * 256 + 128, t_p = tmem + prev_g * 256;
+            if (issuer) {
+                if (ksteps == 16) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16_ss(tmem + g * 256, ptx::make_smem_desc_sw128(sq1 + k * 32, 16, 1024),
-                                                  ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
-                            ptx::umma_commit(&s_ready[g]);
-                            ++cnt_s[g];
-                        };
-                        if (p.order == 1) {          // scores first, then the previous tile's P.V
-                            ptx::mbar_wait(&q_full[g], par);
-                            ptx::mbar_wait(&s_free[g], par ^ 1);
-                            issue_s();
-                            if (prev_g >= 0) {
-                                ptx::mbar_wait(&p_ready[prev_g], cnt_o[prev_g] & 1);
-                                issue_pv();
-                            }
-                        } else {                     // whichever becomes ready first
-                            bool s_done = false, pv_done = prev_g < 0;
-                            while (!s_done || !pv_done) {
-                                if (!s_done && ptx::mbar_try_wait(&q_full[g], par) &&
-                                    ptx::mbar_try_wait(&s_free[g], par ^ 1)) {
-                                    issue_s();
-                                    s_done = true;
-                                }
-                                if (!pv_done && ptx::mbar_try_wait(&p_ready[prev_g], cnt_o[prev_g] & 1)) {
-                                    issue_pv();
-                                    pv_done = true;
-                                }
-                            }
-                        }
-                        prev_g = g;
-                        prev_s = s;
-                        prev_kvpar = kvpar;
-                        prev_last = (qb == nqb - 1);
-                        continue;
-                    }
-                    bool pv_pending = prev_g >= 0;
-                    if (pv_pending) {
-                        ptx::mbar_wait(&p_ready[prev_g], cnt_o[prev_g] & 1);
-                        // if this tile's inputs are not there yet, do not let the finished tile's P.V queue behind them
-                        if (!(ptx::mbar_try_wait(&q_full[g], par) && ptx::mbar_try_wait(&s_free[g], par ^ 1))) {
-                            issue_pv();
-                            pv_pending = false;
-                        }
-                    }
-                    ptx::mbar_wait(&q_full[g], par);
-                    ptx::mbar_wait(&s_free[g], par ^ 1);
-                    ptx::tc_fence_after_sync();
-                    const uint32_t sq = ptx::smem_u32(smem + k4OffQ + g * 16 * 1024);
+                    for (int k = 0; k < 16; ++k)
+                        ptx::umma_bf16_ts(t_o, t_p + k * 8, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc_o,
+                                          k != 0);
+                } else {
+                    for (int k = 0; k < ksteps; ++k)
+                        ptx::umma_bf16_ts(t_o, t_p + k * 8, ptx::make_smem_desc_sw128(sv + k * 2048, 8192, 1024), idesc_o,
+                                          k != 0);
+                }
+                ptx::umma_commit(&o_ready[prev_g]);
+                if (prev_last) ptx::umma_commit(&kv_empty[prev_s]);  // every MMA of that unit has been issued
+            }
+            __syncwarp();
+            if (prev_g) ++cnt_o1; else ++cnt_o0;
+        };
+        int it = 0;
+        for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+            const int s = it & 1;
+            const uint32_t kvpar = (it >> 1) & 1;
+            const uint32_t sk = ptx::smem_u32(smem + s * k4KVStage);
+            ptx::mbar_wait(&kfull[s], kvpar);
+            for (int qb = 0; qb < nqb; ++qb) {
+                const int g = qb & 1;
+                const uint32_t par = (g ? cnt_s1 : cnt_s0) & 1;
+                ptx::mbar_wait(&q_full[g], par);
+                ptx::mbar_wait(&s_free[g], par ^ 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t sq = ptx::smem_u32(smem + k4OffQ + g * 16 * 1024);
+                if (issuer) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_bf16_ss(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
                                           ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
                     ptx::umma_commit(&s_ready[g]);
-                    ++cnt_s[g];
-                    if (pv_pending) issue_pv();
-                    prev_g = g;
-                    prev_s = s;
-                    prev_kvpar = kvpar;
-                    prev_last = (qb == nqb - 1);
                 }
-            }
-            if (prev_g >= 0) {  // drain: the last tile's P.V
-                ptx::mbar_wait(&p_ready[prev_g], cnt_o[prev_g] & 1);
-                issue_pv();
+                __syncwarp();
+                if (g) ++cnt_s1; else ++cnt_s0;
+                if (prev_g >= 0) issue_pv();
+                prev_g = g;
+                prev_s = s;
+                prev_kvpar = kvpar;
+                prev_last = (qb == nqb - 1);
             }
         }
+        if (prev_g >= 0) issue_pv();  // drain: the last tile's P.V
     } else if (warp >= 4) {
         // ===================================== softmax / epilogue groups ========================
         const int g = (warp - 4) >> 2;
@@ -635,9 +600,6 @@ int attn_mid_fwd(const void* q, const void* k, const void* v, void* o, float* ls
     p4.q_bs = q_bs;
     p4.q_rs = q_rs;
     p4.tail_rows = tail;   // folded into the persistent kernel
-    // MMA issue order 1 (scores of the next block before the previous block's P.V), measured at B=64, H=16, T=257
-    // (graph-timed): order 0 78.0 us, 1 73.5 us, 2 76.5 us
-    p4.order = 1;
     const int sms = device_sm_count();
     VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
     const int units = B * H;
