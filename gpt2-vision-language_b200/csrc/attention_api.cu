@@ -7,6 +7,8 @@
 //   Tq < 64 against Tk > 64          attention_simt.cu     CUDA-core forward (KV-cached decode rows)
 //
 // The map is a pure function of the shapes: no environment switches, no alternative implementations in the library.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vlk {
@@ -28,7 +30,7 @@ int attn_pair_bwd(const void* q, const void* k, const void* v, const void* o, co
                   const unsigned long long* seed_state, unsigned int stream_id, cudaStream_t stream);
 int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                    long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, cudaStream_t stream);
+                   int o_rs, int causal, float scale, cudaStream_t stream, int q_rows);
 int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int B, int H, int Tq, int Tk, long long q_bs, int q_rs, long long k_bs,
                    int k_rs, long long v_bs, int v_rs, long long o_bs, int o_rs, long long dq_bs, int dq_rs,
@@ -64,9 +66,17 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (small)
         return attn_pair_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale,
                              dropout_p, seed_state, stream_id, s);
-    if (Tk > kMidMaxKeys)
-        return attn_flash_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale,
-                              s);
+    if (Tk > kMidMaxKeys || (Tq >= 64 && Tk > 64 && getenv("VLK_MID_FLASH") != nullptr)) {
+        // whole 128-row query blocks on the tensor cores; a remainder of <= 8 rows (CLIP's 257th token) would waste a
+        // 128-row tile per (batch, head): those rows go to the CUDA-core few-rows kernel
+        const int tail = Tq % 128;
+        const bool split = tail > 0 && tail <= 8 && Tq > 128 && Tk <= 288;
+        int rc = attn_flash_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale,
+                                s, split ? Tq - tail : Tq);
+        if (rc || !split) return rc;
+        return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale, s,
+                             Tq - tail);
+    }
     if (Tq >= 64 && Tk > 64)
         return attn_mid_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale, s);
     return attn_fwd_simt(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale, s,

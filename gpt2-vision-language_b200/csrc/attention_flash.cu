@@ -34,6 +34,21 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
+#ifdef VLK_BRINGUP
+// bring-up instrumentation (never compiled into the shipped library): cycles per phase of the forward loop, summed over
+// the iterations of a CTA, by thread 0 and thread 255; read back by vlk_debug_flash_dump
+__device__ long long g_flash_dbg[64 * 16];
+#define FDBG_DECL long long fd_t = clock64(), fd_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FDBG(slot) do { const long long t__ = clock64(); fd_acc[slot] += t__ - fd_t; fd_t = t__; } while (0)
+#define FDBG_DUMP(iters) do { if (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) < 32 && (threadIdx.x == 0 || threadIdx.x == 255)) { \
+    long long* o__ = g_flash_dbg + ((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 2 + (threadIdx.x != 0)) * 16; \
+    for (int i__ = 0; i__ < 8; ++i__) o__[i__] = fd_acc[i__]; o__[8] = (iters); } } while (0)
+#else
+#define FDBG_DECL
+#define FDBG(slot)
+#define FDBG_DUMP(iters)
+#endif
+
 struct Strides {
     long long bs;
     int rs;
@@ -46,40 +61,113 @@ struct FlashFwdParams {
     bf16* o;
     float* lse;
     Strides os;
-    int H, Tq, Tk, causal;
+    int B, H, Tq, Tk, causal;
+    int q_rows;        // rows [0, q_rows) of every (b, h) are produced here (whole 128-row blocks + a partial last one)
+    int nqb;           // query blocks per (b, h) = ceil(q_rows / 128)
+    int wide_store;    // output rows are 32-byte aligned: 256-bit stores
     float scale, scale_log2e;
 };
 
-// smem: Q | K0 | V0 | K1 | V1 | barriers
-__global__ void __launch_bounds__(128, 2)
+// One step of a CTA's flat sequence of (work item, key block) iterations.  A work item is one 128-row query block of one
+// (batch, head); a persistent CTA walks items  blockIdx.x, blockIdx.x + gridDim.x, ...
+struct FwdIter {
+    int n;       // ordinal of the item inside this CTA (Q slot = n & 1)
+    int item;    // global item index; < 0 = past the end
+    int j, nkb;  // key block, number of key blocks the item sees
+    int q0, h, b;
+};
+__device__ __forceinline__ void fwd_item_setup(FwdIter& it, const FlashFwdParams& p, int item, int nkb_all) {
+    it.item = item;
+    int qb, r;
+    if (p.causal) {   // heaviest query blocks first: the per-CTA item lists then end with the cheapest items
+        qb = p.nqb - 1 - item / (p.H * p.B);
+        r = item % (p.H * p.B);
+    } else {          // query blocks of one (b, h) next to each other (their K / V meet in L2)
+        qb = item % p.nqb;
+        r = item / p.nqb;
+    }
+    it.h = r % p.H;
+    it.b = r / p.H;
+    it.q0 = qb * BQ;
+    it.nkb = p.causal ? min(nkb_all, (it.q0 + BQ - 1 + (p.Tk - p.Tq)) / BK + 1) : nkb_all;
+    it.j = 0;
+}
+__device__ __forceinline__ bool fwd_advance(FwdIter& it, const FlashFwdParams& p, int num_items, int nkb_all) {
+    if (it.item < 0) return false;
+    if (++it.j < it.nkb) return true;
+    const int next = it.item + static_cast<int>(gridDim.x);
+    if (next >= num_items) {
+        it.item = -1;
+        return false;
+    }
+    ++it.n;
+    fwd_item_setup(it, p, next, nkb_all);
+    return true;
+}
+
+// Streaming attention forward, persistent and warp-specialised.  What an iteration costs is instruction issue and the
+// latency chain QK -> softmax -> PV (ncu of the first tcgen05 version: 35 % issue-active, the rest fixed-latency and
+// scoreboard waits with two warps per scheduler; phase counters of the bring-up build: profiles/r02/flash_fwd_phases.md),
+// so the loop is built to touch every score ONCE, to keep both tensor products, all issue duties and every load latency
+// off the softmax warps' critical path, and to have four softmax warps per scheduler:
+//   * persistent: 2 CTAs per SM walk the work items (128-row query block of one (b, h)); the flat sequence of
+//     (item, key block) iterations is ONE software pipeline — the next item's Q (double-buffered), K and V are in flight
+//     and its first QK product is issued while the softmax warps still normalise and store the current item's output
+//     (a non-persistent CTA spent ~3,300 clk of prologue per item against ~3,000 per iteration);
+//   * warps 0..7 = softmax: a query row is shared by two threads (warp w and w + 4 own the same 32 TMEM lanes), each
+//     holding 64 of the row's 128 scores in registers after ONE tcgen05.ld pass (max, then exp2 from the same registers);
+//     the two partial row maxima meet in shared memory under a 64-thread named barrier;
+//   * warp 8 = TMA + MMA issue (converged, one elected lane): QK(g+1) is issued as soon as the eight softmax warps have
+//     S(g) in registers (mbarrier s_free) and runs under the exponentials of iteration g; PV(g) is issued when P(g) is
+//     complete (mbarrier p_ready) and runs under the loads of iteration g+1;
+//   * O accumulates in tensor memory across key blocks (tcgen05.mma accumulate), it is NOT read out every iteration;
+//     the running maximum is only raised when it grows by more than 2^8 (a stale maximum is exact arithmetic: P and the
+//     row sum are scaled by the same factor, bounded by 256), and only then is O rescaled in tensor memory;
+//   * S, P and O have their own columns: S fp32 [0,128) | P bf16 [128,192) | O fp32 [192,256);
+//   * K and V have separate double buffers and barriers: K(g+2) is fetched once QK(g) has completed, V(g+1) once PV(g-1) has;
+//   * 32-column chunks that no row of the warp can see (causal diagonal) skip their exponentials;
+//   * the last key block may be narrower than 128 (a multiple of 16 columns: CLIP's 257th key costs one 16-wide MMA).
+// 256 TMEM columns and ~100 KB of shared memory per CTA: two CTAs per SM overlap each other's phases.
+// smem: Q0 | Q1 | K0 | K1 | V0 | V1 | row-max exchange [2][2][128] + row-sum exchange [2][128] | barriers
+constexpr int kFwdSoftmaxWarps = 8;
+// Three warpgroups: two softmax warpgroups and one whose first warp issues TMA / MMA (the other three only give their
+// registers away).  Registers are allocated per warpgroup, so 9 warps would cost 12 anyway: 2 CTAs x 384 threads leave
+// 80 registers per thread at launch; setmaxnreg moves the issue warpgroup's surplus to the softmax warpgroups
+// (2 x 128 x 104 + 128 x 32 = 384 x 80).
+constexpr int kFwdThreads = 384;
+constexpr int kFwdSoftmaxRegs = 104, kFwdIssueRegs = 32;
+constexpr int kFwdXchBytes = 4096;
+__global__ void __launch_bounds__(kFwdThreads, 2)
 flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, FlashFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sKV = smem + kTile;  // [buf][K|V]
-    uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 5 * kTile);
-    uint64_t* bar_kv = bar_q + 1;   // [2]
-    uint64_t* bar_s = bar_q + 3;
-    uint64_t* bar_o = bar_q + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
+    uint8_t* sQ = smem;               // [2]
+    uint8_t* sK = smem + 2 * kTile;   // [2]
+    uint8_t* sV = smem + 4 * kTile;   // [2]
+    float* sX = reinterpret_cast<float*>(smem + 6 * kTile);   // maxima, then sums: each [2 parities][2 halves][128 rows]
+    uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 6 * kTile + kFwdXchBytes);   // [2]
+    uint64_t* bar_k = bar_q + 2;   // [2]
+    uint64_t* bar_v = bar_q + 4;   // [2]
+    uint64_t* bar_s = bar_q + 6;        // MMA -> softmax: S(g) complete
+    uint64_t* bar_o = bar_q + 7;        // MMA -> softmax: PV(g) complete
+    uint64_t* bar_sfree = bar_q + 8;    // softmax (8 warps) -> MMA: S(g) is in registers
+    uint64_t* bar_p = bar_q + 9;        // softmax (8 warps) -> MMA: P(g) (and a rescaled O) are in tensor memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 10);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qb * BQ;
-    const int shift = p.Tk - p.Tq;
-    int nkb = (p.Tk + BK - 1) / BK;
-    if (p.causal) nkb = min(nkb, (q0 + BQ - 1 + shift) / BK + 1);
+    const int lane = threadIdx.x & 31;
+    const int num_items = p.nqb * p.H * p.B;
+    const int nkb_all = (p.Tk + BK - 1) / BK;
+    const int n_last = ((p.Tk - (nkb_all - 1) * BK) + 15) & ~15;   // columns of the last key block of the sequence
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_k);
         ptx::prefetch_tensormap(&tmap_v);
-        ptx::mbar_init(bar_q, 1);
-        ptx::mbar_init(&bar_kv[0], 1);
-        ptx::mbar_init(&bar_kv[1], 1);
-        ptx::mbar_init(bar_s, 1);
-        ptx::mbar_init(bar_o, 1);
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(bar_q + i, 1);
+        ptx::mbar_init(bar_sfree, kFwdSoftmaxWarps);
+        ptx::mbar_init(bar_p, kFwdSoftmaxWarps);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -90,134 +178,288 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tO = tmem + 128;
+    const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
 
-    auto load_kv = [&](int j) {
-        uint8_t* dst = sKV + (j & 1) * 2 * kTile;
-        ptx::mbar_arrive_expect_tx(&bar_kv[j & 1], 2 * kTile);
-        ptx::tma_load_3d(dst, &tmap_k, &bar_kv[j & 1], h * 64, j * BK, b);
-        ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[j & 1], h * 64, j * BK, b);
-    };
-    if (threadIdx.x == 0) {
-        ptx::mbar_arrive_expect_tx(bar_q, kTile);
-        ptx::tma_load_3d(sQ, &tmap_q, bar_q, h * 64, q0, b);
-        load_kv(0);
+    if (warp >= kFwdSoftmaxWarps) {
+        ptx::setmaxnreg_dec<kFwdIssueRegs>();
+    } else {
+        ptx::setmaxnreg_inc<kFwdSoftmaxRegs>();
     }
-
-    const int row = threadIdx.x, qi = q0 + row;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    int lim = p.Tk;  // keys [0, lim) visible to this row
-    if (p.causal) lim = min(p.Tk, qi + shift + 1);
-    if (lim < 1) lim = 1;
-    float m = -INFINITY, l = 0.f;
-    float o[64];
+    if (warp == kFwdSoftmaxWarps) {
+        // ===================================== TMA + MMA issue ==================================
+        const bool issuer = ptx::elect_one();
+        const uint32_t aq0 = ptx::smem_u32(sQ), ak0 = ptx::smem_u32(sK), av0 = ptx::smem_u32(sV);
+        auto load_q = [&](const FwdIter& it) {     // Q of the item `it` belongs to, into slot n & 1
+            ptx::mbar_arrive_expect_tx(&bar_q[it.n & 1], kTile);
+            ptx::tma_load_3d(sQ + (it.n & 1) * kTile, &tmap_q, &bar_q[it.n & 1], it.h * 64, it.q0, it.b);
+        };
+        auto load_k = [&](const FwdIter& it, int g) {
+            ptx::mbar_arrive_expect_tx(&bar_k[g & 1], kTile);
+            ptx::tma_load_3d(sK + (g & 1) * kTile, &tmap_k, &bar_k[g & 1], it.h * 64, it.j * BK, it.b);
+        };
+        auto load_v = [&](const FwdIter& it, int g) {
+            ptx::mbar_arrive_expect_tx(&bar_v[g & 1], kTile);
+            ptx::tma_load_3d(sV + (g & 1) * kTile, &tmap_v, &bar_v[g & 1], it.h * 64, it.j * BK, it.b);
+        };
+        auto issue_qk = [&](const FwdIter& it, int g) {   // S(g) = Q K^T, N = this block's columns
+            const int bc = (it.j == nkb_all - 1) ? n_last : BK;
+            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, bc, 0, 0);
+            const uint32_t aq = aq0 + (it.n & 1) * kTile, ak = ak0 + (g & 1) * kTile;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-
-    for (int j = 0; j < nkb; ++j) {
-        const uint32_t par = (j >> 1) & 1;
-        if (warp == 0) {   // converged warp, one elected lane issues: MMA operands stay in uniform registers
-            if (j == 0) ptx::mbar_wait(bar_q, 0);
-            ptx::mbar_wait(&bar_kv[j & 1], par);
+            for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
+            ptx::umma_commit(bar_s);
+        };
+        FwdIter cur;
+        cur.n = 0;
+        fwd_item_setup(cur, p, blockIdx.x, nkb_all);
+        FwdIter ck = cur, cv = cur, cq = cur;   // next iteration whose K / V, next item whose Q has not been requested
+        int gk = 0, gv = 0;
+        if (issuer) {
+            load_q(cq);
+            load_k(ck, gk);
+            load_v(cv, gv);
+        }
+        ++gk;
+        ++gv;
+        // second Q (the next item's), second K / V (the next iteration's)
+        {
+            const int next_item = cq.item + static_cast<int>(gridDim.x);
+            if (next_item < num_items) {
+                ++cq.n;
+                fwd_item_setup(cq, p, next_item, nkb_all);
+                if (issuer) load_q(cq);
+            } else {
+                cq.item = -1;
+            }
+        }
+        if (fwd_advance(ck, p, num_items, nkb_all)) {
+            if (issuer) load_k(ck, gk);
+            ++gk;
+        }
+        if (fwd_advance(cv, p, num_items, nkb_all)) {
+            if (issuer) load_v(cv, gv);
+            ++gv;
+        }
+        __syncwarp();
+        ptx::mbar_wait(&bar_q[0], 0);
+        ptx::mbar_wait(&bar_k[0], 0);
+        ptx::tc_fence_after_sync();
+        if (issuer) issue_qk(cur, 0);
+        __syncwarp();
+        for (int g = 0; cur.item >= 0; ++g) {
+            const int bc = (cur.j == nkb_all - 1) ? n_last : BK;
+            FwdIter nxt = cur;
+            const bool has_next = fwd_advance(nxt, p, num_items, nkb_all);
+            if (has_next) {
+                ptx::mbar_wait(bar_sfree, g & 1);                           // S(g) has been read by every softmax warp
+                ptx::mbar_wait(&bar_k[(g + 1) & 1], ((g + 1) >> 1) & 1);
+                if (nxt.j == 0) ptx::mbar_wait(&bar_q[nxt.n & 1], (nxt.n >> 1) & 1);
+                ptx::tc_fence_after_sync();
+                if (issuer) issue_qk(nxt, g + 1);
+                // QK(g) has completed (its scores were read): its K buffer — and, after an item's last block, its Q slot —
+                // are free
+                if (fwd_advance(ck, p, num_items, nkb_all)) {
+                    if (issuer) load_k(ck, gk);
+                    ++gk;
+                }
+                if (nxt.j == 0 && cq.item >= 0) {
+                    const int next_item = cq.item + static_cast<int>(gridDim.x);
+                    if (next_item < num_items) {
+                        ++cq.n;
+                        fwd_item_setup(cq, p, next_item, nkb_all);
+                        if (issuer) load_q(cq);
+                    } else {
+                        cq.item = -1;
+                    }
+                }
+                __syncwarp();
+            }
+            ptx::mbar_wait(bar_p, g & 1);                                   // P(g) written; PV(g-1) was waited for before
+            ptx::mbar_wait(&bar_v[g & 1], (g >> 1) & 1);
             ptx::tc_fence_after_sync();
-            const uint32_t aq = ptx::smem_u32(sQ), ak = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
-            if (ptx::elect_one()) {
+            if (issuer) {
+                const uint32_t av = av0 + (g & 1) * kTile;
+                constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // V [key x 64] read MN-major
+                const int ksteps = bc >> 4;
+                if (ksteps == 8) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                                      ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
-                ptx::umma_commit(bar_s);
-                if (j + 1 < nkb) load_kv(j + 1);  // the other buffer was released by the previous iteration's bar_o wait
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16_ts(tO, tP + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc,
+                                          (cur.j | k) != 0);
+                } else {
+                    for (int k = 0; k < ksteps; ++k)
+                        ptx::umma_bf16_ts(tO, tP + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc,
+                                          (cur.j | k) != 0);
+                }
+                ptx::umma_commit(bar_o);
+            }
+            // PV(g-1) completed before P(g) was written: the V buffer it read is free
+            if (g >= 1 && fwd_advance(cv, p, num_items, nkb_all)) {
+                if (issuer) load_v(cv, gv);
+                ++gv;
             }
             __syncwarp();
+            cur = nxt;
         }
-        ptx::mbar_wait(bar_s, j & 1);
-        ptx::tc_fence_after_sync();
-        const int k0 = j * BK;
-        const bool masked = (k0 + BK > __reduce_min_sync(0xffffffffu, lim));  // warp-uniform
-        // ---- row max of this block ----
-        float mj = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < BK; c += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, r);
-            ptx::tmem_ld_wait();
-            if (!masked) {
+    } else if (warp < kFwdSoftmaxWarps) {
+        // ===================================== softmax ==========================================
+        const int half = warp >> 2;                 // which 64 of the block's 128 score columns (32 of the 64 O columns)
+        const int row = ((warp & 3) << 5) + lane;   // query row inside the block = TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const uint32_t pair_bar = 1 + (warp & 3);   // named barrier of the two warps that share these rows
+        const float sl2e = p.scale_log2e;
+        const int col_h = half * 64;   // this thread's first score column inside the block
+        const int shift = p.Tk - p.Tq;
+        FDBG_DECL;
+        int g = 0;
+        FwdIter it;
+        it.n = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it.n) {
+            fwd_item_setup(it, p, item, nkb_all);
+            const int nkb = it.nkb;
+            const int qi = it.q0 + row;
+            int lim = p.Tk;  // keys [0, lim) visible to this row
+            if (p.causal) lim = min(p.Tk, qi + shift + 1);
+            if (lim < 1) lim = 1;
+            const int lim_min = __reduce_min_sync(0xffffffffu, lim), lim_max = __reduce_max_sync(0xffffffffu, lim);
+            float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+            for (int j = 0; j < nkb; ++j, ++g) {
+                const int bc = (j == nkb_all - 1) ? n_last : BK;
+                const int k0 = j * BK;
+                FDBG(7);
+                ptx::mbar_wait(bar_s, g & 1);
+                ptx::tc_fence_after_sync();
+                FDBG(0);
+                uint32_t s[64];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mj = fmaxf(mj, __uint_as_float(r[i]));
-            } else {
+                for (int c = 0; c < 2; ++c)
+                    if (col_h + c * 32 < bc)
+                        ptx::tmem_ld_32x32b_x32(tS + lane_base + col_h + c * 32,
+                                                *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_sfree);   // this warp's scores are in registers
+                FDBG(1);
+                // ---- this thread's half of the row maximum (from registers) ----
+                // masked: some (row, key) pair of this block is invisible to this warp, or the block is narrower than 128
+                const bool masked = (k0 + bc > lim_min) || (bc < BK);
+                float mj = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (k0 + c + i < lim) mj = fmaxf(mj, __uint_as_float(r[i]));
+                for (int c = 0; c < 2; ++c) {
+                    const int kc = k0 + col_h + c * 32;
+                    if (col_h + c * 32 < bc && kc < lim_max) {   // warp-uniform
+                        if (!masked) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2)
+                                mj = fmaxf(mj, fmaxf(__uint_as_float(s[c * 32 + i]), __uint_as_float(s[c * 32 + i + 1])));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (kc + i < lim) mj = fmaxf(mj, __uint_as_float(s[c * 32 + i]));
+                        }
+                    }
+                }
+                float* xch = sX + (g & 1) * 256;
+                xch[half * 128 + row] = mj;
+                ptx::named_bar_sync(pair_bar, 64);
+                FDBG(2);
+                mj = fmaxf(mj, xch[(half ^ 1) * 128 + row]);
+                const float m_new = fmaxf(m_ref, mj);
+                // raise the reference maximum only when it would grow by more than 2^8 (exact: P and the sum share the factor)
+                const bool raise = (m_new - m_ref) * sl2e > 8.0f;   // -inf -> finite: true; -inf -> -inf: NaN, false
+                FDBG(3);
+                if (j > 0) {   // PV(g-1) must be complete before P is overwritten or O is rescaled
+                    ptx::mbar_wait(bar_o, (g - 1) & 1);
+                    ptx::tc_fence_after_sync();
+                }
+                if (__any_sync(0xffffffffu, raise)) {
+                    const float corr = raise ? (m_ref == -INFINITY ? 0.f : ex2f((m_ref - m_new) * sl2e)) : 1.0f;
+                    l0 *= corr;
+                    l1 *= corr;
+                    if (raise) m_ref = m_new;
+                    if (j > 0) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_32x32b_x32(tO + lane_base + half * 32, r);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+                        ptx::tmem_st_32x32b_x32(tO + lane_base + half * 32, r);
+                    }
+                }
+                FDBG(4);
+                const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * sl2e;
+                // ---- probabilities (bf16) -> their own tensor-memory columns ----
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int kc = k0 + col_h + c * 32;
+                    if (col_h + c * 32 < bc) {
+                        uint32_t pk[16];
+                        if (kc < lim_max) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float x0, x1;
+                                ptx::ffma2_bcast(x0, x1, __uint_as_float(s[c * 32 + 2 * i]),
+                                                 __uint_as_float(s[c * 32 + 2 * i + 1]), sl2e, -mb);
+                                float e0 = ex2f(x0), e1 = ex2f(x1);
+                                if (masked) {
+                                    if (kc + 2 * i >= lim) e0 = 0.f;
+                                    if (kc + 2 * i + 1 >= lim) e1 = 0.f;
+                                }
+                                ptx::fadd2_acc(l0, l1, e0, e1);
+                                const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+                                pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            }
+                        } else {   // no row of this warp sees these 32 keys (causal diagonal)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                        }
+                        ptx::tmem_st_32x32b_x16(tP + lane_base + (col_h >> 1) + c * 16, pk);
+                    }
+                }
+                FDBG(5);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_p);   // this warp's part of P(g) (and of a rescaled O) is in tensor memory
+                FDBG(6);
             }
-        }
-        const float m_new = fmaxf(m, mj);
-        // rows that see nothing in this block keep their state (m_new may still be -inf for early causal rows)
-        const float mb = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2e;
-        const float corr = (m == -INFINITY) ? 0.f : ex2f(m * p.scale_log2e - mb);
-        float lj = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BK; c += 32) {
+            // ---- the item's output: O / row sum.  The two halves of the row sum meet in shared memory. ----
+            float* xs = sX + 512 + (it.n & 1) * 256;
+            xs[half * 128 + row] = l0 + l1;
+            ptx::mbar_wait(bar_o, (g - 1) & 1);
+            ptx::tc_fence_after_sync();
             uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, r);
+            ptx::tmem_ld_32x32b_x32(tO + lane_base + half * 32, r);
+            ptx::named_bar_sync(pair_bar, 64);
+            const float l = (l0 + l1) + xs[(half ^ 1) * 128 + row];
             ptx::tmem_ld_wait();
+            const float inv = l > 0.f ? 1.0f / l : 0.f;
+            bf16* orow = p.o + it.b * p.os.bs + static_cast<size_t>(qi) * p.os.rs + it.h * 64 + half * 32;
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                float e0 = ex2f(fmaf(__uint_as_float(r[2 * i]), p.scale_log2e, -mb));
-                float e1 = ex2f(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2e, -mb));
-                if (masked) {
-                    if (k0 + c + 2 * i >= lim) e0 = 0.f;
-                    if (k0 + c + 2 * i + 1 >= lim) e1 = 0.f;
-                }
-                lj += e0 + e1;
-                const bf162 h2 = __floats2bfloat162_rn(e0, e1);
+                const bf162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
                 pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
             }
-            ptx::tmem_st_32x32b_x16(tS + lane_base + (c >> 1), pk);
-        }
-        l = l * corr + lj;
-        m = m_new;
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {
-            ptx::tc_fence_after_sync();
-            const uint32_t av = ptx::smem_u32(sKV + (j & 1) * 2 * kTile + kTile);
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
-            if (ptx::elect_one()) {
+            if (qi < p.q_rows) {
+                if (p.wide_store) {
+                    ptx::stg_v8(orow, pk);
+                    ptx::stg_v8(orow + 16, pk + 8);
+                } else {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    ptx::umma_bf16_ts(tO, tS + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc, k != 0);
-                ptx::umma_commit(bar_o);
+                    for (int q = 0; q < 4; ++q)
+                        stg16(orow + q * 8, make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+                }
+                if (half == 0 && p.lse != nullptr)
+                    p.lse[(static_cast<size_t>(it.b) * p.H + it.h) * p.Tq + qi] = m_ref * p.scale + __logf(l);
             }
-            __syncwarp();
+            FDBG(7);
         }
-        ptx::mbar_wait(bar_o, j & 1);
-        ptx::tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tO + lane_base + c, r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], corr, __uint_as_float(r[i]));
-        }
-        ptx::tc_fence_before_sync();  // S / O columns are rewritten by the next iteration's MMAs
-        __syncthreads();
-    }
-    if (qi < p.Tq) {
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        bf16* orow = p.o + b * p.os.bs + static_cast<size_t>(qi) * p.os.rs + h * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 8) {
-            float t[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = o[c + i] * inv;
-            stg16(orow + c, pack8(t));
-        }
-        if (p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m * p.scale + __logf(l);
+        FDBG_DUMP(g);
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
@@ -661,19 +903,20 @@ int tmap_rows128(CUtensorMap* map, const void* base, int W, int T, int B, int rs
     return VLK_OK;
 }
 
-constexpr int kFwdSmem = 5 * kTile + 128 + 1024;
+constexpr int kFwdSmem = 6 * kTile + kFwdXchBytes + 128 + 1024;
 constexpr int kBwdSmem = 6 * kTile + 2 * 256 * 4 + 128 + 1024;
 
 }  // namespace
 
 int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H, int Tq, int Tk,
                    long long q_bs, int q_rs, long long k_bs, int k_rs, long long v_bs, int v_rs, long long o_bs,
-                   int o_rs, int causal, float scale, cudaStream_t stream) {
+                   int o_rs, int causal, float scale, cudaStream_t stream, int q_rows) {
     static bool configured = false;
     if (!configured) {
         VLK_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
         configured = true;
     }
+    if (q_rows <= 0 || q_rows > Tq) q_rows = Tq;
     CUtensorMap tq, tk, tv;
     int rc = tmap_rows128(&tq, q, H * 64, Tq, B, q_rs, q_bs);
     if (rc) return rc;
@@ -685,13 +928,21 @@ int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* 
     p.o = static_cast<bf16*>(o);
     p.lse = lse;
     p.os = Strides{o_bs, o_rs};
+    p.B = B;
     p.H = H;
     p.Tq = Tq;
     p.Tk = Tk;
     p.causal = causal;
+    p.q_rows = q_rows;
+    p.nqb = (q_rows + BQ - 1) / BQ;
+    p.wide_store = (reinterpret_cast<uintptr_t>(o) & 31u) == 0 && o_rs % 16 == 0 && o_bs % 16 == 0;
     p.scale = scale;
     p.scale_log2e = scale * 1.4426950408889634f;
-    flash_fwd_kernel<<<dim3((Tq + BQ - 1) / BQ, H, B), 128, kFwdSmem, stream>>>(tq, tk, tv, p);
+    const int sms = device_sm_count();
+    VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
+    const long long items = static_cast<long long>(p.nqb) * H * B;
+    const int grid = static_cast<int>(items < 2LL * sms ? items : 2LL * sms);   // persistent: two CTAs per SM
+    flash_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, stream>>>(tq, tk, tv, p);
     VLK_CHECK_LAUNCH("vlk_attn_fwd(flash)");
     return VLK_OK;
 }
@@ -744,3 +995,10 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
 }
 
 }  // namespace vlk
+
+#ifdef VLK_BRINGUP
+extern "C" int vlk_debug_flash_dump(long long* host_out, int n) {
+    if (n > 64 * 16) n = 64 * 16;
+    return static_cast<int>(cudaMemcpyFromSymbol(host_out, vlk::g_flash_dbg, sizeof(long long) * n));
+}
+#endif
