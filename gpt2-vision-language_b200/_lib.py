@@ -32,11 +32,14 @@ SIGNATURES = {
     "vlk_gemm_bf16_stats": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_int, c_void_p, c_void_p],
     "vlk_colsum_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "vlk_colsum_bf16_acc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "vlk_transpose_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "vlk_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                           c_void_p],
     "vlk_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_int, c_int, c_int, c_void_p],
+    "vlk_layernorm_bwd_acc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "vlk_sum_copies": [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
     "vlk_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                      c_ll, c_int, c_ll, c_int, c_ll, c_int, c_ll, c_int, c_int, c_float,

@@ -7,8 +7,6 @@
 //   Tq < 64 against Tk > 64          attention_simt.cu     CUDA-core forward (KV-cached decode rows)
 //
 // The map is a pure function of the shapes: no environment switches, no alternative implementations in the library.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace vlk {
@@ -66,7 +64,7 @@ extern "C" int vlk_attn_fwd(const void* q, const void* k, const void* v, void* o
     if (small)
         return attn_pair_fwd(q, k, v, o, lse, B, H, Tq, Tk, q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs, causal, scale,
                              dropout_p, seed_state, stream_id, s);
-    if (Tk > kMidMaxKeys || (Tq >= 64 && Tk > 64 && getenv("VLK_MID_FLASH") != nullptr)) {
+    if (Tk > kMidMaxKeys) {
         // whole 128-row query blocks on the tensor cores; a remainder of <= 8 rows (CLIP's 257th token) would waste a
         // 128-row tile per (batch, head): those rows go to the CUDA-core few-rows kernel
         const int tail = Tq % 128;

@@ -250,8 +250,11 @@ __global__ void clip_assemble_kernel(const bf16* __restrict__ patch, const bf16*
 // (26 us for 25 MB).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kColsumGroups = 32;
+// grad_out != nullptr: `out` is a zeroed fp32 workspace; the last of the gridDim.y blocks of a 256-column group (counters,
+// one zeroed uint32 per group) ADDS the finished sums into the bf16 gradient and zeroes workspace and counter again.
 __global__ void __launch_bounds__(1024) colsum_kernel(const bf16* __restrict__ X, float* __restrict__ out, int rows,
-                                                      int cols, int ldx) {
+                                                      int cols, int ldx, bf16* __restrict__ grad_out,
+                                                      unsigned int* __restrict__ counters) {
     __shared__ float red[kColsumGroups][32 * 8 + 1];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     const int col = (blockIdx.x * 32 + lane) * 8;
@@ -289,6 +292,23 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const bf16* __restrict__ X
         for (int w = 0; w < kColsumGroups / 4; ++w) s += red[part * (kColsumGroups / 4) + w][c];
         const int gc = blockIdx.x * 256 + c;
         if (gc < cols) atomicAdd(out + gc, s);
+    }
+    if (grad_out != nullptr) {
+        __shared__ int is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1;
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const int gc = blockIdx.x * 256 + threadIdx.x;
+            if (threadIdx.x < 256 && gc < cols) {
+                const float v = __ldcg(out + gc);
+                out[gc] = 0.f;
+                grad_out[gc] = __float2bfloat16(v + __bfloat162float(grad_out[gc]));
+            }
+            if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
+        }
     }
 }
 
@@ -549,8 +569,22 @@ extern "C" int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, in
     int gy = (rows + 255) / 256;     // at least 8 rows per thread ...
     if (gy > 32) gy = 32;            // ... and at most 32 (x4) same-address atomics per column
     if (gy < 1) gy = 1;
-    colsum_kernel<<<dim3(gx, gy), 1024, 0, s>>>(static_cast<const bf16*>(X), out, rows, cols, ldx);
+    colsum_kernel<<<dim3(gx, gy), 1024, 0, s>>>(static_cast<const bf16*>(X), out, rows, cols, ldx, nullptr, nullptr);
     VLK_CHECK_LAUNCH("vlk_colsum_bf16");
+    return VLK_OK;
+}
+
+extern "C" int vlk_colsum_bf16_acc(const void* X, float* workspace, unsigned int* counters, void* grad, int rows, int cols,
+                                   int ldx, void* stream) {
+    VLK_REQUIRE(X && workspace && counters && grad && rows > 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0,
+                VLK_ERR_INVALID_ARG, "vlk_colsum_bf16_acc: rows=%d cols=%d ldx=%d", rows, cols, ldx);
+    const int gx = (cols + 255) / 256;
+    int gy = (rows + 255) / 256;
+    if (gy > 32) gy = 32;
+    if (gy < 1) gy = 1;
+    colsum_kernel<<<dim3(gx, gy), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(X), workspace, rows, cols, ldx, static_cast<bf16*>(grad), counters);
+    VLK_CHECK_LAUNCH("vlk_colsum_bf16_acc");
     return VLK_OK;
 }
 

@@ -200,11 +200,21 @@ def sum_copies(src, copies, n, dst, accumulate=False, clear_src=False):
 def bias_grad(dy2, bias):
     """Bias gradient of nn.Linear = column sums of dy.  Accumulated straight into ``bias.grad`` when possible (returns
     None), else returned as a bf16 tensor."""
-    s32 = colsum(dy2)
     g = grad_slot(bias)
     if g is not None:
+        cols = dy2.shape[1]
+        ws = persistent_workspace(("colsum_ws", dy2.device.index),
+                                  lambda: (torch.zeros(65536, device=dy2.device, dtype=torch.float32),
+                                           torch.zeros(256, device=dy2.device, dtype=torch.int32)))
+        if ws is not None and cols <= 65536 and dy2.dtype == BF16 and dy2.stride(1) == 1:
+            # one launch: the last block of each column group adds the sums into bias.grad and re-zeroes the workspace
+            check(_lib.load().vlk_colsum_bf16_acc(dy2.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), g.data_ptr(),
+                                                  dy2.shape[0], cols, dy2.stride(0), _stream()), "vlk_colsum_bf16_acc")
+            return None
+        s32 = colsum(dy2)
         sum_copies(s32, 1, s32.numel(), g, accumulate=True)
         return None
+    s32 = colsum(dy2)
     out = torch.empty(s32.numel(), device=s32.device, dtype=BF16)
     sum_copies(s32, 1, s32.numel(), out)
     return out
@@ -326,6 +336,16 @@ def layernorm_bwd(dy2d, x2d, weight, mean, rstd, param_grads=False, dx=None, acc
         persistent = acc is not None
         if acc is None:
             acc = torch.zeros((2, LN_GRAD_COPIES, cols), device=x2d.device, dtype=torch.float32)
+        gw, gb = grad_slot(weight), grad_slot(bias) if bias is not None else None
+        counter = persistent_workspace(("ln_counter", x2d.device.index),
+                                       lambda: torch.zeros(1, device=x2d.device, dtype=torch.int32))
+        if persistent and counter is not None and gw is not None and gb is not None:
+            # one launch: the last block folds the replicas into weight.grad / bias.grad and re-zeroes the workspace
+            check(lib.vlk_layernorm_bwd_acc(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(),
+                                            rstd.data_ptr(), dx.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(), rows, cols,
+                                            int(accumulate), LN_GRAD_COPIES, gw.data_ptr(), gb.data_ptr(),
+                                            counter.data_ptr(), _stream()), "vlk_layernorm_bwd_acc")
+            return dx, None, None
     check(lib.vlk_layernorm_bwd(dy2d.data_ptr(), x2d.data_ptr(), weight.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                 dx.data_ptr(), _p(acc), acc[1].data_ptr() if acc is not None else 0, rows, cols,
                                 int(accumulate), LN_GRAD_COPIES, _stream()), "vlk_layernorm_bwd")

@@ -112,6 +112,11 @@ int vlk_gemm_bf16_stats(const void* A, const void* B, void* D, int M, int N, int
 
 /* out[n] (fp32, overwritten) = sum_m X[m,n]; used for bias gradients (autograd of nn.Linear). */
 int vlk_colsum_bf16(const void* X, float* out, int rows, int cols, int ldx, void* stream);
+/* grad[n] (bf16) += sum_m X[m,n] in ONE launch (autograd's AccumulateGrad of nn.Linear.bias, train_gpt2.py:458-469):
+ * `workspace` (>= cols fp32) and `counters` (>= ceil(cols / 256) uint32) must be zero on entry and are zero again on
+ * exit — the last block of every 256-column group folds the sums into `grad`. */
+int vlk_colsum_bf16_acc(const void* X, float* workspace, unsigned int* counters, void* grad, int rows, int cols, int ldx,
+                        void* stream);
 
 /* dst[c, r] = src[r, c] for bf16 matrices (ld in elements). */
 int vlk_transpose_bf16(const void* src, void* dst, int rows, int cols, int ld_src, int ld_dst, void* stream);
@@ -130,6 +135,13 @@ int vlk_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
 int vlk_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                       void* dx, float* dgamma, float* dbeta, int rows, int cols, int dx_accum, int grad_copies,
                       void* stream);
+/* vlk_layernorm_bwd with the parameter gradients ADDED into the parameters' bf16 gradients (autograd's
+ * AccumulateGrad for nn.LayerNorm.weight / .bias, train_gpt2.py:458-469) by the same launch: the blocks accumulate into
+ * `grad_copies` zeroed fp32 replicas dgamma_ws / dbeta_ws [grad_copies][cols]; the block that finishes last (counter,
+ * one zeroed uint32) folds them into dgamma_grad / dbeta_grad and leaves replicas and counter zeroed again. */
+int vlk_layernorm_bwd_acc(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                          void* dx, float* dgamma_ws, float* dbeta_ws, int rows, int cols, int dx_accum, int grad_copies,
+                          void* dgamma_grad, void* dbeta_grad, unsigned int* counter, void* stream);
 /* dst[i] = (accumulate ? dst[i] : 0) + sum_c src[c*n + i], written as fp32 (dst_bf16 == 0) or bf16.  accumulate adds
  * into an existing gradient (p.grad += g of autograd's AccumulateGrad, without the extra kernel); clear_src zeroes
  * the replicas after reading them, so a persistent accumulator workspace is clean for its next user. */
