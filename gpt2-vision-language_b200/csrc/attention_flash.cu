@@ -38,11 +38,12 @@ __device__ __forceinline__ float ex2f(float x) {
 // bring-up instrumentation (never compiled into the shipped library): cycles per phase of the forward loop, summed over
 // the iterations of a CTA, by thread 0 and thread 255; read back by vlk_debug_flash_dump
 __device__ long long g_flash_dbg[64 * 16];
-#define FDBG_DECL long long fd_t = clock64(), fd_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FDBG_DECL long long fd_t = clock64(), fd_t0 = fd_t, fd_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define FDBG(slot) do { const long long t__ = clock64(); fd_acc[slot] += t__ - fd_t; fd_t = t__; } while (0)
 #define FDBG_DUMP(iters) do { if (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) < 32 && (threadIdx.x == 0 || threadIdx.x == 255)) { \
     long long* o__ = g_flash_dbg + ((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 2 + (threadIdx.x != 0)) * 16; \
-    for (int i__ = 0; i__ < 8; ++i__) o__[i__] = fd_acc[i__]; o__[8] = (iters); } } while (0)
+    for (int i__ = 0; i__ < 8; ++i__) o__[i__] = fd_acc[i__]; o__[8] = (iters); o__[9] = clock64() - fd_t0; \
+    long long gt__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__)); o__[10] = gt__; } } while (0)
 #else
 #define FDBG_DECL
 #define FDBG(slot)

@@ -260,9 +260,11 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         const int ksteps = n_main / 16;
         int prev_g = -1, prev_s = 0, prev_last = 0;
         uint32_t prev_kvpar = 0;
+        auto pv_ready = [&]() {   // warp-uniform: the previous tile's probabilities are complete
+            return __all_sync(0xffffffffu, ptx::mbar_try_wait(&p_ready[prev_g], (prev_g ? cnt_o1 : cnt_o0) & 1));
+        };
         auto issue_pv = [&]() {
-            // P.V of the previous tile, once its probabilities are complete
-            ptx::mbar_wait(&p_ready[prev_g], (prev_g ? cnt_o1 : cnt_o0) & 1);
+            // P.V of the previous tile (its probabilities are complete)
             const uint32_t sv = ptx::smem_u32(smem + prev_s * k4KVStage) + 34 * 1024;
             ptx::mbar_wait(&vfull[prev_s], prev_kvpar);
             ptx::tc_fence_after_sync();
@@ -293,27 +295,42 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             for (int qb = 0; qb < nqb; ++qb) {
                 const int g = qb & 1;
                 const uint32_t par = (g ? cnt_s1 : cnt_s0) & 1;
-                ptx::mbar_wait(&q_full[g], par);
-                ptx::mbar_wait(&s_free[g], par ^ 1);
-                ptx::tc_fence_after_sync();
                 const uint32_t sq = ptx::smem_u32(smem + k4OffQ + g * 16 * 1024);
-                if (issuer) {
+                // Two things are pending: the scores of this tile (needs its Q and the group's free TMEM slot) and the
+                // P.V of the previous tile (needs its probabilities).  Whichever becomes possible first is issued first
+                // — with the cheap issue path a P.V no longer delays the next scores noticeably, while waiting for the
+                // other group's slot before issuing a finished tile's P.V cost 4-5 us per tile (phase stamps).
+                bool s_done = false, pv_done = prev_g < 0;
+                while (!s_done || !pv_done) {
+                    if (!s_done && __all_sync(0xffffffffu, ptx::mbar_try_wait(&q_full[g], par) &&
+                                                               ptx::mbar_try_wait(&s_free[g], par ^ 1))) {
+                        ptx::tc_fence_after_sync();
+                        if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ptx::umma_bf16_ss(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
-                                          ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
-                    ptx::umma_commit(&s_ready[g]);
+                            for (int k = 0; k < 4; ++k)
+                                ptx::umma_bf16_ss(tmem + g * 256, ptx::make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                                                  ptx::make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0);
+                            ptx::umma_commit(&s_ready[g]);
+                        }
+                        __syncwarp();
+                        if (g) ++cnt_s1; else ++cnt_s0;
+                        s_done = true;
+                    }
+                    if (!pv_done && pv_ready()) {
+                        issue_pv();
+                        pv_done = true;
+                    }
                 }
-                __syncwarp();
-                if (g) ++cnt_s1; else ++cnt_s0;
-                if (prev_g >= 0) issue_pv();
                 prev_g = g;
                 prev_s = s;
                 prev_kvpar = kvpar;
                 prev_last = (qb == nqb - 1);
             }
         }
-        if (prev_g >= 0) issue_pv();  // drain: the last tile's P.V
+        if (prev_g >= 0) {  // drain: the last tile's P.V
+            ptx::mbar_wait(&p_ready[prev_g], (prev_g ? cnt_o1 : cnt_o0) & 1);
+            issue_pv();
+        }
     } else if (warp >= 4) {
         // ===================================== softmax / epilogue groups ========================
         const int g = (warp - 4) >> 2;

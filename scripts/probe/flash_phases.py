@@ -32,4 +32,5 @@ for cta in range(0, 32, 3):
         r = [buf[(cta * 2 + t) * 16 + i] for i in range(9)]
         it = max(r[8], 1)
         print(f"cta {cta:2d} thread {'0  ' if t == 0 else '255'} iters {it}: " + "  ".join(f"{x / it:7.0f}" for x in r[:8]) +
-              f"   | total/iter {sum(r[:8]) / it:7.0f} clk")
+              f"   | total/iter {sum(r[:8]) / it:7.0f} clk | softmax loop lifetime {buf[(cta * 2 + t) * 16 + 9]} clk, end stamp "
+              f"{(buf[(cta * 2 + t) * 16 + 10] - min(buf[(c * 2) * 16 + 10] for c in range(32))) / 1e3:.1f} us after the first CTA's end")
