@@ -444,10 +444,12 @@ def run_pretrain(args, torch, dist, dev, world, rank, local, peaks, steps, warmu
             th.join(timeout=2)
         # roofline of the GEMMs: an instrumented eager micro-step (run twice: the first pass warms the allocator)
         with GemmRecorder(torch) as rec:
-            for _ in range(2):
+            for i in range(2):
                 rec.records.clear()
                 step.bucket.zero()
                 step._set_slot(0)
+                if i == 1:
+                    torch.cuda._sleep(int(4e8))   # the host enqueues the pass while the GPU is parked (see gemm_roofline)
                 step._micro()
             torch.cuda.synchronize()
         records = [(a, b, 2.0 * m * n * k) for a, b, (m, n, k), _ in rec.records]
@@ -531,8 +533,13 @@ def gemm_roofline(torch, step, peaks):
     is for the DOMINANT kernel = the GEMM launch shape with the largest total time in the step (CLIP fc1,
     16448 x 4096 x 1024 with bias + quick-GELU at B=64); the aggregate over all GEMM launches is reported beside it."""
     with GemmRecorder(torch) as rec:
-        for _ in range(2):           # the first pass warms the allocator: an allocation inside a timed window is host time
+        for i in range(2):           # the first pass warms the allocator: an allocation inside a timed window is host time
             rec.records.clear()
+            if i == 1:
+                # Park the GPU behind a spin kernel while the host enqueues the whole pass: the events then bracket GPU
+                # time only.  (Without it the host — Python, ctypes, two cuTensorMapEncode per product — is slower than
+                # the GPU on this path and its latency lands inside the event windows: the 117 us fc1 product read 134 us.)
+                torch.cuda._sleep(int(4e8))
             step._fwd_bwd()          # rank-local: no collective here (only rank 0 runs this pass)
             step._update()
         torch.cuda.synchronize()
@@ -568,7 +575,11 @@ def gemm_roofline(torch, step, peaks):
             "share_of_step_gemm_time": dms / tot_ms, "frac_of_nominal_2250": achieved / 2250.0, "traffic": traffic,
             "all_gemms": {"launches_per_step": len(records), "gemm_ms_per_step": tot_ms,
                           "achieved": tot_fl / (tot_ms * 1e-3) / 1e12, "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak,
-                          "algorithmic_tflop": tot_fl / 1e12}}
+                          "algorithmic_tflop": tot_fl / 1e12},
+            # every launch shape of the step, largest share of the GEMM time first (eager pass, CUDA events per launch)
+            "by_shape": [{"M": m, "N": n, "K": k, "kind": kind, "launches": cnt, "avg_us": ms_ / cnt * 1e3,
+                          "tflops": 2.0 * m * n * k / (ms_ / cnt * 1e-3) / 1e12, "share": ms_ / tot_ms}
+                         for ((m, n, k), kind), (cnt, ms_) in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:16]]}
 
 
 def stage(msg):
