@@ -96,32 +96,36 @@ __device__ __forceinline__ const uint8_t* kv_row(const uint8_t* main_tile, int j
 
 // One query row against all keys of the unit, by the 128 threads of a softmax group (CUDA cores).
 __device__ __forceinline__ void tail_row(const Fwd4Params& p, const uint8_t* st, float* scr, int g, int b, int h, int qi,
-                                         int gt /* thread index inside the group */) {
+                                         int gt /* thread index inside the group */, uint32_t dbg_tile = 0) {
     float* qx = scr;            // [64]   scaled query
     float* sp = scr + 64;       // [288]  scores -> probabilities
     float* red = scr + 352;     // [8]
     float* part = scr + 360;    // [4][64]
     const int lane = gt & 31, w = gt >> 5;
     const int lim = p.causal ? min(p.Tk, qi + (p.Tk - p.Tq) + 1) : p.Tk;
+    dbg4(p.debug, gt == 0, g, dbg_tile, 9);
     if (gt < 64) qx[gt] = __bfloat162float(p.q[b * p.q_bs + static_cast<size_t>(qi) * p.q_rs + h * 64 + gt]) * p.scale;
     ptx::named_bar_sync(1 + g, 128);
+    dbg4(p.debug, gt == 0, g, dbg_tile, 10);
     float m = -INFINITY;
     for (int j = gt; j < lim; j += 128) {
         const uint8_t* kr = kv_row(st, j);
-        float acc = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains (one chain of 64 FMAs is 256 clk of latency)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             float kf[8];
             unpack8(*reinterpret_cast<const uint4*>(kr + ((c ^ (j & 7)) << 4)), kf);
             const float4 q0 = *reinterpret_cast<const float4*>(qx + c * 8);
             const float4 q1 = *reinterpret_cast<const float4*>(qx + c * 8 + 4);
-            acc = fmaf(q0.x, kf[0], acc); acc = fmaf(q0.y, kf[1], acc); acc = fmaf(q0.z, kf[2], acc);
-            acc = fmaf(q0.w, kf[3], acc); acc = fmaf(q1.x, kf[4], acc); acc = fmaf(q1.y, kf[5], acc);
-            acc = fmaf(q1.z, kf[6], acc); acc = fmaf(q1.w, kf[7], acc);
+            a0 = fmaf(q0.x, kf[0], a0); a1 = fmaf(q0.y, kf[1], a1); a2 = fmaf(q0.z, kf[2], a2);
+            a3 = fmaf(q0.w, kf[3], a3); a0 = fmaf(q1.x, kf[4], a0); a1 = fmaf(q1.y, kf[5], a1);
+            a2 = fmaf(q1.z, kf[6], a2); a3 = fmaf(q1.w, kf[7], a3);
         }
+        const float acc = (a0 + a1) + (a2 + a3);
         sp[j] = acc;
         m = fmaxf(m, acc);
     }
+    dbg4(p.debug, gt == 0, g, dbg_tile, 11);
     m = warp_max(m);
     if (lane == 0) red[w] = m;
     ptx::named_bar_sync(1 + g, 128);
@@ -136,17 +140,38 @@ __device__ __forceinline__ void tail_row(const Fwd4Params& p, const uint8_t* st,
     if (lane == 0) red[4 + w] = sum;
     ptx::named_bar_sync(1 + g, 128);
     sum = red[4] + red[5] + red[6] + red[7];
+    dbg4(p.debug, gt == 0, g, dbg_tile, 12);
     // O[d]: warp w walks keys j = w, w+4, ...; lane owns dims 2*lane, 2*lane+1 (conflict-free swizzled reads)
     float a0 = 0.f, a1 = 0.f;
     const uint8_t* vt = st + 34 * 1024;
-    for (int j = w; j < lim; j += 4) {
-        const uint8_t* vr = kv_row(vt, j);
-        const uint32_t word = *reinterpret_cast<const uint32_t*>(vr + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4);
-        const float2 v2 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&word));
-        const float pj = sp[j];
-        a0 = fmaf(pj, v2.x, a0);
-        a1 = fmaf(pj, v2.y, a1);
+    {
+        // four keys per round with independent loads and accumulators (the serial loop was 65 dependent
+        // address -> load -> FMA steps per warp)
+        float b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+        auto vword = [&](int j) {
+            const uint8_t* vr = kv_row(vt, j);
+            const uint32_t word = *reinterpret_cast<const uint32_t*>(vr + (((lane >> 2) ^ (j & 7)) << 4) + (lane & 3) * 4);
+            return __bfloat1622float2(*reinterpret_cast<const bf162*>(&word));
+        };
+        int j = w;
+        for (; j + 12 < lim; j += 16) {
+            const float2 v0 = vword(j), v1 = vword(j + 4), v2 = vword(j + 8), v3 = vword(j + 12);
+            const float p0 = sp[j], p1 = sp[j + 4], p2 = sp[j + 8], p3 = sp[j + 12];
+            a0 = fmaf(p0, v0.x, a0); a1 = fmaf(p0, v0.y, a1);
+            b0 = fmaf(p1, v1.x, b0); b1 = fmaf(p1, v1.y, b1);
+            c0 = fmaf(p2, v2.x, c0); c1 = fmaf(p2, v2.y, c1);
+            d0 = fmaf(p3, v3.x, d0); d1 = fmaf(p3, v3.y, d1);
+        }
+        for (; j < lim; j += 4) {
+            const float2 v2 = vword(j);
+            const float pj = sp[j];
+            a0 = fmaf(pj, v2.x, a0);
+            a1 = fmaf(pj, v2.y, a1);
+        }
+        a0 = (a0 + b0) + (c0 + d0);
+        a1 = (a1 + b1) + (c1 + d1);
     }
+    dbg4(p.debug, gt == 0, g, dbg_tile, 13);
     part[w * 64 + 2 * lane] = a0;
     part[w * 64 + 2 * lane + 1] = a1;
     ptx::named_bar_sync(1 + g, 128);
@@ -163,6 +188,7 @@ __device__ __forceinline__ void tail_row(const Fwd4Params& p, const uint8_t* st,
         if (gt == 0 && p.lse != nullptr) p.lse[(static_cast<size_t>(b) * p.H + h) * p.Tq + qi] = m + __logf(sum);
     }
     ptx::named_bar_sync(1 + g, 128);  // scratch may be reused
+    dbg4(p.debug, gt == 0, g, dbg_tile, 14);
 }
 
 __global__ void __launch_bounds__(384, 1)
@@ -472,7 +498,7 @@ attn_fwd_tcgen05_v4_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
                     ptx::mbar_wait(&vfull[s], kvpar);
                     float* scr = reinterpret_cast<float*>(smem + k4OffTail) + g * k4TailFloats;
                     for (int tr = 0; tr < p.tail_rows; ++tr)
-                        tail_row(p, st, scr, g, b, h, nqb * 128 + tr, threadIdx.x & 127);
+                        tail_row(p, st, scr, g, b, h, nqb * 128 + tr, threadIdx.x & 127, cnt);
                 }
                 ptx::mbar_wait(&o_ready[g], par);
                 if (n_extra > 0) ptx::mbar_wait(&vfull[s], kvpar);

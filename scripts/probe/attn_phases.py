@@ -25,6 +25,6 @@ names = ["0 tile start", "1 extra key done", "2 s_ready seen", "3 pass1+max exch
 t0 = min(x for x in buf if x > 0)
 for g in range(2):
     for tile in range(4):
-        st = [buf[(g * 4 + tile) * 16 + s] for s in range(9)]
+        st = [buf[(g * 4 + tile) * 16 + s] for s in range(15)]
         print(f"group {g} tile {tile + 2}: " + "  ".join(f"{(x - t0) / 1e3:7.2f}" for x in st) + "   (us since first stamp)")
-print("phases:", " | ".join(names))
+print("phases:", " | ".join(names), "| 9-14 leftover row: start, q staged, scores, max+exp+sum, P.V, done")
