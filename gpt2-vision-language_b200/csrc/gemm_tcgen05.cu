@@ -27,6 +27,7 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kColVecBytes = 128 * 4 + 128 * 2;   // per epilogue warp: the folded-LayerNorm column sums and the bias of its columns
 
 struct EpiParams {
     const bf16* bias;
@@ -96,7 +97,8 @@ struct SmemLayout {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kColVecOffset = kStages * kStageBytes;   // kNumEpiWarps x (128 fp32 colsum + 128 bf16 bias)
+    static constexpr int kBarOffset = kColVecOffset + kNumEpiWarps * kColVecBytes;
     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
     static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024B alignment
@@ -285,6 +287,33 @@ __device__ __forceinline__ const bf16* epi_staged_input(const EpiParams& ep, int
 // core's operand reads and the TMA writes already load to the limit, frees 64 KB for two more pipeline stages, and
 // produces the pre-activation copy (aux_out) in the same pass.
 // ------------------------------------------------------------------------------------------------
+// Packed (f32x2: FFMA2 / FMUL2 / FADD2) forms of the forward activations for a pair of values: the epilogue warps are
+// latency-bound at two warps per scheduler (IPC 0.15-0.27 per scheduler under ncu), so what shortens a tile's epilogue
+// is fewer instructions per element, not a faster pipe.
+__device__ __forceinline__ void act_apply2(int act, float& x0, float& x1) {
+    if (act == VLK_ACT_GELU_TANH) {   // 0.5 x (1 + tanh(k0 (x + k1 x^3))) = x (0.5 tanh(x (k0 + k0 k1 x^2)) + 0.5)
+        constexpr float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+        float s0, s1, w0, w1;
+        ptx::fmul2(s0, s1, x0, x1, x0, x1);
+        ptx::ffma2(w0, w1, s0, s1, k01, k01, k0, k0);
+        ptx::fmul2(w0, w1, w0, w1, x0, x1);
+        w0 = tanh_fast(w0);
+        w1 = tanh_fast(w1);
+        ptx::ffma2(w0, w1, w0, w1, 0.5f, 0.5f, 0.5f, 0.5f);
+        ptx::fmul2(x0, x1, x0, x1, w0, w1);
+    } else if (act == VLK_ACT_QUICK_GELU) {   // x sigmoid(1.702 x) = x (0.5 tanh(0.851 x) + 0.5)
+        float w0, w1;
+        ptx::fmul2(w0, w1, x0, x1, 0.851f, 0.851f);
+        w0 = tanh_fast(w0);
+        w1 = tanh_fast(w1);
+        ptx::ffma2(w0, w1, w0, w1, 0.5f, 0.5f, 0.5f, 0.5f);
+        ptx::fmul2(x0, x1, x0, x1, w0, w1);
+    } else if (act != VLK_ACT_NONE) {
+        x0 = act_apply(act, x0);
+        x1 = act_apply(act, x1);
+    }
+}
+
 struct EpiPre {
     uint32_t r[16];  // 32 bf16 of this thread's row
 };
@@ -321,6 +350,45 @@ __device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&r)[16]) 
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const bf162*>(&u)); }
 
+// The column vectors of the warp's tile columns (bias; column sums of a folded LayerNorm) are staged in shared memory
+// BEFORE the accumulator wait, one coalesced load per warp and tile.  Read with __ldg inside the chunk loop they were
+// the epilogue's critical path: every 32-column chunk waited a full L2 round trip for them (ncu: 43 % of the kernel's
+// stall samples were long-scoreboard waits on their first use) and the MMA warp waited 30-45 % of its time for a free
+// accumulator on every K <= 1024 product.
+struct ColVec {
+    const float* colsum;   // [ncols_warp] fp32 (valid when the launch folds a LayerNorm)
+    const bf16* bias;      // [ncols_warp] bf16 (valid when the launch has a bias)
+    float ln_mu, ln_rs;    // this thread's row statistics of a folded LayerNorm (fetched under the MMAs as well)
+};
+__device__ __forceinline__ ColVec stage_colvec(const EpiParams& ep, uint8_t* buf, int row, int M, int n0, int ncols_warp,
+                                               int N, int lane) {
+    float* cs = reinterpret_cast<float*>(buf);
+    bf16* bs = reinterpret_cast<bf16*>(buf + 128 * 4);
+    float ln_mu = 0.f, ln_rs = 1.f;
+    if (ep.ln_colsum != nullptr && row < M) {
+        if (ep.ln_sums != nullptr) {
+            const float2 s12 = __ldg(reinterpret_cast<const float2*>(ep.ln_sums) + row);
+            ln_mu = s12.x * ep.ln_inv_k;
+            ln_rs = rsqrtf(fmaxf(s12.y * ep.ln_inv_k - ln_mu * ln_mu, 0.f) + ep.ln_eps);
+        } else {
+            ln_mu = __ldg(ep.ln_mean + row);
+            ln_rs = __ldg(ep.ln_rstd + row);
+        }
+    }
+    __syncwarp();   // the previous tile's readers are done
+    for (int c = lane * 4; c < ncols_warp; c += 128) {
+        const bool ok = n0 + c < N;   // N % 8 == 0 and c % 4 == 0: a group of four never straddles N
+        if (ep.ln_colsum != nullptr)
+            *reinterpret_cast<float4*>(cs + c) =
+                ok ? __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias != nullptr)
+            *reinterpret_cast<uint2*>(bs + c) =
+                ok ? __ldg(reinterpret_cast<const uint2*>(ep.bias + n0 + c)) : make_uint2(0u, 0u);
+    }
+    __syncwarp();
+    return ColVec{cs, bs, ln_mu, ln_rs};
+}
+
 // The first chunk of the staged input, fetched BEFORE the accumulator wait (the warp is idle while its tile's MMAs run).
 __device__ __forceinline__ void epilogue_prefetch_direct(const EpiParams& ep, EpiPre& pre, int row0, int n0, int M, int N,
                                                          int lane) {
@@ -333,8 +401,8 @@ __device__ __forceinline__ void epilogue_prefetch_direct(const EpiParams& ep, Ep
 }
 
 template <int ACT, int DACT, int RES, int SCALE, int AUX, int LNF, int STATS = 0, int CE = 0>
-__device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& pre, uint32_t taddr, int row0, int n0,
-                                                  int ncols_warp, int M, int N, int lane) {
+__device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& pre, const ColVec& cv, uint32_t taddr,
+                                                  int row0, int n0, int ncols_warp, int M, int N, int lane) {
     const int row = row0 + lane;
     const bool row_ok = row < M;
     const int act = ACT < 0 ? ep.act : ACT;
@@ -345,17 +413,7 @@ __device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& p
     const bool ln_fold = LNF < 0 ? (ep.ln_colsum != nullptr) : (LNF != 0);
     const bool stats = STATS < 0 ? (ep.stats_out != nullptr) : (STATS != 0);
     const bool wide = ep.wide_io != 0;
-    float ln_mu = 0.f, ln_rs = 1.f;
-    if (ln_fold && row_ok) {
-        if (ep.ln_sums != nullptr) {
-            const float2 s12 = __ldg(reinterpret_cast<const float2*>(ep.ln_sums) + row);
-            ln_mu = s12.x * ep.ln_inv_k;
-            ln_rs = rsqrtf(fmaxf(s12.y * ep.ln_inv_k - ln_mu * ln_mu, 0.f) + ep.ln_eps);
-        } else {
-            ln_mu = __ldg(ep.ln_mean + row);
-            ln_rs = __ldg(ep.ln_rstd + row);
-        }
-    }
+    const float ln_mu = cv.ln_mu, ln_rs = cv.ln_rs;
     float st1 = 0.f, st2 = 0.f;
     const bool aux_direct = dact && has_res;  // both present: the residual is the prefetched stream, aux_in is read in place
     const float scale = has_scale ? __ldg(ep.scale) : 1.0f;
@@ -376,19 +434,25 @@ __device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& p
         if (VLK_DBG_LDTM_ONLY(ep)) continue;
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * ep.alpha;
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (ep.alpha != 1.0f) {   // uniform
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) ptx::fmul2(v[i], v[i + 1], v[i], v[i + 1], ep.alpha, ep.alpha);
+        }
         if (CE != 0) {
             if (row_ok) ce_grad32(ep, v, row, col0);
         }
-        if (ln_fold) {
+        if (ln_fold) {   // v = rstd (v - mean colsum) = v rstd + colsum (-rstd mean)
+            const float nrm = -ln_rs * ln_mu;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 if (q * 4 < ncols) {
-                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0) + q);
-                    v[q * 4 + 0] = ln_rs * (v[q * 4 + 0] - ln_mu * c4.x);
-                    v[q * 4 + 1] = ln_rs * (v[q * 4 + 1] - ln_mu * c4.y);
-                    v[q * 4 + 2] = ln_rs * (v[q * 4 + 2] - ln_mu * c4.z);
-                    v[q * 4 + 3] = ln_rs * (v[q * 4 + 3] - ln_mu * c4.w);
+                    const float4 c4 = *reinterpret_cast<const float4*>(cv.colsum + c + q * 4);   // broadcast read
+                    float t0, t1, t2, t3;
+                    ptx::fmul2(t0, t1, c4.x, c4.y, nrm, nrm);
+                    ptx::fmul2(t2, t3, c4.z, c4.w, nrm, nrm);
+                    ptx::ffma2(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 0], v[q * 4 + 1], ln_rs, ln_rs, t0, t1);
+                    ptx::ffma2(v[q * 4 + 2], v[q * 4 + 3], v[q * 4 + 2], v[q * 4 + 3], ln_rs, ln_rs, t2, t3);
                 }
             }
         }
@@ -396,10 +460,12 @@ __device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& p
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (q * 8 < ncols) {
-                    float b[8];
-                    unpack8(ldg16(ep.bias + col0 + q * 8), b);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[q * 8 + i] += b[i];
+                    const uint4 bq = *reinterpret_cast<const uint4*>(cv.bias + c + q * 8);   // broadcast read
+                    const float2 b0 = unpack2(bq.x), b1 = unpack2(bq.y), b2 = unpack2(bq.z), b3 = unpack2(bq.w);
+                    ptx::fadd2(v[q * 8 + 0], v[q * 8 + 1], v[q * 8 + 0], v[q * 8 + 1], b0.x, b0.y);
+                    ptx::fadd2(v[q * 8 + 2], v[q * 8 + 3], v[q * 8 + 2], v[q * 8 + 3], b1.x, b1.y);
+                    ptx::fadd2(v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 4], v[q * 8 + 5], b2.x, b2.y);
+                    ptx::fadd2(v[q * 8 + 6], v[q * 8 + 7], v[q * 8 + 6], v[q * 8 + 7], b3.x, b3.y);
                 }
             }
         }
@@ -430,18 +496,17 @@ __device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& p
             }
         } else if (act != VLK_ACT_NONE) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_apply(act, v[i]);
+            for (int i = 0; i < 32; i += 2) act_apply2(act, v[i], v[i + 1]);
         }
         if (has_scale) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= scale;
+            for (int i = 0; i < 32; i += 2) ptx::fmul2(v[i], v[i + 1], v[i], v[i + 1], scale, scale);
         }
         if (has_res) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float2 t = unpack2(pre.r[i]);
-                v[2 * i] += t.x;
-                v[2 * i + 1] += t.y;
+                ptx::fadd2(v[2 * i], v[2 * i + 1], v[2 * i], v[2 * i + 1], t.x, t.y);
             }
         }
         pack32(v, pk);
@@ -469,8 +534,9 @@ __device__ __forceinline__ void epilogue_direct_t(const EpiParams& ep, EpiPre& p
 }
 
 template <bool SPECIALISE>
-__device__ __forceinline__ void epilogue_warp_direct(const EpiParams& ep, EpiPre& pre, uint32_t taddr, int row0, int n0,
-                                                     int ncols_warp, int M, int N, int lane, size_t d_off = 0) {
+__device__ __forceinline__ void epilogue_warp_direct(const EpiParams& ep, EpiPre& pre, const ColVec& cv, uint32_t taddr,
+                                                     int row0, int n0, int ncols_warp, int M, int N, int lane,
+                                                     size_t d_off = 0) {
     if (VLK_DBG_SKIP_EPILOGUE(ep)) return;
     if (ep.ce_mode == 1) {
         ce_stats_warp(ep, taddr, row0, n0, ncols_warp, M, N, lane);
@@ -490,19 +556,19 @@ __device__ __forceinline__ void epilogue_warp_direct(const EpiParams& ep, EpiPre
         return;
     }
 #define VLK_EPI(ACT, DACT, RES, SCALE, AUX) \
-    epilogue_direct_t<ACT, DACT, RES, SCALE, AUX, 0>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane)
-#define VLK_EPI_LN(ACT) epilogue_direct_t<ACT, 0, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane)
+    epilogue_direct_t<ACT, DACT, RES, SCALE, AUX, 0>(ep, pre, cv, taddr, row0, n0, ncols_warp, M, N, lane)
+#define VLK_EPI_LN(ACT) epilogue_direct_t<ACT, 0, 0, 0, 0, 1>(ep, pre, cv, taddr, row0, n0, ncols_warp, M, N, lane)
     const bool res = ep.residual != nullptr, sc = ep.scale != nullptr, aux = ep.aux_out != nullptr;
     if (ep.ce_mode == 2) {   // d logits of a vocabulary chunk
-        epilogue_direct_t<0, 0, 0, 0, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
+        epilogue_direct_t<0, 0, 0, 0, 0, 0, 0, 1>(ep, pre, cv, taddr, row0, n0, ncols_warp, M, N, lane);
         return;
     }
     if constexpr (!SPECIALISE) {
-        epilogue_direct_t<-1, -1, -1, -1, -1, -1, -1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
+        epilogue_direct_t<-1, -1, -1, -1, -1, -1, -1>(ep, pre, cv, taddr, row0, n0, ncols_warp, M, N, lane);
         return;
     }
     if (ep.stats_out != nullptr) {  // residual GEMM that also produces the row statistics of its output
-        epilogue_direct_t<0, 0, -1, 0, 0, 0, 1>(ep, pre, taddr, row0, n0, ncols_warp, M, N, lane);
+        epilogue_direct_t<0, 0, -1, 0, 0, 0, 1>(ep, pre, cv, taddr, row0, n0, ncols_warp, M, N, lane);
     } else if (ep.ln_colsum != nullptr) {   // LayerNorm folded into the weights: plain / quick-GELU / tanh-GELU bodies
         if (ep.act == VLK_ACT_QUICK_GELU) VLK_EPI_LN(VLK_ACT_QUICK_GELU);
         else if (ep.act == VLK_ACT_GELU_TANH) VLK_EPI_LN(VLK_ACT_GELU_TANH);
@@ -725,9 +791,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             EpiPre pre;
             epilogue_prefetch_direct(ep, pre, row0, n0, M, N, lane);
+            const ColVec cv = stage_colvec(ep, smem + L::kColVecOffset + (warp_idx - kEpiWarp0) * kColVecBytes, row0 + lane, M,
+                                           n0, kColsPerWarp, N, lane);
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tc_fence_after_sync();
-            epilogue_warp_direct<false>(ep, pre, taddr, row0, n0, kColsPerWarp, M, N, lane,
+            epilogue_warp_direct<false>(ep, pre, cv, taddr, row0, n0, kColsPerWarp, M, N, lane,
                                         static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles));
             // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
             ptx::tc_fence_before_sync();
@@ -764,7 +832,8 @@ struct SmemLayout2 {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kColVecOffset = kStages * kStageBytes;
+    static constexpr int kBarOffset = kColVecOffset + kNumEpiWarps * kColVecBytes;
     static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
     static constexpr int kDynamic = kTotal + 1024;
 };
@@ -940,9 +1009,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerWarp;
             EpiPre pre;
             VLK_DBG_TIMED(c_pre, epilogue_prefetch_direct(ep, pre, row0, n0, M, N, lane));
+            const ColVec cv = stage_colvec(ep, smem + L::kColVecOffset + (warp_idx - kEpiWarp0) * kColVecBytes, row0 + lane, M,
+                                           n0, kColsPerWarp, N, lane);
             VLK_DBG_TIMED(c_wait, ptx::mbar_wait(&tmem_full_bar[acc], acc_phase));
             ptx::tc_fence_after_sync();
-            VLK_DBG_TIMED(c_work, epilogue_warp_direct<(BLOCK_N == 256)>(ep, pre, taddr, row0, n0, kColsPerWarp, M, N, lane,
+            VLK_DBG_TIMED(c_work, epilogue_warp_direct<(BLOCK_N == 256)>(ep, pre, cv, taddr, row0, n0, kColsPerWarp, M, N, lane,
                           static_cast<size_t>(ep.split_stride) * (tile / num_out_tiles)));
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -1107,7 +1178,7 @@ template <bool A_MN, bool B_MN>
 int dispatch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int sms, int bn,
              int cluster, cudaStream_t stream) {
     if (cluster == 3) {  // cta_group::2 pair
-        if (bn == 256) return launch_2cta<256, 7, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
+        if (bn == 256) return launch_2cta<256, 6, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
         return launch_2cta<128, 8, A_MN, B_MN>(ta, tb, M, N, K, ep, sms, stream);
     }
 #ifdef VLK_GEMM_MULTICAST_VARIANT   // single-CTA MMA with TMA multicast of B across a CTA pair: measured, never the

@@ -397,6 +397,18 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, 
         : "=f"(d0), "=f"(d1)
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// packed product
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}\n"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // {d0, d1} += {a0, a1}
 __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
     asm("{\n\t"
