@@ -13,7 +13,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gpt2_vision_language_b200 import ops, optim  # noqa: E402
+from gpt2_vision_language_b200 import _lib, ops, optim  # noqa: E402
+if os.environ.get("VLK_ZOO_LIB"):      # A/B of two library builds on the same box
+    _lib.LIB_PATH = os.path.abspath(os.environ["VLK_ZOO_LIB"])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--once", action="store_true")
