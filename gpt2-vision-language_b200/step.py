@@ -109,8 +109,11 @@ class CaptionTrainStep:
                  use_graph=True, pixels_dtype=torch.float32, group=None, overlap_comm=None, nccl_in_graph=None):
         """kind: 'linear' | 'qformer' (GPT_Caption(patch_tokens, input_ids, labels)) or 'xattn'
         (GPT(idx, z, targets, target_mask)).
-        overlap_comm (xattn only; default: on when data parallel): backward is cut in the middle of the stack and
-        the all-reduce of the upper layers' gradients runs on a second stream UNDER the lower half of backward.
+        overlap_comm (xattn only; default OFF): backward is cut in the middle of the stack and the all-reduce of the
+        upper layers' gradients runs on a second stream UNDER the lower half of backward.  Measured on one box
+        (profiles/r01_dp2_*, profiles/r02/overlap_ab_n4.md): 58 MB exchanged, 6,866 vs 6,919 samples/s at 2 GPUs and
+        16,162 vs 16,212 at 4 — the extra graph boundary costs what the overlap hides, so the single exchange after
+        backward is the default and the split path stays available (and tested) for larger rings.
         (Linear / Q-Former bridge gradients all materialise at the very end of backward: nothing to overlap.)"""
         assert kind in ("linear", "qformer", "xattn")
         self.model, self.clip, self.kind, self.group = model, clip_tower, kind, group
@@ -129,9 +132,7 @@ class CaptionTrainStep:
         self.graph = None
         self._warm = 0
         self.nccl_in_graph = _nccl_in_graph_default() if nccl_in_graph is None else bool(nccl_in_graph)
-        if overlap_comm is None:
-            overlap_comm = self._multi()
-        self.overlap = bool(overlap_comm) and kind == "xattn"
+        self.overlap = bool(overlap_comm) and kind == "xattn"   # None = default = off
         if self.overlap:
             self.split = len(model.transformer.h) // 2
             self.upper = _upper_range(self.bucket, model.transformer.h, self.split)
