@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -38,16 +39,23 @@ __device__ __forceinline__ float ex2f(float x) {
 // bring-up instrumentation (never compiled into the shipped library): cycles per phase of the forward loop, summed over
 // the iterations of a CTA, by thread 0 and thread 255; read back by vlk_debug_flash_dump
 __device__ long long g_flash_dbg[64 * 16];
-#define FDBG_DECL long long fd_t = clock64(), fd_t0 = fd_t, fd_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FDBG_DECL long long fd_t = clock64(), fd_t0 = fd_t, fd_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define FDBG(slot) do { const long long t__ = clock64(); fd_acc[slot] += t__ - fd_t; fd_t = t__; } while (0)
 #define FDBG_DUMP(iters) do { if (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) < 32 && (threadIdx.x == 0 || threadIdx.x == 255)) { \
     long long* o__ = g_flash_dbg + ((blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 2 + (threadIdx.x != 0)) * 16; \
     for (int i__ = 0; i__ < 8; ++i__) o__[i__] = fd_acc[i__]; o__[8] = (iters); o__[9] = clock64() - fd_t0; \
     long long gt__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__)); o__[10] = gt__; } } while (0)
+// backward kernel A: record r of (thread == tid) lands in row 3 * cta + r
+#define FDBG_DUMP_ROW(iters, tid, r) do { if (blockIdx.x < 20 && threadIdx.x == (tid)) { \
+    long long* o__ = g_flash_dbg + (blockIdx.x * 3 + (r)) * 16; \
+    for (int i__ = 0; i__ < 8; ++i__) o__[i__] = fd_acc[i__]; o__[8] = (iters); o__[9] = clock64() - fd_t0; \
+    for (int i__ = 8; i__ < 12; ++i__) o__[i__ + 3] = fd_acc[i__]; \
+    long long gt__; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__)); o__[10] = gt__; } } while (0)
 #else
 #define FDBG_DECL
 #define FDBG(slot)
 #define FDBG_DUMP(iters)
+#define FDBG_DUMP_ROW(iters, tid, r)
 #endif
 
 struct Strides {
@@ -506,215 +514,422 @@ struct FlashBwdParams {
     float scale, scale_log2e;
 };
 
-// ---- kernel A: dK_j, dV_j.  smem: K | V | (Q,dO) x 2 | lse/delta x 2 | barriers ----
-// TMEM: 256 columns (two CTAs per SM): S^T [0,128) -> P^T bf16 in [0,64), this query block's dV contribution in
-// [64,128); dP^T [128,256) -> dS^T bf16 in [128,192), dK contribution in [192,256).  The contributions are added to
-// register accumulators each iteration (the next iteration's S^T / dP^T overwrite all 256 columns).
-__global__ void __launch_bounds__(128, 2)
+// ---- kernel A: dK_j, dV_j — persistent, warp-specialised, TWO 64-query sub-blocks in flight (one CTA per SM) ----
+// Work item = one 128-key block of one (batch, head); the CTA walks the 64-query sub-blocks that see it.  Everything is
+// computed TRANSPOSED so that the TMEM-resident operand is always the A operand (thread = key row = TMEM lane):
+//     S^T = K Q_u^T,  dP^T = V dO_u^T   ->  P^T = exp2(S^T * scale*log2e - lse_u*log2e),  dS^T = P^T (dP^T - delta_u)
+//     dV += P^T dO_u,  dK += dS^T Q_u     (accumulated IN tensor memory over the sub-blocks, read out once per item)
+// TMEM (all 512 columns), slot s = sub-iteration parity:  S^T [128 s, +64) | dP^T [128 s + 64, +64) | P^T bf16
+// [256 + 64 s, +32) | dS^T bf16 [288 + 64 s, +32) | dV fp32 [384, 448) | dK fp32 [448, 512).
+//   * two softmax groups of eight warps, group g owns slot g: a key row is shared by two threads of the group (32 query
+//     columns each), ONE tcgen05.ld pass over S^T and dP^T, probabilities and score gradients go back as bf16.  The two
+//     groups are half an iteration out of phase, so one group's tcgen05.ld / barrier / statistics latencies run under the
+//     other group's exponentials — a single group of sixteen warps (all waiting on the same barriers) and the two-CTA
+//     kernel with per-iteration read-out both measured 138-140 us (profiles/r02/r02_notes.md);
+//   * warp 16 (converged, one elected lane issues): when P^T / dS^T of sub-iteration G are complete (p_ready[slot]) it
+//     issues their gradient products and, right behind them, the scores of G+2 into the same slot;
+//   * Q / dO sub-tiles in a ring of four, K / V in a ring of four items (the load cursor runs three sub-iterations ahead).
+constexpr int BQS = 64;                   // queries per sub-block
+constexpr int kSubTile = BQS * 128;       // bytes of a 64-row x 64-col bf16 tile
+struct BwdIter {
+    int n, item;      // ordinal of the (non-empty) item inside this CTA (K/V slot = n % 4), global item index (< 0: end)
+    int u, u0, nsub;  // 64-query sub-block, first sub-block that sees the key block, sub-blocks of the sequence
+    int k0, h, b;
+};
+__device__ __forceinline__ void bwd_item_setup(BwdIter& it, const FlashBwdParams& p, int item, int B) {
+    it.item = item;
+    const int hb = p.H * B;
+    const int kb = item / hb, r = item % hb;   // key block 0 sees the most query blocks: heaviest items first
+    it.h = r % p.H;
+    it.b = r / p.H;
+    it.k0 = kb * BK;
+    // whole 128-query blocks, i.e. an EVEN number of sub-blocks per item (a sub-block past the sequence or below the
+    // causal diagonal is masked to zero): every item starts in slot 0, both groups do the same number of sub-iterations,
+    // and an item never has fewer than two — which the K / V ring of three relies on
+    it.nsub = 2 * ((p.Tq + 2 * BQS - 1) / (2 * BQS));
+    it.u0 = p.causal ? 2 * (max(0, it.k0 - (p.Tk - p.Tq)) / (2 * BQS)) : 0;
+    it.u = it.u0;
+}
+__device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p, int num_items, int B) {
+    if (it.item < 0) return false;
+    if (++it.u < it.nsub) return true;
+    for (int next = it.item + static_cast<int>(gridDim.x); next < num_items; next += gridDim.x) {
+        bwd_item_setup(it, p, next, B);
+        if (it.u0 < it.nsub) {   // (items no query sees are handled by the softmax warps alone and are not counted)
+            ++it.n;
+            return true;
+        }
+    }
+    it.item = -1;
+    return false;
+}
+
+constexpr int kDkvSoftmaxWarps = 16;                       // two groups of eight
+constexpr int kDkvThreads = (kDkvSoftmaxWarps + 4) * 32;   // + the issue warpgroup (one active warp)
+constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 64 <= 640 x 96
+// smem: (K, V) x 3 | (Q, dO) sub-tiles x 6 | statistics [2 groups][2][128] | barriers
+constexpr int kNKV = 3, kNQ = 6;   // K / V ring (items), Q / dO ring (sub-blocks)
+constexpr int kDkvOffQ = kNKV * 2 * kTile, kDkvOffStat = kDkvOffQ + kNQ * 2 * kSubTile, kDkvOffBar = kDkvOffStat + 2 * 2 * 128 * 4;
+constexpr int kDkvSmem = kDkvOffBar + 256 + 1024;
+
+__global__ void __launch_bounds__(kDkvThreads, 1)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                     FlashBwdParams p) {
+                     FlashBwdParams p, int B) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;
-    uint8_t* sV = smem + kTile;
-    uint8_t* sQdO = smem + 2 * kTile;  // [buf][Q|dO]
-    float* sStat = reinterpret_cast<float*>(smem + 6 * kTile);  // [buf][lse(128) | delta(128)]
-    uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + 6 * kTile + 2 * 256 * 4);
-    uint64_t* bar_q = bar_kv + 1;  // [2]
-    uint64_t* bar_s = bar_kv + 3;
-    uint64_t* bar_acc = bar_kv + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
+    uint8_t* sKV = smem;                    // [kNKV][K | V]
+    uint8_t* sQdO = smem + kDkvOffQ;        // [kNQ][Q | dO], 64 rows each
+    float* sStat = reinterpret_cast<float*>(smem + kDkvOffStat);
+    uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kDkvOffBar);   // [kNKV] TMA -> MMA
+    uint64_t* bar_q = bar_kv + kNKV;           // [kNQ] TMA -> MMA
+    uint64_t* bar_s = bar_q + kNQ;             // [2] MMA -> group: S^T, dP^T of the slot complete
+    uint64_t* bar_acc = bar_s + 2;             // [2] MMA -> group / issue warp: the gradient products of the slot have retired
+    uint64_t* bar_p = bar_acc + 2;             // [2] group (8 warps) -> MMA: P^T, dS^T of the slot are in tensor memory
+    uint64_t* bar_sfree = bar_p + 2;           // [2] group (8 warps) -> MMA: S^T, dP^T of the slot are in registers
+    uint64_t* bar_done = bar_sfree + 2;        // all 16 warps -> MMA: dV / dK of the finished item have been read out
+    uint64_t* bar_item = bar_done + 1;         // MMA -> all 16 warps: every gradient product of the item has retired (one phase
+                                               // per item, waited for by both groups in order: a group never polls the OTHER
+                                               // slot's bar_acc, whose phase it does not track)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_item + 1);
 
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
-    const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int k0 = kb * BK;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int nkb = (p.Tk + BK - 1) / BK;
+    const int num_items = nkb * p.H * B;
     const int shift = p.Tk - p.Tq;
-    const int nqb = (p.Tq + BQ - 1) / BQ;
-    int qb0 = 0;  // first query block that sees this key block (causal: query i sees key j iff j <= i + shift)
-    if (p.causal) qb0 = max(0, k0 - shift) / BQ;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_k);
         ptx::prefetch_tensormap(&tmap_v);
         ptx::prefetch_tensormap(&tmap_do);
-        ptx::mbar_init(bar_kv, 1);
-        ptx::mbar_init(&bar_q[0], 1);
-        ptx::mbar_init(&bar_q[1], 1);
-        ptx::mbar_init(bar_s, 1);
-        ptx::mbar_init(bar_acc, 1);
+        for (int i = 0; i < kNKV + kNQ + 4; ++i) ptx::mbar_init(bar_kv + i, 1);
+        ptx::mbar_init(bar_item, 1);
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(bar_p + i, kDkvSoftmaxWarps / 2);   // bar_p[2], bar_sfree[2]
+        ptx::mbar_init(bar_done, kDkvSoftmaxWarps);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 64, tDK = tmem + 192;
-    float acc_dv[64], acc_dk[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) {
-        acc_dv[i] = 0.f;
-        acc_dk[i] = 0.f;
-    }
+    const uint32_t tDV = tmem + 384, tDK = tmem + 448;
 
-    auto load_q = [&](int i) {
-        const int buf = (i - qb0) & 1;
-        uint8_t* dst = sQdO + buf * 2 * kTile;
-        ptx::mbar_arrive_expect_tx(&bar_q[buf], 2 * kTile);
-        ptx::tma_load_3d(dst, &tmap_q, &bar_q[buf], h * 64, i * BQ, b);
-        ptx::tma_load_3d(dst + kTile, &tmap_do, &bar_q[buf], h * 64, i * BQ, b);
-    };
-    if (threadIdx.x == 0) {
-        ptx::mbar_arrive_expect_tx(bar_kv, 2 * kTile);
-        ptx::tma_load_3d(sK, &tmap_k, bar_kv, h * 64, k0, b);
-        ptx::tma_load_3d(sV, &tmap_v, bar_kv, h * 64, k0, b);
-        if (qb0 < nqb) load_q(qb0);
+    if (warp >= kDkvSoftmaxWarps) {
+        ptx::setmaxnreg_dec<kDkvIssueRegs>();
+    } else {
+        ptx::setmaxnreg_inc<kDkvSoftmaxRegs>();
     }
-    const int row = threadIdx.x, kj = k0 + row;  // this thread's key
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const size_t stat_base = (static_cast<size_t>(b) * p.H + h) * p.Tq;
-
-    // per-column statistics of a query block (lse pre-multiplied by log2e for exp2): this thread stages query `row` of
-    // the block.  They are fetched ONE ITERATION AHEAD (ncu: the loads of the current block, issued right before the
-    // barrier that publishes them, were 13 % of the kernel's stall samples).
-    float nx_lse = 0.f, nx_delta = 0.f;
-    auto fetch_stats = [&](int i) {
-        const int qi = i * BQ + row;
-        nx_lse = qi < p.Tq ? p.lse[stat_base + qi] : INFINITY;   // p -> 0 for padded rows
-        nx_delta = qi < p.Tq ? p.delta[stat_base + qi] : 0.f;
-    };
-    if (qb0 < nqb) fetch_stats(qb0);
-    for (int i = qb0; i < nqb; ++i) {
-        const int it = i - qb0, buf = it & 1;
-        const uint32_t par = (it >> 1) & 1;
-        const int qs = i * BQ;
-        float* st = sStat + buf * 256;
-        st[row] = nx_lse * 1.4426950408889634f;
-        st[128 + row] = nx_delta;
-        if (i + 1 < nqb) fetch_stats(i + 1);   // in flight under this iteration
-        if (warp == 0) {   // converged warp, one elected lane issues
-            if (it == 0) ptx::mbar_wait(bar_kv, 0);
-            ptx::mbar_wait(&bar_q[buf], par);
-            ptx::tc_fence_after_sync();
-            const uint32_t ak = ptx::smem_u32(sK), av = ptx::smem_u32(sV);
-            const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQ, 0, 0);
-            if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {  // S^T = K Q^T ; dP^T = V dO^T
-                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024),
-                                      ptx::make_smem_desc_sw128(bq + k * 32, 16, 1024), idesc, k != 0);
-                    ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(av + k * 32, 16, 1024),
-                                      ptx::make_smem_desc_sw128(bdo + k * 32, 16, 1024), idesc, k != 0);
-                }
-                ptx::umma_commit(bar_s);
-                if (i + 1 < nqb) load_q(i + 1);  // other buffer: its last readers (dV/dK MMAs) were waited on via bar_acc
-            }
-            __syncwarp();
+    if (warp == kDkvSoftmaxWarps) {
+        // ===================================== TMA + MMA issue ==================================
+        // ONE cursor (the load cursor, three sub-iterations ahead of the products) and a shift register of packed
+        // per-sub-iteration facts, one call site per operation: the kernel's code has to stay inside the 32 KB
+        // instruction cache level (the first version of this loop, with three cursors and unrolled prologues, made the
+        // kernel 48 KB and every cold path — item read-out, item setup — paid instruction fetches from L2).
+        const bool issuer = ptx::elect_one();
+        const uint32_t akv0 = ptx::smem_u32(sKV), aq0 = ptx::smem_u32(sQdO);
+        const uint64_t dKV0 = ptx::make_smem_desc_sw128(akv0, 16, 1024);     // K / V rows, K-major A operand
+        const uint64_t dQ0 = ptx::make_smem_desc_sw128(aq0, 16, 1024);       // Q / dO rows, K-major B operand (scores)
+        const uint64_t dQmn0 = ptx::make_smem_desc_sw128(aq0, 8192, 1024);   // the same tiles read MN-major (products)
+        constexpr uint32_t kMValid = 1u << 6, kMFirst = 1u << 3, kMLast = 1u << 4, kMNz = 1u << 5;
+        BwdIter cq;
+        cq.n = 0;
+        cq.item = -1;
+        for (int first = blockIdx.x; first < num_items; first += gridDim.x) {   // first item some query sees
+            bwd_item_setup(cq, p, first, B);
+            if (cq.u0 < cq.nsub) break;
+            cq.item = -1;
         }
-        __syncthreads();  // sStat visible
-        ptx::mbar_wait(bar_s, it & 1);
-        ptx::tc_fence_after_sync();
-        const bool diag = p.causal && (qs < kj + 128 - shift);  // some (key, query) pairs of this block are masked
+        // Iteration G of the loop: (B) the gradient products of G - 1 once its P^T / dS^T are written, (A) the scores of
+        // G + 2 once S^T / dP^T of G (same slot) are in the group's registers — long before the group has finished its
+        // exponentials, so the next scores are ready when it comes back —, (C) the loads of G + 4.  B precedes A: a group
+        // arrives on bar_sfree of a new item's first sub-iteration only after the previous item's read-out, which waits
+        // for products that B issues.
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;   // facts of sub-iterations G-1 .. G+4
+        int retired = -1;   // the products of every sub-iteration <= retired are known complete (bar_acc phases, in order)
+        FDBG_DECL;
+        int Gend = 0;
 #pragma unroll 1
-        for (int c = 0; c < BQ; c += 32) {
-            uint32_t rs[32], rp[32];
-            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, rs);
-            ptx::tmem_ld_32x32b_x32(tDP + lane_base + c, rp);
-            ptx::tmem_ld_wait();
-            uint32_t pk[16], dk[16];
+        for (int G = -4;; ++G) {
+            m0 = m1;
+            m1 = m2;
+            m2 = m3;
+            m3 = m4;
+            m4 = m5;
+            m5 = 0;
+            FDBG(7);
+            // ---- (B) gradient products of G - 1: dV += P^T dO, dK += dS^T Q ----
+            if (G >= 1) {
+                if (!(m0 & kMValid)) break;
+                const int Gp = G - 1, slot = Gp & 1;
+                ptx::mbar_wait(&bar_p[slot], (Gp >> 1) & 1);
+                FDBG(0);
+                if ((m0 & (kMFirst | kMNz)) == (kMFirst | kMNz))     // the previous item's dV / dK have been read out
+                    ptx::mbar_wait(bar_done, ((m0 >> 7) & 1) ^ 1);   // parity of item n - 1
+                FDBG(1);
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t bdq = dQmn0 + static_cast<uint32_t>(((Gp % kNQ) * 2 * kSubTile) >> 4);
+                    const uint64_t bdo = bdq + (kSubTile >> 4);
+                    const uint32_t tP = tmem + 256 + slot * 64, tDS = tP + 32;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // B = [query x 64] read MN-major
+                    const uint32_t acc = (m0 & kMFirst) ? 0u : 1u;
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                float pv[2], dv[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int col = c + 2 * t + u;  // query index within the block
-                    float pr = ex2f(fmaf(__uint_as_float(rs[2 * t + u]), p.scale_log2e, -st[col]));
-                    if (diag && (qs + col + shift < kj)) pr = 0.f;   // causal: query sees key iff key <= query + shift
-                    if (kj >= p.Tk) pr = 0.f;
-                    pv[u] = pr;
-                    dv[u] = pr * (__uint_as_float(rp[2 * t + u]) - st[128 + col]);
+                    for (int kk = 0; kk < BQS / 16; ++kk) {
+                        ptx::umma_bf16_ts(tDV, tP + kk * 8, bdo + kk * (2048 >> 4), idesc, (acc | kk) != 0);
+                        ptx::umma_bf16_ts(tDK, tDS + kk * 8, bdq + kk * (2048 >> 4), idesc, (acc | kk) != 0);
+                    }
+                    ptx::umma_commit(&bar_acc[slot]);
+                    if (m0 & kMLast) ptx::umma_commit(bar_item);   // the item's last sub-iteration
                 }
-                const bf162 hp = __floats2bfloat162_rn(pv[0], pv[1]);
-                const bf162 hd = __floats2bfloat162_rn(dv[0], dv[1]);
-                pk[t] = *reinterpret_cast<const uint32_t*>(&hp);
-                dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+                __syncwarp();
+                Gend = G;
             }
-            ptx::tmem_st_32x32b_x16(tS + lane_base + (c >> 1), pk);    // P^T in place
-            ptx::tmem_st_32x32b_x16(tDP + lane_base + (c >> 1), dk);   // dS^T in place
+            FDBG(4);
+            // ---- (A) scores of G + 2 into the slot of G: S^T = K Q^T, dP^T = V dO^T ----
+            if (G >= -2 && (m3 & kMValid)) {
+                const int G2 = G + 2, kvs = m3 & 3;
+                if (G >= 0) ptx::mbar_wait(&bar_sfree[G & 1], (G >> 1) & 1);
+                FDBG(2);
+                ptx::mbar_wait(&bar_q[G2 % kNQ], (G2 / kNQ) & 1);
+                ptx::mbar_wait(&bar_kv[kvs], (m3 >> 2) & 1);
+                FDBG(6);
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t ak = dKV0 + static_cast<uint32_t>((kvs * 2 * kTile) >> 4), av = ak + (kTile >> 4);
+                    const uint64_t bq = dQ0 + static_cast<uint32_t>(((G2 % kNQ) * 2 * kSubTile) >> 4), bdo = bq + (kSubTile >> 4);
+                    const uint32_t tS = tmem + (G2 & 1) * 128, tDP = tS + 64;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQS, 0, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ptx::umma_bf16_ss(tS, ak + k * 2, bq + k * 2, idesc, k != 0);
+                        ptx::umma_bf16_ss(tDP, av + k * 2, bdo + k * 2, idesc, k != 0);
+                    }
+                    ptx::umma_commit(&bar_s[G2 & 1]);
+                }
+                __syncwarp();
+            }
+            FDBG(5);
+            // ---- (C) Q / dO (and a new item's K / V) of sub-iteration G + 4 ----
+            if (cq.item >= 0) {
+                const int Gq = G + 4;
+                const uint32_t first = cq.u == cq.u0, last = cq.u + 1 == cq.nsub;
+                m5 = kMValid | (cq.n % kNKV) | (((cq.n / kNKV) & 1) << 2) | (first ? kMFirst : 0u) | (last ? kMLast : 0u) |
+                     (cq.n > 0 ? kMNz : 0u) | ((cq.n & 1) << 7);
+                // ring slot Gq % 6 was read by the products of G - 2; a new item's K / V slot by item n - 3, whose last
+                // products are those of G - 1 at the latest (every item has >= 2 sub-iterations)
+                const int need = first ? G - 1 : G - 2;
+                while (retired < need) {
+                    ++retired;
+                    ptx::mbar_wait(&bar_acc[retired & 1], (retired >> 1) & 1);
+                }
+                const int c_h = __shfl_sync(0xffffffffu, cq.h * 64, 0), c_b = __shfl_sync(0xffffffffu, cq.b, 0);
+                const int c_q = __shfl_sync(0xffffffffu, cq.u * BQS, 0), c_k = __shfl_sync(0xffffffffu, cq.k0, 0);
+                const int kvs = __shfl_sync(0xffffffffu, cq.n % kNKV, 0);
+                if (issuer) {
+                    if (first) {
+                        uint8_t* dst = sKV + kvs * 2 * kTile;
+                        ptx::mbar_arrive_expect_tx(&bar_kv[kvs], 2 * kTile);
+                        ptx::tma_load_3d(dst, &tmap_k, &bar_kv[kvs], c_h, c_k, c_b);
+                        ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[kvs], c_h, c_k, c_b);
+                    }
+                    const int r = Gq % kNQ;
+                    uint8_t* dst = sQdO + r * 2 * kSubTile;
+                    ptx::mbar_arrive_expect_tx(&bar_q[r], 2 * kSubTile);
+                    ptx::tma_load_3d(dst, &tmap_q, &bar_q[r], c_h, c_q, c_b);
+                    ptx::tma_load_3d(dst + kSubTile, &tmap_do, &bar_q[r], c_h, c_q, c_b);
+                }
+                __syncwarp();
+                bwd_advance(cq, p, num_items, B);
+            }
+            FDBG(3);
         }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {
+        FDBG_DUMP_ROW(Gend, kDkvSoftmaxWarps * 32, 2);
+    } else if (warp < kDkvSoftmaxWarps) {
+        // ===================================== softmax / gradient of the scores =================
+        const int grp = warp >> 3;                           // the slot this group owns
+        const int w8 = warp & 7;
+        const int half = w8 >> 2;                            // which 32 of the sub-block's 64 query columns
+        const int row = ((w8 & 3) << 5) + lane;              // key row inside the block = TMEM lane
+        const int gt = threadIdx.x & 255;                    // thread index inside the group
+        const uint32_t lane_base = static_cast<uint32_t>((w8 & 3) * 32) << 16;
+        const int col_h = half * 32;
+        const float sl2e = p.scale_log2e;
+        const uint32_t tS = tmem + grp * 128 + lane_base + col_h, tDP = tS + 64;
+        const uint32_t tP = tmem + 256 + grp * 64 + lane_base + (col_h >> 1), tDS = tP + 32;
+        float* stat = sStat + grp * 256;                     // [2 buffers][64 queries x (lse2, lse2', delta, delta') pairs]
+        int kown = 0;                                        // this group's sub-iterations so far (phase of its slot's barriers)
+        int n_done = 0;                                      // non-empty items finished (phase of bar_item)
+        float cur_stat = 0.f;                                // this thread's staged statistic (prefetched one sub-iteration ahead)
+        bool have_stat = false;
+        BwdIter it;
+        FDBG_DECL;
+        int my_iters = 0;
+        bool pending = false;        // an item whose dV / dK have not been read out yet
+        bf16* rout_prev = nullptr;
+        int kj_prev = 0;
+        auto read_out = [&](bf16* rout_, int kj_) {
+            // ---- the item's gradients, once every product of the item has retired ----
+            FDBG(7);
+            ptx::mbar_wait(bar_item, n_done & 1);
+            FDBG(6);
+            ++n_done;
             ptx::tc_fence_after_sync();
-            const uint32_t bq = ptx::smem_u32(sQdO + buf * 2 * kTile), bdo = bq + kTile;
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // B = [query x 64] read MN-major
-            if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < BQ / 16; ++k) {
-                    ptx::umma_bf16_ts(tDV, tS + k * 8, ptx::make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc, k != 0);
-                    ptx::umma_bf16_ts(tDK, tDP + k * 8, ptx::make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc, k != 0);
-                }
-                ptx::umma_commit(bar_acc);
-            }
-            __syncwarp();
-        }
-        // these MMAs read P^T / dS^T and this Q/dO buffer: wait before either is overwritten
-        ptx::mbar_wait(bar_acc, it & 1);
-        ptx::tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
             uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tDV + lane_base + c, r);
+            ptx::tmem_ld_32x32b_x32((grp == 0 ? tDV : tDK) + lane_base + half * 32, r);
             ptx::tmem_ld_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_done);   // the next item's first products may overwrite dV / dK
+            FDBG(5);
+            // Four lanes transpose their 4 x 16-byte chunks so that one store instruction writes 64 contiguous bytes per
+            // row for eight rows (lane = row would touch 32 different 128-byte lines per instruction: measured 3,100 clk
+            // per item in the store queue).
+            {
+                const float sc = grp == 0 ? 1.0f : p.scale;
+                uint32_t w[16];
 #pragma unroll
-            for (int t = 0; t < 32; ++t) acc_dv[c + t] += __uint_as_float(r[t]);
-            ptx::tmem_ld_32x32b_x32(tDK + lane_base + c, r);
-            ptx::tmem_ld_wait();
+                for (int x = 0; x < 16; ++x) {
+                    const bf162 hv = __floats2bfloat162_rn(__uint_as_float(r[2 * x]) * sc, __uint_as_float(r[2 * x + 1]) * sc);
+                    w[x] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                const int j = lane & 3;
 #pragma unroll
-            for (int t = 0; t < 32; ++t) acc_dk[c + t] += __uint_as_float(r[t]);
-        }
-        // the next iteration's products overwrite every column: all reads must be complete first
-        ptx::tc_fence_before_sync();
-        __syncthreads();
-    }
-    // ---- write dK (scaled) and dV ----
-    if (qb0 < nqb) {
-        if (kj < p.Tk) {
-            bf16* rk = p.out0 + b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs + h * 64;
-            bf16* rv = p.out1 + b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs + h * 64;
+                for (int step = 1; step <= 2; ++step) {   // butterfly: swap chunk c of lane i with chunk c^step of lane i^step
+                    const bool hi = (j & step) != 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float t[8];
+                    for (int c = 0; c < 4; ++c) {
+                        if (c & step) continue;            // pair (c, c + step)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = acc_dk[q * 8 + u] * p.scale;
-                stg16(rk + q * 8, pack8(t));
+                        for (int x = 0; x < 4; ++x) {
+                            const uint32_t send = hi ? w[4 * c + x] : w[4 * (c + step) + x];
+                            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, step);
+                            if (hi) w[4 * c + x] = recv;
+                            else w[4 * (c + step) + x] = recv;
+                        }
+                    }
+                }
+                // now chunk position c holds columns [8 j, 8 j + 8) of row (row - j + c)
+                const size_t rs = grp == 0 ? p.s1.rs : p.s0.rs;
+                bf16* rq = rout_ + 8 * j - static_cast<size_t>(j) * rs;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = acc_dv[q * 8 + u];
-                stg16(rv + q * 8, pack8(t));
+                for (int c = 0; c < 4; ++c)
+                    if (kj_ - j + c < p.Tk) stg16(rq + c * rs, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
             }
-        }
-    } else if (kj < p.Tk) {  // no query sees this key block: zero gradients
-        const uint4 z = make_uint4(0, 0, 0, 0);
-        bf16* r0 = p.out0 + b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs + h * 64;
-        bf16* r1 = p.out1 + b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs + h * 64;
+            FDBG(8);
+        };
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            bwd_item_setup(it, p, item, B);
+            const int kj = it.k0 + row;
+            // read-out assignment: group 0 stores dV, group 1 stores dK; a row is shared by the group's two threads
+            bf16* rout = (grp == 0 ? p.out1 + it.b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs
+                                   : p.out0 + it.b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs) + it.h * 64 + half * 32;
+            if (it.u0 >= it.nsub) {   // no query sees this key block: zero gradients
+                if (kj < p.Tk) {
+                    const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int c = 0; c < 64; c += 8) {
-            stg16(r0 + c, z);
-            stg16(r1 + c, z);
+                    for (int c = 0; c < 32; c += 8) stg16(rout + c, z);
+                }
+                continue;
+            }
+            const size_t stat_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq;
+            const bool tail_keys = it.k0 + BK > p.Tk;   // some key rows of this block are past the sequence
+            have_stat = false;
+            FDBG(9);
+            // (an item has an even number of sub-iterations and starts in slot 0: this group's are u0 + grp, + 2, ...)
+            for (int u = it.u0 + grp; u < it.nsub; u += 2, ++kown) {
+                const int slot = grp;
+                const int k = kown;               // the k-th sub-iteration of this slot (barrier phase)
+                const int qs = u * BQS;
+                ++my_iters;
+                FDBG(7);
+                // statistics of the sub-block: float4 (-lse * log2e, -lse' * log2e, -delta, -delta') per PAIR of query columns
+                float* st = stat + (k & 1) * 128;
+                auto load_stat = [&](int q0_) -> float {   // thread gt < 64: lse of query gt; 64 <= gt < 128: delta (raw values:
+                    const int qi = q0_ + (gt & 63);        // nothing here may depend on the load, it is still in flight)
+                    float v = gt < 64 ? INFINITY : 0.f;    // a query past the sequence: p -> 0, dS -> 0
+                    if (gt < 128 && qi < p.Tq) v = (gt < 64 ? p.lse : p.delta)[stat_base + qi];
+                    return v;
+                };
+                if (!have_stat) cur_stat = load_stat(qs);
+                if (gt < 128) st[((gt & 63) >> 1) * 4 + (gt >> 6) * 2 + (gt & 1)] = -cur_stat * (gt < 64 ? 1.4426950408889634f : 1.f);
+                have_stat = u + 2 < it.nsub;
+                if (have_stat) cur_stat = load_stat(qs + 2 * BQS);   // this group's next sub-block: in flight under the arithmetic
+                ptx::named_bar_sync(1 + grp, 256);
+                FDBG(0);
+                const float4* st4 = reinterpret_cast<const float4*>(st) + (col_h >> 1);
+                ptx::mbar_wait(&bar_s[slot], k & 1);
+                FDBG(1);
+                ptx::tc_fence_after_sync();
+                uint32_t s[32], dp[32];
+                ptx::tmem_ld_32x32b_x32(tS, s);
+                ptx::tmem_ld_32x32b_x32(tDP, dp);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bar_sfree[slot]);   // the scores of G + 2 may overwrite the slot
+                FDBG(2);
+                const bool slow = tail_keys || (p.causal && (qs + shift < it.k0 + BK - 1));   // masked pairs in this sub-block
+                uint32_t pk[16], dk[16];
+                auto body = [&](auto masked_tag) {   // two copies of the arithmetic behind ONE uniform branch
+                    constexpr bool kMasked = decltype(masked_tag)::value;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const float4 sv = st4[t];
+                        float p0 = ex2f(fmaf(__uint_as_float(s[2 * t]), sl2e, sv.x));
+                        float p1 = ex2f(fmaf(__uint_as_float(s[2 * t + 1]), sl2e, sv.y));
+                        if (kMasked) {   // causal: query sees key iff key <= query + shift; keys past the sequence see nothing
+                            const int col = col_h + 2 * t;
+                            if (kj >= p.Tk || (p.causal && qs + col + shift < kj)) p0 = 0.f;
+                            if (kj >= p.Tk || (p.causal && qs + col + 1 + shift < kj)) p1 = 0.f;
+                        }
+                        const float d0 = p0 * (__uint_as_float(dp[2 * t]) + sv.z);
+                        const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) + sv.w);
+                        const bf162 hp = __floats2bfloat162_rn(p0, p1);
+                        const bf162 hd = __floats2bfloat162_rn(d0, d1);
+                        pk[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                        dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+                    }
+                };
+                if (slow) body(std::true_type{});
+                else body(std::false_type{});
+                FDBG(3);
+                if (k > 0) {   // this slot's previous gradient products read P^T / dS^T: retired before the stores
+                    ptx::mbar_wait(&bar_acc[slot], (k - 1) & 1);
+                    ptx::tc_fence_after_sync();
+                }
+                ptx::tmem_st_32x32b_x16(tP, pk);
+                ptx::tmem_st_32x32b_x16(tDS, dk);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&bar_p[slot]);
+                FDBG(4);
+                if (pending) {
+                    read_out(rout_prev, kj_prev);
+                    pending = false;
+                }
+            }
+            // the read-out of this item is deferred until this group has written the first P^T / dS^T of the NEXT item:
+            // the wait for the item's last products (issued for the other group half a period later) runs under useful work
+            pending = true;
+            rout_prev = rout;
+            kj_prev = kj;
         }
+        if (pending) read_out(rout_prev, kj_prev);
+        FDBG_DUMP_ROW(my_iters, 0, 0);
+        FDBG_DUMP_ROW(my_iters, 256, 1);
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, 256);
+        ptx::tmem_dealloc(tmem, 512);
     }
 }
 
@@ -898,12 +1113,12 @@ EncodeTiledFn encode_fn2() {
 }
 
 // [B, T, W] bf16 view -> box 64 x 128 x 1, 128B swizzle, zero fill
-int tmap_rows128(CUtensorMap* map, const void* base, int W, int T, int B, int rs, long long bs) {
+int tmap_rows128(CUtensorMap* map, const void* base, int W, int T, int B, int rs, long long bs, int box_rows = 128) {
     EncodeTiledFn fn = encode_fn2();
     VLK_REQUIRE(fn != nullptr, VLK_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -963,7 +1178,7 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
                    cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
         VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
         configured = true;
     }
@@ -993,7 +1208,18 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
     p.out1 = static_cast<bf16*>(dv);
     p.s0 = Strides{dk_bs, dk_rs};
     p.s1 = Strides{dv_bs, dv_rs};
-    flash_bwd_dkv_kernel<<<dim3((Tk + BK - 1) / BK, H, B), 128, kBwdSmem, stream>>>(tq, tk, tv, tdo, p);
+    {
+        CUtensorMap tq64, tdo64;   // 64-row boxes: the dK/dV kernel walks the queries in sub-blocks of 64
+        rc = tmap_rows128(&tq64, q, H * 64, Tq, B, q_rs, q_bs, BQS);
+        if (rc) return rc;
+        rc = tmap_rows128(&tdo64, d_o, H * 64, Tq, B, o_rs, o_bs, BQS);
+        if (rc) return rc;
+        const int sms = device_sm_count();
+        VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_bwd: no sm_100 device");
+        const long long items = static_cast<long long>((Tk + BK - 1) / BK) * H * B;
+        const int grid = static_cast<int>(items < sms ? items : sms);   // persistent: one CTA per SM
+        flash_bwd_dkv_kernel<<<grid, kDkvThreads, kDkvSmem, stream>>>(tq64, tk, tv, tdo64, p, B);
+    }
     VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dkv)");
     p.out0 = static_cast<bf16*>(dq);
     p.out1 = nullptr;
