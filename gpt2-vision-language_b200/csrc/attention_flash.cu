@@ -531,6 +531,7 @@ struct FlashBwdParams {
 //   * Q / dO sub-tiles in a ring of four, K / V in a ring of four items (the load cursor runs three sub-iterations ahead).
 constexpr int BQS = 64;                   // queries per sub-block
 constexpr int kSubTile = BQS * 128;       // bytes of a 64-row x 64-col bf16 tile
+constexpr int kBwdEnd = -0x7fffffff;   // BwdIter::item once the CTA's items are exhausted
 struct BwdIter {
     int n, item;      // ordinal of the (non-empty) item inside this CTA (K/V slot = n % 4), global item index (< 0: end)
     int u, u0, nsub;  // 64-query sub-block, first sub-block that sees the key block, sub-blocks of the sequence
@@ -551,7 +552,7 @@ __device__ __forceinline__ void bwd_item_setup(BwdIter& it, const FlashBwdParams
     it.u = it.u0;
 }
 __device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p, int num_items, int B) {
-    if (it.item < 0) return false;
+    if (it.item == kBwdEnd) return false;
     if (++it.u < it.nsub) return true;
     for (int next = it.item + static_cast<int>(gridDim.x); next < num_items; next += gridDim.x) {
         bwd_item_setup(it, p, next, B);
@@ -560,13 +561,13 @@ __device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p
             return true;
         }
     }
-    it.item = -1;
+    it.item = kBwdEnd;
     return false;
 }
 
 constexpr int kDkvSoftmaxWarps = 16;                       // two groups of eight
 constexpr int kDkvThreads = (kDkvSoftmaxWarps + 4) * 32;   // + the issue warpgroup (one active warp)
-constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 64 <= 640 x 96
+constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 64 <= 640 x 96 (112 + 64 would take the WHOLE file: the kernel hangs in setmaxnreg.inc)
 // smem: (K, V) x 3 | (Q, dO) sub-tiles x 6 | statistics [2 groups][2][128] | barriers
 constexpr int kNKV = 3, kNQ = 6;   // K / V ring (items), Q / dO ring (sub-blocks)
 constexpr int kDkvOffQ = kNKV * 2 * kTile, kDkvOffStat = kDkvOffQ + kNQ * 2 * kSubTile, kDkvOffBar = kDkvOffStat + 2 * 2 * 128 * 4;
@@ -591,7 +592,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* bar_item = bar_done + 1;         // MMA -> all 16 warps: every gradient product of the item has retired (one phase
                                                // per item, waited for by both groups in order: a group never polls the OTHER
                                                // slot's bar_acc, whose phase it does not track)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_item + 1);
+    uint64_t* bar_free = bar_item + 1;         // [kNQ] MMA -> TMA: the products that read the Q / dO ring slot have retired
+    uint64_t* bar_kvfree = bar_free + kNQ;     // [kNKV] MMA -> TMA: every product of the item in the K / V slot has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kvfree + kNKV);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -606,6 +609,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         ptx::prefetch_tensormap(&tmap_do);
         for (int i = 0; i < kNKV + kNQ + 4; ++i) ptx::mbar_init(bar_kv + i, 1);
         ptx::mbar_init(bar_item, 1);
+        for (int i = 0; i < kNQ + kNKV; ++i) ptx::mbar_init(bar_free + i, 1);
         for (int i = 0; i < 4; ++i) ptx::mbar_init(bar_p + i, kDkvSoftmaxWarps / 2);   // bar_p[2], bar_sfree[2]
         ptx::mbar_init(bar_done, kDkvSoftmaxWarps);
         ptx::fence_barrier_init();
@@ -620,117 +624,33 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t tmem = *tmem_slot;
     const uint32_t tDV = tmem + 384, tDK = tmem + 448;
 
+    // ===================================== TMA, score MMAs, product MMAs: one warp each ========================
+    // Three converged warps on three different schedulers (one elected lane issues), each with its own cursor over the
+    // CTA's sub-iterations and NO ordering between them except the barriers: as one in-order warp the issue side was busy
+    // ~1,450 clk per sub-iteration (it shares its scheduler with four softmax warps) and bounded the whole kernel.
+    // (setmaxnreg sits INSIDE each role's branch: ptxas sizes a region's registers by the setmaxnreg that dominates it)
     if (warp >= kDkvSoftmaxWarps) {
         ptx::setmaxnreg_dec<kDkvIssueRegs>();
-    } else {
-        ptx::setmaxnreg_inc<kDkvSoftmaxRegs>();
-    }
-    if (warp == kDkvSoftmaxWarps) {
-        // ===================================== TMA + MMA issue ==================================
-        // ONE cursor (the load cursor, three sub-iterations ahead of the products) and a shift register of packed
-        // per-sub-iteration facts, one call site per operation: the kernel's code has to stay inside the 32 KB
-        // instruction cache level (the first version of this loop, with three cursors and unrolled prologues, made the
-        // kernel 48 KB and every cold path — item read-out, item setup — paid instruction fetches from L2).
         const bool issuer = ptx::elect_one();
-        const uint32_t akv0 = ptx::smem_u32(sKV), aq0 = ptx::smem_u32(sQdO);
-        const uint64_t dKV0 = ptx::make_smem_desc_sw128(akv0, 16, 1024);     // K / V rows, K-major A operand
-        const uint64_t dQ0 = ptx::make_smem_desc_sw128(aq0, 16, 1024);       // Q / dO rows, K-major B operand (scores)
-        const uint64_t dQmn0 = ptx::make_smem_desc_sw128(aq0, 8192, 1024);   // the same tiles read MN-major (products)
-        constexpr uint32_t kMValid = 1u << 6, kMFirst = 1u << 3, kMLast = 1u << 4, kMNz = 1u << 5;
-        BwdIter cq;
-        cq.n = 0;
-        cq.item = -1;
-        for (int first = blockIdx.x; first < num_items; first += gridDim.x) {   // first item some query sees
-            bwd_item_setup(cq, p, first, B);
-            if (cq.u0 < cq.nsub) break;
-            cq.item = -1;
+        BwdIter c;   // "before the first item": the first advance finds the first item some query sees
+        c.n = -1;
+        c.item = static_cast<int>(blockIdx.x) - static_cast<int>(gridDim.x);
+        c.u = c.u0 = c.nsub = 0;
+        c.k0 = c.h = c.b = 0;
+        bool valid = bwd_advance(c, p, num_items, B);
+        if (warp == kDkvSoftmaxWarps + 3) {
+            valid = false;   // the warpgroup's fourth warp has no role
         }
-        // Iteration G of the loop: (B) the gradient products of G - 1 once its P^T / dS^T are written, (A) the scores of
-        // G + 2 once S^T / dP^T of G (same slot) are in the group's registers — long before the group has finished its
-        // exponentials, so the next scores are ready when it comes back —, (C) the loads of G + 4.  B precedes A: a group
-        // arrives on bar_sfree of a new item's first sub-iteration only after the previous item's read-out, which waits
-        // for products that B issues.
-        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;   // facts of sub-iterations G-1 .. G+4
-        int retired = -1;   // the products of every sub-iteration <= retired are known complete (bar_acc phases, in order)
-        FDBG_DECL;
-        int Gend = 0;
+        if (warp == kDkvSoftmaxWarps + 2) {
+            // ---- TMA: Q / dO of every sub-iteration (ring of six), K / V of every item (ring of three) ----
 #pragma unroll 1
-        for (int G = -4;; ++G) {
-            m0 = m1;
-            m1 = m2;
-            m2 = m3;
-            m3 = m4;
-            m4 = m5;
-            m5 = 0;
-            FDBG(7);
-            // ---- (B) gradient products of G - 1: dV += P^T dO, dK += dS^T Q ----
-            if (G >= 1) {
-                if (!(m0 & kMValid)) break;
-                const int Gp = G - 1, slot = Gp & 1;
-                ptx::mbar_wait(&bar_p[slot], (Gp >> 1) & 1);
-                FDBG(0);
-                if ((m0 & (kMFirst | kMNz)) == (kMFirst | kMNz))     // the previous item's dV / dK have been read out
-                    ptx::mbar_wait(bar_done, ((m0 >> 7) & 1) ^ 1);   // parity of item n - 1
-                FDBG(1);
-                ptx::tc_fence_after_sync();
-                if (issuer) {
-                    const uint64_t bdq = dQmn0 + static_cast<uint32_t>(((Gp % kNQ) * 2 * kSubTile) >> 4);
-                    const uint64_t bdo = bdq + (kSubTile >> 4);
-                    const uint32_t tP = tmem + 256 + slot * 64, tDS = tP + 32;
-                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // B = [query x 64] read MN-major
-                    const uint32_t acc = (m0 & kMFirst) ? 0u : 1u;
-#pragma unroll
-                    for (int kk = 0; kk < BQS / 16; ++kk) {
-                        ptx::umma_bf16_ts(tDV, tP + kk * 8, bdo + kk * (2048 >> 4), idesc, (acc | kk) != 0);
-                        ptx::umma_bf16_ts(tDK, tDS + kk * 8, bdq + kk * (2048 >> 4), idesc, (acc | kk) != 0);
-                    }
-                    ptx::umma_commit(&bar_acc[slot]);
-                    if (m0 & kMLast) ptx::umma_commit(bar_item);   // the item's last sub-iteration
-                }
-                __syncwarp();
-                Gend = G;
-            }
-            FDBG(4);
-            // ---- (A) scores of G + 2 into the slot of G: S^T = K Q^T, dP^T = V dO^T ----
-            if (G >= -2 && (m3 & kMValid)) {
-                const int G2 = G + 2, kvs = m3 & 3;
-                if (G >= 0) ptx::mbar_wait(&bar_sfree[G & 1], (G >> 1) & 1);
-                FDBG(2);
-                ptx::mbar_wait(&bar_q[G2 % kNQ], (G2 / kNQ) & 1);
-                ptx::mbar_wait(&bar_kv[kvs], (m3 >> 2) & 1);
-                FDBG(6);
-                ptx::tc_fence_after_sync();
-                if (issuer) {
-                    const uint64_t ak = dKV0 + static_cast<uint32_t>((kvs * 2 * kTile) >> 4), av = ak + (kTile >> 4);
-                    const uint64_t bq = dQ0 + static_cast<uint32_t>(((G2 % kNQ) * 2 * kSubTile) >> 4), bdo = bq + (kSubTile >> 4);
-                    const uint32_t tS = tmem + (G2 & 1) * 128, tDP = tS + 64;
-                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQS, 0, 0);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        ptx::umma_bf16_ss(tS, ak + k * 2, bq + k * 2, idesc, k != 0);
-                        ptx::umma_bf16_ss(tDP, av + k * 2, bdo + k * 2, idesc, k != 0);
-                    }
-                    ptx::umma_commit(&bar_s[G2 & 1]);
-                }
-                __syncwarp();
-            }
-            FDBG(5);
-            // ---- (C) Q / dO (and a new item's K / V) of sub-iteration G + 4 ----
-            if (cq.item >= 0) {
-                const int Gq = G + 4;
-                const uint32_t first = cq.u == cq.u0, last = cq.u + 1 == cq.nsub;
-                m5 = kMValid | (cq.n % kNKV) | (((cq.n / kNKV) & 1) << 2) | (first ? kMFirst : 0u) | (last ? kMLast : 0u) |
-                     (cq.n > 0 ? kMNz : 0u) | ((cq.n & 1) << 7);
-                // ring slot Gq % 6 was read by the products of G - 2; a new item's K / V slot by item n - 3, whose last
-                // products are those of G - 1 at the latest (every item has >= 2 sub-iterations)
-                const int need = first ? G - 1 : G - 2;
-                while (retired < need) {
-                    ++retired;
-                    ptx::mbar_wait(&bar_acc[retired & 1], (retired >> 1) & 1);
-                }
-                const int c_h = __shfl_sync(0xffffffffu, cq.h * 64, 0), c_b = __shfl_sync(0xffffffffu, cq.b, 0);
-                const int c_q = __shfl_sync(0xffffffffu, cq.u * BQS, 0), c_k = __shfl_sync(0xffffffffu, cq.k0, 0);
-                const int kvs = __shfl_sync(0xffffffffu, cq.n % kNKV, 0);
+            for (int G = 0; valid; ++G) {
+                const int r = G % kNQ, kvs = c.n % kNKV;
+                const bool first = c.u == c.u0;
+                if (G >= kNQ) ptx::mbar_wait(&bar_free[r], (G / kNQ - 1) & 1);
+                if (first && c.n >= kNKV) ptx::mbar_wait(&bar_kvfree[kvs], (c.n / kNKV - 1) & 1);
+                const int c_h = __shfl_sync(0xffffffffu, c.h * 64, 0), c_b = __shfl_sync(0xffffffffu, c.b, 0);
+                const int c_q = __shfl_sync(0xffffffffu, c.u * BQS, 0), c_k = __shfl_sync(0xffffffffu, c.k0, 0);
                 if (issuer) {
                     if (first) {
                         uint8_t* dst = sKV + kvs * 2 * kTile;
@@ -738,20 +658,75 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                         ptx::tma_load_3d(dst, &tmap_k, &bar_kv[kvs], c_h, c_k, c_b);
                         ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[kvs], c_h, c_k, c_b);
                     }
-                    const int r = Gq % kNQ;
                     uint8_t* dst = sQdO + r * 2 * kSubTile;
                     ptx::mbar_arrive_expect_tx(&bar_q[r], 2 * kSubTile);
                     ptx::tma_load_3d(dst, &tmap_q, &bar_q[r], c_h, c_q, c_b);
                     ptx::tma_load_3d(dst + kSubTile, &tmap_do, &bar_q[r], c_h, c_q, c_b);
                 }
                 __syncwarp();
-                bwd_advance(cq, p, num_items, B);
+                valid = bwd_advance(c, p, num_items, B);
             }
-            FDBG(3);
+        } else if (warp == kDkvSoftmaxWarps + 1) {
+            // ---- scores of G: S^T = K Q^T, dP^T = V dO^T, as soon as the group has S^T / dP^T of G - 2 in registers ----
+            const uint64_t dKV0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sKV), 16, 1024);    // K-major A operand
+            const uint64_t dQ0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sQdO), 16, 1024);    // K-major B operand
+#pragma unroll 1
+            for (int G = 0; valid; ++G) {
+                const int kvs = c.n % kNKV;
+                if (G >= 2) ptx::mbar_wait(&bar_sfree[G & 1], ((G - 2) >> 1) & 1);
+                ptx::mbar_wait(&bar_q[G % kNQ], (G / kNQ) & 1);
+                ptx::mbar_wait(&bar_kv[kvs], (c.n / kNKV) & 1);
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t ak = dKV0 + static_cast<uint32_t>((kvs * 2 * kTile) >> 4), av = ak + (kTile >> 4);
+                    const uint64_t bq = dQ0 + static_cast<uint32_t>(((G % kNQ) * 2 * kSubTile) >> 4), bdo = bq + (kSubTile >> 4);
+                    const uint32_t tS = tmem + (G & 1) * 128, tDP = tS + 64;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQS, 0, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ptx::umma_bf16_ss(tS, ak + k * 2, bq + k * 2, idesc, k != 0);
+                        ptx::umma_bf16_ss(tDP, av + k * 2, bdo + k * 2, idesc, k != 0);
+                    }
+                    ptx::umma_commit(&bar_s[G & 1]);
+                }
+                __syncwarp();
+                valid = bwd_advance(c, p, num_items, B);
+            }
+        } else {
+            // ---- gradient products of G: dV += P^T dO, dK += dS^T Q, once the group has written P^T / dS^T ----
+            const uint64_t dQmn0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sQdO), 8192, 1024);   // the tiles read MN-major
+#pragma unroll 1
+            for (int G = 0; valid; ++G) {
+                const int slot = G & 1;
+                const bool first = c.u == c.u0, last = c.u + 1 == c.nsub;
+                ptx::mbar_wait(&bar_p[slot], (G >> 1) & 1);
+                if (first && c.n > 0) ptx::mbar_wait(bar_done, (c.n - 1) & 1);   // dV / dK of the previous item were read out
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t bdq = dQmn0 + static_cast<uint32_t>(((G % kNQ) * 2 * kSubTile) >> 4);
+                    const uint64_t bdo = bdq + (kSubTile >> 4);
+                    const uint32_t tP = tmem + 256 + slot * 64, tDS = tP + 32;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // B = [query x 64] read MN-major
+                    const uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+                    for (int kk = 0; kk < BQS / 16; ++kk) {
+                        ptx::umma_bf16_ts(tDV, tP + kk * 8, bdo + kk * (2048 >> 4), idesc, (acc | kk) != 0);
+                        ptx::umma_bf16_ts(tDK, tDS + kk * 8, bdq + kk * (2048 >> 4), idesc, (acc | kk) != 0);
+                    }
+                    ptx::umma_commit(&bar_acc[slot]);
+                    ptx::umma_commit(&bar_free[G % kNQ]);
+                    if (last) {
+                        ptx::umma_commit(bar_item);
+                        ptx::umma_commit(&bar_kvfree[c.n % kNKV]);
+                    }
+                }
+                __syncwarp();
+                valid = bwd_advance(c, p, num_items, B);
+            }
         }
-        FDBG_DUMP_ROW(Gend, kDkvSoftmaxWarps * 32, 2);
-    } else if (warp < kDkvSoftmaxWarps) {
+    } else {
         // ===================================== softmax / gradient of the scores =================
+        ptx::setmaxnreg_inc<kDkvSoftmaxRegs>();
         const int grp = warp >> 3;                           // the slot this group owns
         const int w8 = warp & 7;
         const int half = w8 >> 2;                            // which 32 of the sub-block's 64 query columns
@@ -823,26 +798,40 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             FDBG(8);
         };
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-            bwd_item_setup(it, p, item, B);
-            const int kj = it.k0 + row;
-            // read-out assignment: group 0 stores dV, group 1 stores dK; a row is shared by the group's two threads
-            bf16* rout = (grp == 0 ? p.out1 + it.b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs
-                                   : p.out0 + it.b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs) + it.h * 64 + half * 32;
-            if (it.u0 >= it.nsub) {   // no query sees this key block: zero gradients
-                if (kj < p.Tk) {
-                    const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int item = blockIdx.x;; item += gridDim.x) {
+            // one pass per item plus a final flush pass (no sub-iteration) that reads out the last item: ONE copy of the
+            // read-out code
+            const bool live = item < num_items;
+            if (!live && !pending) break;
+            int kj = 0, u_beg = 0, u_end = 0;
+            bf16* rout = nullptr;
+            size_t stat_base = 0;
+            bool tail_keys = false;
+            if (live) {
+                bwd_item_setup(it, p, item, B);
+                kj = it.k0 + row;
+                // read-out assignment: group 0 stores dV, group 1 stores dK; a row is shared by the group's two threads
+                rout = (grp == 0 ? p.out1 + it.b * p.s1.bs + static_cast<size_t>(kj) * p.s1.rs
+                                 : p.out0 + it.b * p.s0.bs + static_cast<size_t>(kj) * p.s0.rs) + it.h * 64 + half * 32;
+                if (it.u0 >= it.nsub) {   // no query sees this key block: zero gradients
+                    if (kj < p.Tk) {
+                        const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int c = 0; c < 32; c += 8) stg16(rout + c, z);
+                        for (int c = 0; c < 32; c += 8) stg16(rout + c, z);
+                    }
+                    continue;
                 }
-                continue;
+                stat_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq;
+                tail_keys = it.k0 + BK > p.Tk;   // some key rows of this block are past the sequence
+                have_stat = false;
+                FDBG(9);
+                // (an item has an even number of sub-iterations and starts in slot 0: this group's are u0 + grp, + 2, ...)
+                u_beg = it.u0 + grp;
+                u_end = it.nsub;
             }
-            const size_t stat_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq;
-            const bool tail_keys = it.k0 + BK > p.Tk;   // some key rows of this block are past the sequence
-            have_stat = false;
-            FDBG(9);
-            // (an item has an even number of sub-iterations and starts in slot 0: this group's are u0 + grp, + 2, ...)
-            for (int u = it.u0 + grp; u < it.nsub; u += 2, ++kown) {
+            int u = u_beg;
+            do {
+                if (u < u_end) {
                 const int slot = grp;
                 const int k = kown;               // the k-th sub-iteration of this slot (barrier phase)
                 const int qs = u * BQS;
@@ -876,28 +865,35 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 FDBG(2);
                 const bool slow = tail_keys || (p.causal && (qs + shift < it.k0 + BK - 1));   // masked pairs in this sub-block
                 uint32_t pk[16], dk[16];
-                auto body = [&](auto masked_tag) {   // two copies of the arithmetic behind ONE uniform branch
-                    constexpr bool kMasked = decltype(masked_tag)::value;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float4 sv = st4[t];
+                    const float p0 = ex2f(fmaf(__uint_as_float(s[2 * t]), sl2e, sv.x));
+                    const float p1 = ex2f(fmaf(__uint_as_float(s[2 * t + 1]), sl2e, sv.y));
+                    const float d0 = p0 * (__uint_as_float(dp[2 * t]) + sv.z);
+                    const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) + sv.w);
+                    const bf162 hp = __floats2bfloat162_rn(p0, p1);
+                    const bf162 hd = __floats2bfloat162_rn(d0, d1);
+                    pk[t] = *reinterpret_cast<const uint32_t*>(&hp);
+                    dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+                }
+                if (slow) {
+                    // Masked pairs are cleared in the packed results (bit operations: an overflowed exponential of a masked
+                    // score never reaches the products) — one copy of the arithmetic keeps the kernel inside the 32 KB
+                    // instruction-cache level.  A query column c of this thread is visible iff c >= cmin: causal = key <=
+                    // query + shift; a key past the sequence sees nothing.
+                    const int cmin = kj >= p.Tk ? (1 << 30) : (p.causal ? kj - qs - shift - col_h : -(1 << 30));
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
-                        const float4 sv = st4[t];
-                        float p0 = ex2f(fmaf(__uint_as_float(s[2 * t]), sl2e, sv.x));
-                        float p1 = ex2f(fmaf(__uint_as_float(s[2 * t + 1]), sl2e, sv.y));
-                        if (kMasked) {   // causal: query sees key iff key <= query + shift; keys past the sequence see nothing
-                            const int col = col_h + 2 * t;
-                            if (kj >= p.Tk || (p.causal && qs + col + shift < kj)) p0 = 0.f;
-                            if (kj >= p.Tk || (p.causal && qs + col + 1 + shift < kj)) p1 = 0.f;
+                        if (2 * t + 1 < cmin) {
+                            pk[t] = 0u;
+                            dk[t] = 0u;
+                        } else if (2 * t < cmin) {
+                            pk[t] &= 0xffff0000u;
+                            dk[t] &= 0xffff0000u;
                         }
-                        const float d0 = p0 * (__uint_as_float(dp[2 * t]) + sv.z);
-                        const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) + sv.w);
-                        const bf162 hp = __floats2bfloat162_rn(p0, p1);
-                        const bf162 hd = __floats2bfloat162_rn(d0, d1);
-                        pk[t] = *reinterpret_cast<const uint32_t*>(&hp);
-                        dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
                     }
-                };
-                if (slow) body(std::true_type{});
-                else body(std::false_type{});
+                }
                 FDBG(3);
                 if (k > 0) {   // this slot's previous gradient products read P^T / dS^T: retired before the stores
                     ptx::mbar_wait(&bar_acc[slot], (k - 1) & 1);
@@ -910,18 +906,21 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&bar_p[slot]);
                 FDBG(4);
-                if (pending) {
+                ++kown;
+                }
+                if (pending) {   // (also the flush pass after the last item, which has no sub-iteration)
                     read_out(rout_prev, kj_prev);
                     pending = false;
                 }
-            }
+                u += 2;
+            } while (u < u_end);
+            if (!live) break;
             // the read-out of this item is deferred until this group has written the first P^T / dS^T of the NEXT item:
             // the wait for the item's last products (issued for the other group half a period later) runs under useful work
             pending = true;
             rout_prev = rout;
             kj_prev = kj;
         }
-        if (pending) read_out(rout_prev, kj_prev);
         FDBG_DUMP_ROW(my_iters, 0, 0);
         FDBG_DUMP_ROW(my_iters, 256, 1);
     }
