@@ -943,168 +943,333 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
 }
 
-// ---- kernel B: dQ_i.  smem: Q | dO | (K,V) x 2 | barriers ----
-// TMEM: 256 columns (two CTAs per SM, so one CTA's exp / store phase runs under the other's MMAs): S [0,128),
-// dP [128,256) -> dS bf16 in place; this block's dQ contribution lands in [0,64) (S is consumed by then) and is added
-// to a register accumulator, because the next iteration's S overwrites it.
-__global__ void __launch_bounds__(128, 2)
+// ---- kernel B: dQ_i — persistent, warp-specialised, TWO 64-key sub-blocks in flight (one CTA per SM) ----
+// The same machine as kernel A with the roles of queries and keys exchanged.  Work item = one 128-query block of one
+// (batch, head); the CTA walks the 64-key sub-blocks it sees (thread = query row = TMEM lane):
+//     S = Q K_v^T,  dP = dO V_v^T   ->   dS = exp2(S * scale*log2e - lse*log2e) (dP - delta)   ->   dQ += dS K_v
+// TMEM: slot s = sub-iteration parity:  S [128 s, +64) | dP [128 s + 64, +64) | dS bf16 [256 + 32 s, +32) | dQ fp32
+// [320, 384).  Q / dO in a ring of two items, K / V sub-tiles in a ring of six; the row statistics are per thread (two
+// loads per item).  Item n is read out by softmax group n & 1 (so the two groups alternate), after that group has written
+// the first dS of the next item.
+struct DqIter {
+    int n, item;      // ordinal of the (non-empty) item inside this CTA, global item index (kBwdEnd: exhausted)
+    int v, nsub;      // 64-key sub-block, sub-blocks this query block sees (even; 0 = none)
+    int q0, h, b;
+};
+__device__ __forceinline__ void dq_item_setup(DqIter& it, const FlashBwdParams& p, int item, int B, int nqb) {
+    it.item = item;
+    const int hb = p.H * B;
+    const int qb = nqb - 1 - item / hb, r = item % hb;   // with a causal mask the last query block sees the most keys: first
+    it.h = r % p.H;
+    it.b = r / p.H;
+    it.q0 = qb * BQ;
+    const int nkeys = p.causal ? min(p.Tk, it.q0 + BQ + (p.Tk - p.Tq)) : p.Tk;   // keys some row of the block sees
+    it.nsub = nkeys > 0 ? 2 * ((nkeys + BK - 1) / BK) : 0;
+    it.v = 0;
+}
+__device__ __forceinline__ bool dq_advance(DqIter& it, const FlashBwdParams& p, int num_items, int B, int nqb) {
+    if (it.item == kBwdEnd) return false;
+    if (++it.v < it.nsub) return true;
+    for (int next = bwd_next_item(it.item); next < num_items; next = bwd_next_item(next)) {
+        dq_item_setup(it, p, next, B, nqb);
+        if (it.nsub > 0) {
+            ++it.n;
+            return true;
+        }
+    }
+    it.item = kBwdEnd;
+    return false;
+}
+constexpr int kDqNKV = 6;   // K / V sub-tile ring
+// smem: (Q, dO) x 2 | (K, V) sub-tiles x 6 | barriers
+constexpr int kDqOffKV = 2 * 2 * kTile, kDqOffBar = kDqOffKV + kDqNKV * 2 * kSubTile;
+constexpr int kDqSmem = kDqOffBar + 256 + 1024;
+
+__global__ void __launch_bounds__(kDkvThreads, 1)
 flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                    FlashBwdParams p) {
+                    FlashBwdParams p, int B) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sdO = smem + kTile;
-    uint8_t* sKV = smem + 2 * kTile;  // [buf][K|V]
-    uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + 6 * kTile);
-    uint64_t* bar_kv = bar_q + 1;  // [2]
-    uint64_t* bar_s = bar_q + 3;
-    uint64_t* bar_acc = bar_q + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
+    uint8_t* sQdO = smem;                  // [2][Q | dO], 128 rows each
+    uint8_t* sKV = smem + kDqOffKV;        // [kDqNKV][K | V], 64 rows each
+    uint64_t* bar_qdo = reinterpret_cast<uint64_t*>(smem + kDqOffBar);   // [2] TMA -> MMA
+    uint64_t* bar_kv = bar_qdo + 2;            // [kDqNKV] TMA -> MMA
+    uint64_t* bar_s = bar_kv + kDqNKV;         // [2] MMA -> group: S, dP of the slot complete
+    uint64_t* bar_acc = bar_s + 2;             // [2] MMA -> group: the product that read the slot's dS has retired
+    uint64_t* bar_p = bar_acc + 2;             // [2] group (8 warps) -> MMA: dS of the slot is in tensor memory
+    uint64_t* bar_sfree = bar_p + 2;           // [2] group (8 warps) -> MMA: S, dP of the slot are in registers
+    uint64_t* bar_done = bar_sfree + 2;        // [2] group n & 1 (8 warps) -> MMA: dQ of item n has been read out
+    uint64_t* bar_item = bar_done + 2;         // [2] MMA -> group n & 1: every product of item n has retired
+    uint64_t* bar_free = bar_item + 2;         // [kDqNKV] MMA -> TMA: the K / V ring slot has been consumed
+    uint64_t* bar_qfree = bar_free + kDqNKV;   // [2] MMA -> TMA: the item's scores have consumed Q / dO
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qfree + 2);
 
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
-    // grid (H, B, query blocks), the LAST query block first: with a causal mask it sees the most key blocks, and blocks
-    // are dispatched x-fastest — heaviest CTAs first, so the last wave is made of the light ones
-    const int qb = static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z), h = blockIdx.x, b = blockIdx.y;
-    const int q0 = qb * BQ;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int nqb = (p.Tq + BQ - 1) / BQ;
+    const int num_items = nqb * p.H * B;
     const int shift = p.Tk - p.Tq;
-    int nkb = (p.Tk + BK - 1) / BK;
-    if (p.causal) nkb = min(nkb, (q0 + BQ - 1 + shift) / BK + 1);
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmap_q);
         ptx::prefetch_tensormap(&tmap_k);
         ptx::prefetch_tensormap(&tmap_v);
         ptx::prefetch_tensormap(&tmap_do);
-        ptx::mbar_init(bar_q, 1);
-        ptx::mbar_init(&bar_kv[0], 1);
-        ptx::mbar_init(&bar_kv[1], 1);
-        ptx::mbar_init(bar_s, 1);
-        ptx::mbar_init(bar_acc, 1);
+        for (int i = 0; i < 2 + kDqNKV + 4; ++i) ptx::mbar_init(bar_qdo + i, 1);          // bar_qdo, bar_kv, bar_s, bar_acc
+        for (int i = 0; i < 6; ++i) ptx::mbar_init(bar_p + i, kDkvSoftmaxWarps / 2);      // bar_p, bar_sfree, bar_done
+        for (int i = 0; i < 2 + kDqNKV + 2; ++i) ptx::mbar_init(bar_item + i, 1);         // bar_item, bar_free, bar_qfree
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, 256);
+        ptx::tmem_alloc(tmem_slot, 512);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem;
-    float dq[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) dq[i] = 0.f;
+    const uint32_t tDQ = tmem + 320;
 
-    auto load_kv = [&](int j) {
-        uint8_t* dst = sKV + (j & 1) * 2 * kTile;
-        ptx::mbar_arrive_expect_tx(&bar_kv[j & 1], 2 * kTile);
-        ptx::tma_load_3d(dst, &tmap_k, &bar_kv[j & 1], h * 64, j * BK, b);
-        ptx::tma_load_3d(dst + kTile, &tmap_v, &bar_kv[j & 1], h * 64, j * BK, b);
-    };
-    if (threadIdx.x == 0) {
-        ptx::mbar_arrive_expect_tx(bar_q, 2 * kTile);
-        ptx::tma_load_3d(sQ, &tmap_q, bar_q, h * 64, q0, b);
-        ptx::tma_load_3d(sdO, &tmap_do, bar_q, h * 64, q0, b);
-        load_kv(0);
-    }
-    const int row = threadIdx.x, qi = q0 + row;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    int lim = p.Tk;
-    if (p.causal) lim = min(p.Tk, qi + shift + 1);
-    const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.Tq + qi;
-    const float lse_raw = qi < p.Tq ? p.lse[stat] : INFINITY;   // consumed after the first product: the loads hide under it
-    const float dlt = qi < p.Tq ? p.delta[stat] : 0.f;
-
-    for (int j = 0; j < nkb; ++j) {
-        const uint32_t par = (j >> 1) & 1;
-        if (warp == 0) {   // converged warp, one elected lane issues
-            if (j == 0) ptx::mbar_wait(bar_q, 0);
-            ptx::mbar_wait(&bar_kv[j & 1], par);
-            ptx::tc_fence_after_sync();
-            const uint32_t aq = ptx::smem_u32(sQ), ado = ptx::smem_u32(sdO);
-            const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile), bv = bk + kTile;
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BK, 0, 0);
-            if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {  // S = Q K^T ; dP = dO V^T
-                    ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                                      ptx::make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc, k != 0);
-                    ptx::umma_bf16_ss(tDP, ptx::make_smem_desc_sw128(ado + k * 32, 16, 1024),
-                                      ptx::make_smem_desc_sw128(bv + k * 32, 16, 1024), idesc, k != 0);
-                }
-                ptx::umma_commit(bar_s);
-                if (j + 1 < nkb) load_kv(j + 1);
-            }
-            __syncwarp();
-        }
-        ptx::mbar_wait(bar_s, j & 1);
-        ptx::tc_fence_after_sync();
-        const int k0 = j * BK;
-        const float lse2 = lse_raw * 1.4426950408889634f;
+    if (warp >= kDkvSoftmaxWarps) {
+        ptx::setmaxnreg_dec<kDkvIssueRegs>();
+        const bool issuer = ptx::elect_one();
+        DqIter c;   // "before the first item"
+        c.n = -1;
+        c.item = -1;
+        c.v = c.nsub = 0;
+        c.q0 = c.h = c.b = 0;
+        bool valid = dq_advance(c, p, num_items, B, nqb);
+        if (warp == kDkvSoftmaxWarps + 3) valid = false;   // the warpgroup's fourth warp has no role
+        if (warp == kDkvSoftmaxWarps + 2) {
+            // ---- TMA: Q / dO of every item (ring of two), K / V of every sub-iteration (ring of six) ----
 #pragma unroll 1
-        for (int c = 0; c < BK; c += 32) {
-            uint32_t rs[32], rp[32];
-            ptx::tmem_ld_32x32b_x32(tS + lane_base + c, rs);
-            ptx::tmem_ld_32x32b_x32(tDP + lane_base + c, rp);
-            ptx::tmem_ld_wait();
-            uint32_t dk[16];
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                float dv[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float pr = ex2f(fmaf(__uint_as_float(rs[2 * t + u]), p.scale_log2e, -lse2));
-                    if (k0 + c + 2 * t + u >= lim) pr = 0.f;
-                    dv[u] = pr * (__uint_as_float(rp[2 * t + u]) - dlt);
+            for (int G = 0; valid; ++G) {
+                const int r = G % kDqNKV, qs = c.n & 1;
+                const bool first = c.v == 0;
+                if (G >= kDqNKV) ptx::mbar_wait(&bar_free[r], (G / kDqNKV - 1) & 1);
+                if (first && c.n >= 2) ptx::mbar_wait(&bar_qfree[qs], (c.n / 2 - 1) & 1);
+                const int c_h = __shfl_sync(0xffffffffu, c.h * 64, 0), c_b = __shfl_sync(0xffffffffu, c.b, 0);
+                const int c_q = __shfl_sync(0xffffffffu, c.q0, 0), c_k = __shfl_sync(0xffffffffu, c.v * BQS, 0);
+                if (issuer) {
+                    if (first) {
+                        uint8_t* dst = sQdO + qs * 2 * kTile;
+                        ptx::mbar_arrive_expect_tx(&bar_qdo[qs], 2 * kTile);
+                        ptx::tma_load_3d(dst, &tmap_q, &bar_qdo[qs], c_h, c_q, c_b);
+                        ptx::tma_load_3d(dst + kTile, &tmap_do, &bar_qdo[qs], c_h, c_q, c_b);
+                    }
+                    uint8_t* dst = sKV + r * 2 * kSubTile;
+                    ptx::mbar_arrive_expect_tx(&bar_kv[r], 2 * kSubTile);
+                    ptx::tma_load_3d(dst, &tmap_k, &bar_kv[r], c_h, c_k, c_b);
+                    ptx::tma_load_3d(dst + kSubTile, &tmap_v, &bar_kv[r], c_h, c_k, c_b);
                 }
-                const bf162 hd = __floats2bfloat162_rn(dv[0], dv[1]);
-                dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+                __syncwarp();
+                valid = dq_advance(c, p, num_items, B, nqb);
             }
-            ptx::tmem_st_32x32b_x16(tDP + lane_base + (c >> 1), dk);  // dS in place
+        } else if (warp == kDkvSoftmaxWarps + 1) {
+            // ---- scores of G: S = Q K^T, dP = dO V^T, as soon as the group has S / dP of G - 2 in registers ----
+            const uint64_t dQ0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sQdO), 16, 1024);   // K-major A operand (128 rows)
+            const uint64_t dK0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sKV), 16, 1024);    // K-major B operand (64 rows)
+#pragma unroll 1
+            for (int G = 0; valid; ++G) {
+                const int qs = c.n & 1;
+                const bool last = c.v + 1 == c.nsub;
+                if (G >= 2) ptx::mbar_wait(&bar_sfree[G & 1], ((G - 2) >> 1) & 1);
+                ptx::mbar_wait(&bar_kv[G % kDqNKV], (G / kDqNKV) & 1);
+                ptx::mbar_wait(&bar_qdo[qs], (c.n >> 1) & 1);
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t aq = dQ0 + static_cast<uint32_t>((qs * 2 * kTile) >> 4), ado = aq + (kTile >> 4);
+                    const uint64_t bk = dK0 + static_cast<uint32_t>(((G % kDqNKV) * 2 * kSubTile) >> 4), bv = bk + (kSubTile >> 4);
+                    const uint32_t tS = tmem + (G & 1) * 128, tDP = tS + 64;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, BQS, 0, 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        ptx::umma_bf16_ss(tS, aq + k * 2, bk + k * 2, idesc, k != 0);
+                        ptx::umma_bf16_ss(tDP, ado + k * 2, bv + k * 2, idesc, k != 0);
+                    }
+                    ptx::umma_commit(&bar_s[G & 1]);
+                    if (last) ptx::umma_commit(&bar_qfree[qs]);
+                }
+                __syncwarp();
+                valid = dq_advance(c, p, num_items, B, nqb);
+            }
+        } else {
+            // ---- product of G: dQ += dS K, once the group has written dS ----
+            const uint64_t dKmn0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sKV), 8192, 1024);   // K sub-tile read MN-major
+#pragma unroll 1
+            for (int G = 0; valid; ++G) {
+                const int slot = G & 1;
+                const bool first = c.v == 0, last = c.v + 1 == c.nsub;
+                ptx::mbar_wait(&bar_p[slot], (G >> 1) & 1);
+                if (first && c.n > 0) ptx::mbar_wait(&bar_done[(c.n - 1) & 1], ((c.n - 1) >> 1) & 1);   // dQ of n - 1 was read out
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint64_t bk = dKmn0 + static_cast<uint32_t>(((G % kDqNKV) * 2 * kSubTile) >> 4);
+                    const uint32_t tDS = tmem + 256 + slot * 32;
+                    constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // B = [key x 64] read MN-major
+                    const uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+                    for (int kk = 0; kk < BQS / 16; ++kk)
+                        ptx::umma_bf16_ts(tDQ, tDS + kk * 8, bk + kk * (2048 >> 4), idesc, (acc | kk) != 0);
+                    ptx::umma_commit(&bar_acc[slot]);
+                    ptx::umma_commit(&bar_free[G % kDqNKV]);
+                    if (last) ptx::umma_commit(&bar_item[c.n & 1]);
+                }
+                __syncwarp();
+                valid = dq_advance(c, p, num_items, B, nqb);
+            }
         }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {
+    } else {
+        // ===================================== gradient of the scores ===========================
+        ptx::setmaxnreg_inc<kDkvSoftmaxRegs>();
+        const int grp = warp >> 3;                           // the slot this group owns
+        const int w8 = warp & 7;
+        const int half = w8 >> 2;                            // which 32 of the sub-block's 64 key columns
+        const int row = ((w8 & 3) << 5) + lane;              // query row inside the block = TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((w8 & 3) * 32) << 16;
+        const int col_h = half * 32;
+        const float sl2e = p.scale_log2e;
+        const uint32_t tS = tmem + grp * 128 + lane_base + col_h, tDP = tS + 64;
+        const uint32_t tDS = tmem + 256 + grp * 32 + lane_base + (col_h >> 1);
+        int kown = 0;        // this group's sub-iterations so far (phase of its slot's barriers)
+        int n = 0;           // ordinal of the current non-empty item
+        bool pending = false;        // an item of this group whose dQ has not been read out yet
+        bf16* rout_prev = nullptr;
+        int qi_prev = 0, n_prev = 0;
+        DqIter it;
+        auto read_out = [&](bf16* rout_, int qi_, int n_) {
+            ptx::mbar_wait(&bar_item[grp], (n_ >> 1) & 1);
             ptx::tc_fence_after_sync();
-            const uint32_t bk = ptx::smem_u32(sKV + (j & 1) * 2 * kTile);
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);  // K_j read MN-major: N = d, K = keys
-            if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    ptx::umma_bf16_ts(tDQ, tDP + k * 8, ptx::make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc, k != 0);
-                ptx::umma_commit(bar_acc);
-            }
-            __syncwarp();
-        }
-        ptx::mbar_wait(bar_acc, j & 1);
-        ptx::tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
             uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tDQ + lane_base + c, r);
+            ptx::tmem_ld_32x32b_x32(tDQ + lane_base + half * 32, r);
             ptx::tmem_ld_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar_done[grp]);   // the next item's first product may overwrite dQ
+            uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dq[c + i] += __uint_as_float(r[i]);
+            for (int x = 0; x < 16; ++x) {
+                const bf162 hv = __floats2bfloat162_rn(__uint_as_float(r[2 * x]) * p.scale, __uint_as_float(r[2 * x + 1]) * p.scale);
+                w[x] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            const int j = lane & 3;   // four lanes transpose their 4 x 16-byte chunks: 64 contiguous bytes per row and store
+#pragma unroll
+            for (int step = 1; step <= 2; ++step) {
+                const bool hi = (j & step) != 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c & step) continue;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const uint32_t send = hi ? w[4 * c + x] : w[4 * (c + step) + x];
+                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, step);
+                        if (hi) w[4 * c + x] = recv;
+                        else w[4 * (c + step) + x] = recv;
+                    }
+                }
+            }
+            const size_t rs = p.s0.rs;
+            bf16* rq = rout_ + 8 * j - static_cast<size_t>(j) * rs;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (qi_ - j + c < p.Tq) stg16(rq + c * rs, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        };
+        for (int item = bwd_first_item();; item = bwd_next_item(item)) {
+            const bool live = item < num_items;
+            if (!live && !pending) break;
+            int qi = 0, v_beg = 0, v_end = 0;
+            bf16* rout = nullptr;
+            float lse2 = -INFINITY, ndelta = 0.f;
+            if (live) {
+                dq_item_setup(it, p, item, B, nqb);
+                qi = it.q0 + row;
+                rout = p.out0 + it.b * p.s0.bs + static_cast<size_t>(qi) * p.s0.rs + it.h * 64 + half * 32;
+                if (it.nsub == 0) {   // this query block sees no key: zero gradient (group 0 writes it)
+                    if (grp == 0 && qi < p.Tq) {
+                        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) stg16(rout + c, z);
+                    }
+                    continue;
+                }
+                if (qi < p.Tq) {   // a row past the sequence keeps -inf: its dS are zero
+                    const size_t si = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq + qi;
+                    lse2 = -p.lse[si] * 1.4426950408889634f;
+                    ndelta = -p.delta[si];
+                }
+                v_beg = grp;   // an item has an even number of sub-iterations and starts in slot 0
+                v_end = it.nsub;
+            }
+            int v = v_beg;
+            do {
+                if (v < v_end) {
+                    const int slot = grp, k = kown;
+                    const int k0 = v * BQS;   // first key of the sub-block
+                    ptx::mbar_wait(&bar_s[slot], k & 1);
+                    ptx::tc_fence_after_sync();
+                    uint32_t s[32], dp[32];
+                    ptx::tmem_ld_32x32b_x32(tS, s);
+                    ptx::tmem_ld_32x32b_x32(tDP, dp);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bar_sfree[slot]);   // the scores of G + 2 may overwrite the slot
+                    uint32_t dk[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const float p0 = ex2f(fmaf(__uint_as_float(s[2 * t]), sl2e, lse2));
+                        const float p1 = ex2f(fmaf(__uint_as_float(s[2 * t + 1]), sl2e, lse2));
+                        const float d0 = p0 * (__uint_as_float(dp[2 * t]) + ndelta);
+                        const float d1 = p1 * (__uint_as_float(dp[2 * t + 1]) + ndelta);
+                        const bf162 hd = __floats2bfloat162_rn(d0, d1);
+                        dk[t] = *reinterpret_cast<const uint32_t*>(&hd);
+                    }
+                    // masked pairs (warp-uniform test): a key column c of this thread is visible iff c <= cmax — causal: key
+                    // <= query + shift; keys past the sequence (zero-filled rows: their p is NOT zero) see nothing
+                    if (k0 + BQS > p.Tk || (p.causal && k0 + BQS - 1 > it.q0 + shift)) {
+                        int cmax = p.Tk - 1 - k0;
+                        if (p.causal) cmax = min(cmax, qi + shift - k0);
+                        cmax -= col_h;
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            if (2 * t > cmax) dk[t] = 0u;
+                            else if (2 * t + 1 > cmax) dk[t] &= 0x0000ffffu;
+                        }
+                    }
+                    if (k > 0) {   // this slot's previous product read dS: retired before the store
+                        ptx::mbar_wait(&bar_acc[slot], (k - 1) & 1);
+                        ptx::tc_fence_after_sync();
+                    }
+                    ptx::tmem_st_32x32b_x16(tDS, dk);
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&bar_p[slot]);
+                    ++kown;
+                }
+                if (pending) {   // (also the flush pass after the last item, which has no sub-iteration)
+                    read_out(rout_prev, qi_prev, n_prev);
+                    pending = false;
+                }
+                v += 2;
+            } while (v < v_end);
+            if (!live) break;
+            // item n is read out by group n & 1, after that group's first sub-iteration of the next item
+            if ((n & 1) == grp) {
+                pending = true;
+                rout_prev = rout;
+                qi_prev = qi;
+                n_prev = n;
+            }
+            ++n;
         }
-        // the next iteration's S / dP products overwrite every column: all reads must be complete first
-        ptx::tc_fence_before_sync();
-        __syncthreads();
     }
-    if (qi < p.Tq) {
-        bf16* orow = p.out0 + b * p.s0.bs + static_cast<size_t>(qi) * p.s0.rs + h * 64;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = dq[q * 8 + u] * p.scale;
-            stg16(orow + q * 8, pack8(t));
-        }
-    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem, 256);
+        ptx::tmem_dealloc(tmem, 512);
     }
 }
 
@@ -1140,7 +1305,6 @@ int tmap_rows128(CUtensorMap* map, const void* base, int W, int T, int B, int rs
 }
 
 constexpr int kFwdSmem = 6 * kTile + kFwdXchBytes + 128 + 1024;
-constexpr int kBwdSmem = 6 * kTile + 2 * 256 * 4 + 128 + 1024;
 
 }  // namespace
 
@@ -1191,7 +1355,7 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
     static bool configured = false;
     if (!configured) {
         VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem));
-        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        VLK_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
         configured = true;
     }
     const int rows = B * H * Tq;
@@ -1236,7 +1400,17 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
     p.out0 = static_cast<bf16*>(dq);
     p.out1 = nullptr;
     p.s0 = Strides{dq_bs, dq_rs};
-    flash_bwd_dq_kernel<<<dim3(H, B, (Tq + BQ - 1) / BQ), 128, kBwdSmem, stream>>>(tq, tk, tv, tdo, p);
+    {
+        CUtensorMap tk64, tv64;   // 64-row boxes: the dQ kernel walks the keys in sub-blocks of 64
+        rc = tmap_rows128(&tk64, k, H * 64, Tk, B, k_rs, k_bs, BQS);
+        if (rc) return rc;
+        rc = tmap_rows128(&tv64, v, H * 64, Tk, B, v_rs, v_bs, BQS);
+        if (rc) return rc;
+        const int sms = device_sm_count();
+        const long long items = static_cast<long long>((Tq + BQ - 1) / BQ) * H * B;
+        const int grid = static_cast<int>(items < sms ? items : sms);   // persistent: one CTA per SM
+        flash_bwd_dq_kernel<<<grid, kDkvThreads, kDqSmem, stream>>>(tq, tk64, tv64, tdo, p, B);
+    }
     VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dq)");
     return VLK_OK;
 }
