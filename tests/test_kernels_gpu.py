@@ -147,7 +147,11 @@ def test_pair_attention_odd_head_counts_and_dropout_determinism(cuda, B, H, Tq, 
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [(2, 12, 1024, 1024, True), (1, 4, 384, 384, True), (1, 2, 500, 500, False),
-                                              (2, 3, 129, 300, False), (1, 2, 640, 640, True)])
+                                              (2, 3, 129, 300, False), (1, 2, 640, 640, True),
+                                              # ragged causal (a half-empty last 128-block), causal with more keys than
+                                              # queries (the diagonal is shifted by Tk - Tq), few queries / many keys
+                                              (1, 2, 1000, 1000, True), (1, 2, 200, 456, True), (2, 2, 65, 1000, False),
+                                              (1, 3, 321, 321, True)])
 def test_flash_attention_long_sequences(cuda, B, H, Tq, Tk, causal):
     """Streaming tcgen05 forward/backward (GPT-2 pretraining shape T=1024 and ragged lengths) vs torch fp32."""
     from gpt2_vision_language_b200 import ops
