@@ -505,6 +505,29 @@ flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, flo
     if (sub == 0 && w < total_rows) delta[w] = s;
 }
 
+// Division by a launch-time constant as multiply-high + shift (exact for 0 <= n < 2^31): the persistent backward kernels
+// decode an item index in every role warp at every item change, and a hardware-less integer division is ~20 instructions
+// on the issue slots the softmax warps need.
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __device__ __forceinline__ int div(int n) const {
+        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr);
+    }
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = static_cast<uint32_t>(d);
+    f.mul = 0;
+    f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1ll << lg) < d) ++lg;   // ceil(log2 d)
+        const int pw = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << pw) + static_cast<uint64_t>(d) - 1) / static_cast<uint64_t>(d));
+        f.shr = static_cast<uint32_t>(pw - 32);
+    }
+    return f;
+}
 struct FlashBwdParams {
     const float* lse;
     const float* delta;
@@ -513,6 +536,7 @@ struct FlashBwdParams {
     Strides s0, s1;
     int H, Tq, Tk, causal;
     float scale, scale_log2e;
+    FastDiv div_hb, div_h, div_grid;   // by H * B, by H, by the grid size (persistent backward kernels)
 };
 
 // ---- kernel A: dK_j, dV_j — persistent, warp-specialised, TWO 64-query sub-blocks in flight (one CTA per SM) ----
@@ -541,9 +565,9 @@ struct BwdIter {
 __device__ __forceinline__ void bwd_item_setup(BwdIter& it, const FlashBwdParams& p, int item, int B) {
     it.item = item;
     const int hb = p.H * B;
-    const int kb = item / hb, r = item % hb;   // key block 0 sees the most query blocks: heaviest items first
-    it.h = r % p.H;
-    it.b = r / p.H;
+    const int kb = p.div_hb.div(item), r = item - kb * hb;   // key block 0 sees the most query blocks: heaviest items first
+    it.b = p.div_h.div(r);
+    it.h = r - it.b * p.H;
     it.k0 = kb * BK;
     // whole 128-query blocks, i.e. an EVEN number of sub-blocks per item (a sub-block past the sequence or below the
     // causal diagonal is masked to zero): every item starts in slot 0, both groups do the same number of sub-iterations,
@@ -556,16 +580,16 @@ __device__ __forceinline__ void bwd_item_setup(BwdIter& it, const FlashBwdParams
 // grid - 1 - x): the items are sorted heaviest first, so plain striding gives CTA 0 the heaviest item of EVERY round
 // (51 vs 46.7 128-query blocks on average at T = 1024); the snake brings the maximum to 48.
 __device__ __forceinline__ int bwd_first_item() { return static_cast<int>(blockIdx.x); }
-__device__ __forceinline__ int bwd_next_item(int item) {
+__device__ __forceinline__ int bwd_next_item(int item, const FastDiv& div_grid) {
     const int g = static_cast<int>(gridDim.x);
     if (item < 0) return bwd_first_item();   // the "before the first item" state of a cursor
-    const int r = item / g, x = item - r * g;
+    const int r = div_grid.div(item), x = item - r * g;
     return (r + 1) * g + (g - 1 - x);
 }
 __device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p, int num_items, int B) {
     if (it.item == kBwdEnd) return false;
     if (++it.u < it.nsub) return true;
-    for (int next = bwd_next_item(it.item); next < num_items; next = bwd_next_item(next)) {
+    for (int next = bwd_next_item(it.item, p.div_grid); next < num_items; next = bwd_next_item(next, p.div_grid)) {
         bwd_item_setup(it, p, next, B);
         if (it.u0 < it.nsub) {   // (items no query sees are handled by the softmax warps alone and are not counted)
             ++it.n;
@@ -809,7 +833,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             }
             FDBG(8);
         };
-        for (int item = bwd_first_item();; item = bwd_next_item(item)) {
+        for (int item = bwd_first_item();; item = bwd_next_item(item, p.div_grid)) {
             // one pass per item plus a final flush pass (no sub-iteration) that reads out the last item: ONE copy of the
             // read-out code
             const bool live = item < num_items;
@@ -959,9 +983,10 @@ struct DqIter {
 __device__ __forceinline__ void dq_item_setup(DqIter& it, const FlashBwdParams& p, int item, int B, int nqb) {
     it.item = item;
     const int hb = p.H * B;
-    const int qb = nqb - 1 - item / hb, r = item % hb;   // with a causal mask the last query block sees the most keys: first
-    it.h = r % p.H;
-    it.b = r / p.H;
+    const int qi = p.div_hb.div(item), r = item - qi * hb;
+    const int qb = nqb - 1 - qi;   // with a causal mask the last query block sees the most keys: first
+    it.b = p.div_h.div(r);
+    it.h = r - it.b * p.H;
     it.q0 = qb * BQ;
     const int nkeys = p.causal ? min(p.Tk, it.q0 + BQ + (p.Tk - p.Tq)) : p.Tk;   // keys some row of the block sees
     it.nsub = nkeys > 0 ? 2 * ((nkeys + BK - 1) / BK) : 0;
@@ -970,7 +995,7 @@ __device__ __forceinline__ void dq_item_setup(DqIter& it, const FlashBwdParams& 
 __device__ __forceinline__ bool dq_advance(DqIter& it, const FlashBwdParams& p, int num_items, int B, int nqb) {
     if (it.item == kBwdEnd) return false;
     if (++it.v < it.nsub) return true;
-    for (int next = bwd_next_item(it.item); next < num_items; next = bwd_next_item(next)) {
+    for (int next = bwd_next_item(it.item, p.div_grid); next < num_items; next = bwd_next_item(next, p.div_grid)) {
         dq_item_setup(it, p, next, B, nqb);
         if (it.nsub > 0) {
             ++it.n;
@@ -1138,6 +1163,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         bf16* rout_prev = nullptr;
         int qi_prev = 0, n_prev = 0;
         DqIter it;
+        FDBG_DECL;
+        int my_iters = 0;
         auto read_out = [&](bf16* rout_, int qi_, int n_) {
             ptx::mbar_wait(&bar_item[grp], (n_ >> 1) & 1);
             ptx::tc_fence_after_sync();
@@ -1175,12 +1202,12 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int c = 0; c < 4; ++c)
                 if (qi_ - j + c < p.Tq) stg16(rq + c * rs, make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
         };
-        for (int item = bwd_first_item();; item = bwd_next_item(item)) {
+        for (int item = bwd_first_item();; item = bwd_next_item(item, p.div_grid)) {
             const bool live = item < num_items;
             if (!live && !pending) break;
             int qi = 0, v_beg = 0, v_end = 0;
             bf16* rout = nullptr;
-            float lse2 = -INFINITY, ndelta = 0.f;
+            float lse_raw = INFINITY, delta_raw = 0.f;   // a row past the sequence keeps +inf: its p and dS are zero
             if (live) {
                 dq_item_setup(it, p, item, B, nqb);
                 qi = it.q0 + row;
@@ -1193,10 +1220,10 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     }
                     continue;
                 }
-                if (qi < p.Tq) {   // a row past the sequence keeps -inf: its dS are zero
+                if (qi < p.Tq) {   // nothing here depends on the loaded values: they are first used after the wait for S
                     const size_t si = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq + qi;
-                    lse2 = -p.lse[si] * 1.4426950408889634f;
-                    ndelta = -p.delta[si];
+                    lse_raw = p.lse[si];
+                    delta_raw = p.delta[si];
                 }
                 v_beg = grp;   // an item has an even number of sub-iterations and starts in slot 0
                 v_end = it.nsub;
@@ -1206,7 +1233,10 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (v < v_end) {
                     const int slot = grp, k = kown;
                     const int k0 = v * BQS;   // first key of the sub-block
+                    ++my_iters;
+                    FDBG(5);
                     ptx::mbar_wait(&bar_s[slot], k & 1);
+                    FDBG(0);
                     ptx::tc_fence_after_sync();
                     uint32_t s[32], dp[32];
                     ptx::tmem_ld_32x32b_x32(tS, s);
@@ -1215,6 +1245,9 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     ptx::tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&bar_sfree[slot]);   // the scores of G + 2 may overwrite the slot
+                    FDBG(1);
+                    asm volatile("" : "+f"(lse_raw), "+f"(delta_raw));   // (keeps the scaling below out of the item setup)
+                    const float lse2 = -lse_raw * 1.4426950408889634f, ndelta = -delta_raw;
                     uint32_t dk[16];
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
@@ -1237,6 +1270,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             else if (2 * t + 1 > cmax) dk[t] &= 0x0000ffffu;
                         }
                     }
+                    FDBG(2);
                     if (k > 0) {   // this slot's previous product read dS: retired before the store
                         ptx::mbar_wait(&bar_acc[slot], (k - 1) & 1);
                         ptx::tc_fence_after_sync();
@@ -1247,10 +1281,12 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&bar_p[slot]);
                     ++kown;
+                    FDBG(3);
                 }
                 if (pending) {   // (also the flush pass after the last item, which has no sub-iteration)
                     read_out(rout_prev, qi_prev, n_prev);
                     pending = false;
+                    FDBG(4);
                 }
                 v += 2;
             } while (v < v_end);
@@ -1264,6 +1300,8 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             ++n;
         }
+        FDBG_DUMP_ROW(my_iters, 0, 0);
+        FDBG_DUMP_ROW(my_iters, 256, 1);
     }
     ptx::tc_fence_before_sync();
     __syncthreads();
@@ -1394,6 +1432,9 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
         VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_bwd: no sm_100 device");
         const long long items = static_cast<long long>((Tk + BK - 1) / BK) * H * B;
         const int grid = static_cast<int>(items < sms ? items : sms);   // persistent: one CTA per SM
+        p.div_hb = make_fastdiv(H * B);
+        p.div_h = make_fastdiv(H);
+        p.div_grid = make_fastdiv(grid);
         flash_bwd_dkv_kernel<<<grid, kDkvThreads, kDkvSmem, stream>>>(tq64, tk, tv, tdo64, p, B);
     }
     VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dkv)");
@@ -1409,6 +1450,7 @@ int attn_flash_bwd(const void* q, const void* k, const void* v, const void* o, c
         const int sms = device_sm_count();
         const long long items = static_cast<long long>((Tq + BQ - 1) / BQ) * H * B;
         const int grid = static_cast<int>(items < sms ? items : sms);   // persistent: one CTA per SM
+        p.div_grid = make_fastdiv(grid);
         flash_bwd_dq_kernel<<<grid, kDkvThreads, kDqSmem, stream>>>(tq, tk64, tv64, tdo, p, B);
     }
     VLK_CHECK_LAUNCH("vlk_attn_bwd(flash dq)");

@@ -34,10 +34,12 @@ for _ in range(4):
 print(f"B={B} H={H} T={T} causal={CAUSAL}: backward {e0.elapsed_time(e1) * 1e3:.1f} us (eager, all launches of the call)")
 buf = (ctypes.c_longlong * (64 * 16))()
 lib.vlk_debug_flash_dump(buf, 64 * 16)
+which = os.environ.get("VLK_PROBE_KERNEL", "dq")   # the LAST kernel of the call that dumps wins: dq
+grp_dq = ["wait S/dP", "tcgen05.ld + arrive", "exp2 / dS / pack / mask", "wait product(k-1) + tcgen05.st + arrive", "read-out (wait item, ld, stores)", "loop + item setup", "-", "-", "-", "-"]
 grp = ["stats + group barrier", "wait S^T/dP^T", "tcgen05.ld", "exp2 / dS / pack", "wait products(k-1) + tcgen05.st + arrive", "read-out tcgen05.ld + arrive", "wait item",
        "sub-iteration loop", "8=stores", "9=next item setup"]
 iss = ["wait P^T/dS^T", "wait read-out", "wait S read", "request loads (+ wait retired)", "issue products", "issue scores(G+2)", "wait Q/dO, K/V tiles", "loop"]
-print("group phases:", " | ".join(f"{i}={n}" for i, n in enumerate(grp)))
+print("group phases (dQ kernel: it runs last and overwrites the dump):", " | ".join(f"{i}={n}" for i, n in enumerate(grp_dq)))
 print("issue phases:", " | ".join(f"{i}={n}" for i, n in enumerate(iss)))
 for cta in range(0, 20, 3):
     for t, name in enumerate(("group0 t0  ", "group1 t256", "issue lane0")):
