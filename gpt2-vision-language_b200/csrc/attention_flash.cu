@@ -777,6 +777,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         int n_done = 0;                                      // non-empty items finished (phase of bar_item)
         float cur_stat = 0.f;                                // this thread's staged statistic (prefetched one sub-iteration ahead)
         bool have_stat = false;
+        int pref_item = -1;                                  // the item cur_stat was prefetched for across an item boundary
         BwdIter it;
         FDBG_DECL;
         int my_iters = 0;
@@ -858,7 +859,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 stat_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq;
                 tail_keys = it.k0 + BK > p.Tk;   // some key rows of this block are past the sequence
-                have_stat = false;
+                have_stat = have_stat && pref_item == item;   // (prefetched at the previous item's last sub-iteration)
                 FDBG(9);
                 // (an item has an even number of sub-iterations and starts in slot 0: this group's are u0 + grp, + 2, ...)
                 u_beg = it.u0 + grp;
@@ -874,16 +875,31 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 FDBG(7);
                 // statistics of the sub-block: float4 (-lse * log2e, -lse' * log2e, -delta, -delta') per PAIR of query columns
                 float* st = stat + (k & 1) * 128;
-                auto load_stat = [&](int q0_) -> float {   // thread gt < 64: lse of query gt; 64 <= gt < 128: delta (raw values:
-                    const int qi = q0_ + (gt & 63);        // nothing here may depend on the load, it is still in flight)
+                auto load_stat = [&](size_t base_, int q0_) -> float {   // thread gt < 64: lse of query gt; 64 <= gt < 128: delta
+                    const int qi = q0_ + (gt & 63);        // (raw values: nothing here may depend on the load, it is in flight)
                     float v = gt < 64 ? INFINITY : 0.f;    // a query past the sequence: p -> 0, dS -> 0
-                    if (gt < 128 && qi < p.Tq) v = (gt < 64 ? p.lse : p.delta)[stat_base + qi];
+                    if (gt < 128 && qi < p.Tq) v = (gt < 64 ? p.lse : p.delta)[base_ + qi];
                     return v;
                 };
-                if (!have_stat) cur_stat = load_stat(qs);
+                if (!have_stat) cur_stat = load_stat(stat_base, qs);
                 if (gt < 128) st[((gt & 63) >> 1) * 4 + (gt >> 6) * 2 + (gt & 1)] = -cur_stat * (gt < 64 ? 1.4426950408889634f : 1.f);
+                // this group's next sub-block — of this item or, at its last one, of the CTA's next item — is in flight under
+                // the arithmetic
                 have_stat = u + 2 < it.nsub;
-                if (have_stat) cur_stat = load_stat(qs + 2 * BQS);   // this group's next sub-block: in flight under the arithmetic
+                if (have_stat) {
+                    cur_stat = load_stat(stat_base, qs + 2 * BQS);
+                } else {
+                    const int nx = bwd_next_item(item, p.div_grid);
+                    if (nx < num_items) {
+                        BwdIter nt;
+                        bwd_item_setup(nt, p, nx, B);
+                        if (nt.u0 < nt.nsub) {
+                            cur_stat = load_stat((static_cast<size_t>(nt.b) * p.H + nt.h) * p.Tq, (nt.u0 + grp) * BQS);
+                            have_stat = true;
+                            pref_item = nx;
+                        }
+                    }
+                }
                 ptx::named_bar_sync(1 + grp, 256);
                 FDBG(0);
                 const float4* st4 = reinterpret_cast<const float4*>(st) + (col_h >> 1);
