@@ -66,6 +66,29 @@ struct Strides {
 // ================================================================================================
 // forward
 // ================================================================================================
+// Division by a launch-time constant as multiply-high + shift (exact for 0 <= n < 2^31): the persistent kernels
+// decode an item index in every role warp at every item change, and a hardware-less integer division is ~20 instructions
+// on the issue slots the softmax warps need.
+struct FastDiv {
+    uint32_t mul, shr, d;
+    __device__ __forceinline__ int div(int n) const {
+        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr);
+    }
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = static_cast<uint32_t>(d);
+    f.mul = 0;
+    f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1ll << lg) < d) ++lg;   // ceil(log2 d)
+        const int pw = 31 + lg;
+        f.mul = static_cast<uint32_t>(((1ull << pw) + static_cast<uint64_t>(d) - 1) / static_cast<uint64_t>(d));
+        f.shr = static_cast<uint32_t>(pw - 32);
+    }
+    return f;
+}
 struct FlashFwdParams {
     bf16* o;
     float* lse;
@@ -75,6 +98,7 @@ struct FlashFwdParams {
     int nqb;           // query blocks per (b, h) = ceil(q_rows / 128)
     int wide_store;    // output rows are 32-byte aligned: 256-bit stores
     float scale, scale_log2e;
+    FastDiv div_hb, div_h, div_nqb;   // by H * B, by H, by nqb
 };
 
 // One step of a CTA's flat sequence of (work item, key block) iterations.  A work item is one 128-row query block of one
@@ -89,14 +113,15 @@ __device__ __forceinline__ void fwd_item_setup(FwdIter& it, const FlashFwdParams
     it.item = item;
     int qb, r;
     if (p.causal) {   // heaviest query blocks first: the per-CTA item lists then end with the cheapest items
-        qb = p.nqb - 1 - item / (p.H * p.B);
-        r = item % (p.H * p.B);
+        const int qi = p.div_hb.div(item);
+        qb = p.nqb - 1 - qi;
+        r = item - qi * (p.H * p.B);
     } else {          // query blocks of one (b, h) next to each other (their K / V meet in L2)
-        qb = item % p.nqb;
-        r = item / p.nqb;
+        r = p.div_nqb.div(item);
+        qb = item - r * p.nqb;
     }
-    it.h = r % p.H;
-    it.b = r / p.H;
+    it.b = p.div_h.div(r);
+    it.h = r - it.b * p.H;
     it.q0 = qb * BQ;
     it.nkb = p.causal ? min(nkb_all, (it.q0 + BQ - 1 + (p.Tk - p.Tq)) / BK + 1) : nkb_all;
     it.j = 0;
@@ -505,29 +530,6 @@ flash_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, flo
     if (sub == 0 && w < total_rows) delta[w] = s;
 }
 
-// Division by a launch-time constant as multiply-high + shift (exact for 0 <= n < 2^31): the persistent backward kernels
-// decode an item index in every role warp at every item change, and a hardware-less integer division is ~20 instructions
-// on the issue slots the softmax warps need.
-struct FastDiv {
-    uint32_t mul, shr, d;
-    __device__ __forceinline__ int div(int n) const {
-        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr);
-    }
-};
-inline FastDiv make_fastdiv(int d) {
-    FastDiv f;
-    f.d = static_cast<uint32_t>(d);
-    f.mul = 0;
-    f.shr = 0;
-    if (d > 1) {
-        int lg = 0;
-        while ((1ll << lg) < d) ++lg;   // ceil(log2 d)
-        const int pw = 31 + lg;
-        f.mul = static_cast<uint32_t>(((1ull << pw) + static_cast<uint64_t>(d) - 1) / static_cast<uint64_t>(d));
-        f.shr = static_cast<uint32_t>(pw - 32);
-    }
-    return f;
-}
 struct FlashBwdParams {
     const float* lse;
     const float* delta;
@@ -1390,6 +1392,9 @@ int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* 
     p.q_rows = q_rows;
     p.nqb = (q_rows + BQ - 1) / BQ;
     p.wide_store = (reinterpret_cast<uintptr_t>(o) & 31u) == 0 && o_rs % 16 == 0 && o_bs % 16 == 0;
+    p.div_hb = make_fastdiv(H * B);
+    p.div_h = make_fastdiv(H);
+    p.div_nqb = make_fastdiv(p.nqb);
     p.scale = scale;
     p.scale_log2e = scale * 1.4426950408889634f;
     const int sms = device_sm_count();
