@@ -167,7 +167,7 @@ constexpr int kFwdSoftmaxWarps = 8;
 // Three warpgroups: two softmax warpgroups and one whose first warp issues TMA / MMA (the other three only give their
 // registers away).  Registers are allocated per warpgroup, so 9 warps would cost 12 anyway: 2 CTAs x 384 threads leave
 // 80 registers per thread at launch; setmaxnreg moves the issue warpgroup's surplus to the softmax warpgroups
-// (2 x 128 x 104 + 128 x 32 = 384 x 80).
+// (2 x 128 x 104 + 128 x 32 = 384 x 80: setmaxnreg only moves registers INSIDE the allocation of the launch — asking for more hangs the CTA in setmaxnreg.inc).
 constexpr int kFwdThreads = 384;
 constexpr int kFwdSoftmaxRegs = 104, kFwdIssueRegs = 32;
 constexpr int kFwdXchBytes = 4096;
@@ -217,127 +217,100 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // (setmaxnreg sits INSIDE each role's branch: ptxas sizes a region's registers by the setmaxnreg that dominates it —
     // placed before the branch, the softmax code was compiled for the 80 registers of the launch and spilled)
     if (warp >= kFwdSoftmaxWarps) {
+        // ===================================== TMA and MMA issue: four warps, one duty each =====
+        // PV MMAs | QK MMAs | TMA of K and Q | TMA of V, each a converged warp (one elected lane issues) with its OWN cursor
+        // over the CTA's flat sequence of (item, key block) iterations and no ordering between them except the barriers.
+        // As one in-order warp with five cursors at 32 registers the issue side spilled, and QK(g+1) — released by
+        // "S(g) is in registers" — queued behind the wait for "P(g) is written" of the PV it had to issue first.
         ptx::setmaxnreg_dec<kFwdIssueRegs>();
-    }
-    if (warp == kFwdSoftmaxWarps) {
-        // ===================================== TMA + MMA issue ==================================
         const bool issuer = ptx::elect_one();
-        const uint32_t aq0 = ptx::smem_u32(sQ), ak0 = ptx::smem_u32(sK), av0 = ptx::smem_u32(sV);
-        auto load_q = [&](const FwdIter& it) {     // Q of the item `it` belongs to, into slot n & 1
-            ptx::mbar_arrive_expect_tx(&bar_q[it.n & 1], kTile);
-            ptx::tma_load_3d(sQ + (it.n & 1) * kTile, &tmap_q, &bar_q[it.n & 1], it.h * 64, it.q0, it.b);
-        };
-        auto load_k = [&](const FwdIter& it, int g) {
-            ptx::mbar_arrive_expect_tx(&bar_k[g & 1], kTile);
-            ptx::tma_load_3d(sK + (g & 1) * kTile, &tmap_k, &bar_k[g & 1], it.h * 64, it.j * BK, it.b);
-        };
-        auto load_v = [&](const FwdIter& it, int g) {
-            ptx::mbar_arrive_expect_tx(&bar_v[g & 1], kTile);
-            ptx::tma_load_3d(sV + (g & 1) * kTile, &tmap_v, &bar_v[g & 1], it.h * 64, it.j * BK, it.b);
-        };
-        auto issue_qk = [&](const FwdIter& it, int g) {   // S(g) = Q K^T, N = this block's columns
-            const int bc = (it.j == nkb_all - 1) ? n_last : BK;
-            const uint32_t idesc = ptx::make_idesc_bf16_f32(128, bc, 0, 0);
-            const uint32_t aq = aq0 + (it.n & 1) * kTile, ak = ak0 + (g & 1) * kTile;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16_ss(tS, ptx::make_smem_desc_sw128(aq + k * 32, 16, 1024),
-                                  ptx::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc, k != 0);
-            ptx::umma_commit(bar_s);
-        };
-        FwdIter cur;
-        cur.n = 0;
-        fwd_item_setup(cur, p, blockIdx.x, nkb_all);
-        FwdIter ck = cur, cv = cur, cq = cur;   // next iteration whose K / V, next item whose Q has not been requested
-        int gk = 0, gv = 0;
-        if (issuer) {
-            load_q(cq);
-            load_k(ck, gk);
-            load_v(cv, gv);
-        }
-        ++gk;
-        ++gv;
-        // second Q (the next item's), second K / V (the next iteration's)
-        {
-            const int next_item = cq.item + static_cast<int>(gridDim.x);
-            if (next_item < num_items) {
-                ++cq.n;
-                fwd_item_setup(cq, p, next_item, nkb_all);
-                if (issuer) load_q(cq);
-            } else {
-                cq.item = -1;
-            }
-        }
-        if (fwd_advance(ck, p, num_items, nkb_all)) {
-            if (issuer) load_k(ck, gk);
-            ++gk;
-        }
-        if (fwd_advance(cv, p, num_items, nkb_all)) {
-            if (issuer) load_v(cv, gv);
-            ++gv;
-        }
-        __syncwarp();
-        ptx::mbar_wait(&bar_q[0], 0);
-        ptx::mbar_wait(&bar_k[0], 0);
-        ptx::tc_fence_after_sync();
-        if (issuer) issue_qk(cur, 0);
-        __syncwarp();
-        for (int g = 0; cur.item >= 0; ++g) {
-            const int bc = (cur.j == nkb_all - 1) ? n_last : BK;
-            FwdIter nxt = cur;
-            const bool has_next = fwd_advance(nxt, p, num_items, nkb_all);
-            if (has_next) {
-                ptx::mbar_wait(bar_sfree, g & 1);                           // S(g) has been read by every softmax warp
-                ptx::mbar_wait(&bar_k[(g + 1) & 1], ((g + 1) >> 1) & 1);
-                if (nxt.j == 0) ptx::mbar_wait(&bar_q[nxt.n & 1], (nxt.n >> 1) & 1);
+        const int role = warp - kFwdSoftmaxWarps;
+        FwdIter c;
+        c.n = 0;
+        fwd_item_setup(c, p, blockIdx.x, nkb_all);
+        bool valid = true;
+        if (role == 0) {
+            // ---- O += P(g) V: released by "P(g) (and a rescaled O) are in tensor memory" ----
+            const uint64_t dV0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sV), 8192, 1024);   // V [key x 64] read MN-major
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);
+#pragma unroll 1
+            for (int g = 0; valid; ++g) {
+                const int bc = (c.j == nkb_all - 1) ? n_last : BK;
+                ptx::mbar_wait(bar_p, g & 1);
+                ptx::mbar_wait(&bar_v[g & 1], (g >> 1) & 1);
                 ptx::tc_fence_after_sync();
-                if (issuer) issue_qk(nxt, g + 1);
-                // QK(g) has completed (its scores were read): its K buffer — and, after an item's last block, its Q slot —
-                // are free
-                if (fwd_advance(ck, p, num_items, nkb_all)) {
-                    if (issuer) load_k(ck, gk);
-                    ++gk;
-                }
-                if (nxt.j == 0 && cq.item >= 0) {
-                    const int next_item = cq.item + static_cast<int>(gridDim.x);
-                    if (next_item < num_items) {
-                        ++cq.n;
-                        fwd_item_setup(cq, p, next_item, nkb_all);
-                        if (issuer) load_q(cq);
+                if (issuer) {
+                    const uint64_t dv = dV0 + static_cast<uint32_t>(((g & 1) * kTile) >> 4);
+                    const int ksteps = bc >> 4;
+                    if (ksteps == 8) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ptx::umma_bf16_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc, (c.j | k) != 0);
                     } else {
-                        cq.item = -1;
+                        for (int k = 0; k < ksteps; ++k)
+                            ptx::umma_bf16_ts(tO, tP + k * 8, dv + k * (2048 >> 4), idesc, (c.j | k) != 0);
+                    }
+                    ptx::umma_commit(bar_o);
+                }
+                __syncwarp();
+                valid = fwd_advance(c, p, num_items, nkb_all);
+            }
+        } else if (role == 1) {
+            // ---- S(g) = Q K^T (N = the block's columns): released by "S(g-1) is in registers" ----
+            const uint64_t dQ0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sQ), 16, 1024);
+            const uint64_t dK0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sK), 16, 1024);
+#pragma unroll 1
+            for (int g = 0; valid; ++g) {
+                const int bc = (c.j == nkb_all - 1) ? n_last : BK;
+                if (g >= 1) ptx::mbar_wait(bar_sfree, (g - 1) & 1);
+                ptx::mbar_wait(&bar_k[g & 1], (g >> 1) & 1);
+                if (c.j == 0) ptx::mbar_wait(&bar_q[c.n & 1], (c.n >> 1) & 1);
+                ptx::tc_fence_after_sync();
+                if (issuer) {
+                    const uint32_t idesc = ptx::make_idesc_bf16_f32(128, bc, 0, 0);
+                    const uint64_t dq = dQ0 + static_cast<uint32_t>(((c.n & 1) * kTile) >> 4);
+                    const uint64_t dk = dK0 + static_cast<uint32_t>(((g & 1) * kTile) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ptx::umma_bf16_ss(tS, dq + k * 2, dk + k * 2, idesc, k != 0);
+                    ptx::umma_commit(bar_s);
+                }
+                __syncwarp();
+                valid = fwd_advance(c, p, num_items, nkb_all);
+            }
+        } else if (role == 2) {
+            // ---- K(g) into buffer g & 1 once S(g-2) was read (so QK(g-2) has completed); an item's Q with its first K:
+            //      the Q slot's previous tenant (item n - 2) finished its last QK at iteration g - 2 at the latest ----
+#pragma unroll 1
+            for (int g = 0; valid; ++g) {
+                if (g >= 2) ptx::mbar_wait(bar_sfree, (g - 2) & 1);
+                const int c_h = __shfl_sync(0xffffffffu, c.h * 64, 0), c_b = __shfl_sync(0xffffffffu, c.b, 0);
+                const int c_k = __shfl_sync(0xffffffffu, c.j * BK, 0), c_q = __shfl_sync(0xffffffffu, c.q0, 0);
+                if (issuer) {
+                    ptx::mbar_arrive_expect_tx(&bar_k[g & 1], kTile);
+                    ptx::tma_load_3d(sK + (g & 1) * kTile, &tmap_k, &bar_k[g & 1], c_h, c_k, c_b);
+                    if (c.j == 0) {
+                        ptx::mbar_arrive_expect_tx(&bar_q[c.n & 1], kTile);
+                        ptx::tma_load_3d(sQ + (c.n & 1) * kTile, &tmap_q, &bar_q[c.n & 1], c_h, c_q, c_b);
                     }
                 }
                 __syncwarp();
+                valid = fwd_advance(c, p, num_items, nkb_all);
             }
-            ptx::mbar_wait(bar_p, g & 1);                                   // P(g) written; PV(g-1) was waited for before
-            ptx::mbar_wait(&bar_v[g & 1], (g >> 1) & 1);
-            ptx::tc_fence_after_sync();
-            if (issuer) {
-                const uint32_t av = av0 + (g & 1) * kTile;
-                constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(128, 64, 0, 1);   // V [key x 64] read MN-major
-                const int ksteps = bc >> 4;
-                if (ksteps == 8) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        ptx::umma_bf16_ts(tO, tP + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc,
-                                          (cur.j | k) != 0);
-                } else {
-                    for (int k = 0; k < ksteps; ++k)
-                        ptx::umma_bf16_ts(tO, tP + k * 8, ptx::make_smem_desc_sw128(av + k * 2048, 8192, 1024), idesc,
-                                          (cur.j | k) != 0);
+        } else {
+            // ---- V(g) into buffer g & 1 once PV(g-2) has completed ----
+#pragma unroll 1
+            for (int g = 0; valid; ++g) {
+                if (g >= 2) ptx::mbar_wait(bar_o, (g - 2) & 1);
+                const int c_h = __shfl_sync(0xffffffffu, c.h * 64, 0), c_b = __shfl_sync(0xffffffffu, c.b, 0);
+                const int c_k = __shfl_sync(0xffffffffu, c.j * BK, 0);
+                if (issuer) {
+                    ptx::mbar_arrive_expect_tx(&bar_v[g & 1], kTile);
+                    ptx::tma_load_3d(sV + (g & 1) * kTile, &tmap_v, &bar_v[g & 1], c_h, c_k, c_b);
                 }
-                ptx::umma_commit(bar_o);
+                __syncwarp();
+                valid = fwd_advance(c, p, num_items, nkb_all);
             }
-            // PV(g-1) completed before P(g) was written: the V buffer it read is free
-            if (g >= 1 && fwd_advance(cv, p, num_items, nkb_all)) {
-                if (issuer) load_v(cv, gv);
-                ++gv;
-            }
-            __syncwarp();
-            cur = nxt;
         }
-    } else if (warp < kFwdSoftmaxWarps) {
+    } else {
         // ===================================== softmax ==========================================
         ptx::setmaxnreg_inc<kFwdSoftmaxRegs>();
         const int half = warp >> 2;                 // which 64 of the block's 128 score columns (32 of the 64 O columns)
@@ -604,7 +577,7 @@ __device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p
 
 constexpr int kDkvSoftmaxWarps = 16;                       // two groups of eight
 constexpr int kDkvThreads = (kDkvSoftmaxWarps + 4) * 32;   // + the issue warpgroup (one active warp)
-constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 64 <= 640 x 96 (112 + 64 would take the WHOLE file: the kernel hangs in setmaxnreg.inc)
+constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 64 <= 640 x 96 (112 + 64 exceeds the 640 x 96 of the launch: the CTA hangs in setmaxnreg.inc)
 // smem: (K, V) x 3 | (Q, dO) sub-tiles x 6 | statistics [2 groups][2][128] | barriers
 constexpr int kNKV = 3, kNQ = 6;   // K / V ring (items), Q / dO ring (sub-blocks)
 constexpr int kDkvOffQ = kNKV * 2 * kTile, kDkvOffStat = kDkvOffQ + kNQ * 2 * kSubTile, kDkvOffBar = kDkvOffStat + 2 * 2 * 128 * 4;
