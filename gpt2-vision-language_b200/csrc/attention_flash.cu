@@ -581,7 +581,7 @@ constexpr int kDkvSoftmaxRegs = 104, kDkvIssueRegs = 64;   // 512 x 104 + 128 x 
 // smem: (K, V) x 3 | (Q, dO) sub-tiles x 6 | statistics [2 groups][2][128] | barriers
 constexpr int kNKV = 3, kNQ = 6;   // K / V ring (items), Q / dO ring (sub-blocks)
 constexpr int kDkvOffQ = kNKV * 2 * kTile, kDkvOffStat = kDkvOffQ + kNQ * 2 * kSubTile, kDkvOffBar = kDkvOffStat + 2 * 2 * 128 * 4;
-constexpr int kDkvSmem = kDkvOffBar + 256 + 1024;
+constexpr int kDkvSmem = kDkvOffBar + 512 + 1024;
 
 __global__ void __launch_bounds__(kDkvThreads, 1)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -604,7 +604,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                                                // slot's bar_acc, whose phase it does not track)
     uint64_t* bar_free = bar_item + 1;         // [kNQ] MMA -> TMA: the products that read the Q / dO ring slot have retired
     uint64_t* bar_kvfree = bar_free + kNQ;     // [kNKV] MMA -> TMA: every product of the item in the K / V slot has retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kvfree + kNKV);
+    uint64_t* bar_stat = bar_kvfree + kNKV;    // [2 groups][2 buffers] 4 writer warps -> the group: statistics are staged
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_stat + 4);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -620,6 +621,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int i = 0; i < kNKV + kNQ + 4; ++i) ptx::mbar_init(bar_kv + i, 1);
         ptx::mbar_init(bar_item, 1);
         for (int i = 0; i < kNQ + kNKV; ++i) ptx::mbar_init(bar_free + i, 1);
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(bar_stat + i, 4);
         for (int i = 0; i < 4; ++i) ptx::mbar_init(bar_p + i, kDkvSoftmaxWarps / 2);   // bar_p[2], bar_sfree[2]
         ptx::mbar_init(bar_done, kDkvSoftmaxWarps);
         ptx::fence_barrier_init();
@@ -752,7 +754,6 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         int n_done = 0;                                      // non-empty items finished (phase of bar_item)
         float cur_stat = 0.f;                                // this thread's staged statistic (prefetched one sub-iteration ahead)
         bool have_stat = false;
-        int pref_item = -1;                                  // the item cur_stat was prefetched for across an item boundary
         BwdIter it;
         FDBG_DECL;
         int my_iters = 0;
@@ -834,7 +835,6 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 }
                 stat_base = (static_cast<size_t>(it.b) * p.H + it.h) * p.Tq;
                 tail_keys = it.k0 + BK > p.Tk;   // some key rows of this block are past the sequence
-                have_stat = have_stat && pref_item == item;   // (prefetched at the previous item's last sub-iteration)
                 FDBG(9);
                 // (an item has an even number of sub-iterations and starts in slot 0: this group's are u0 + grp, + 2, ...)
                 u_beg = it.u0 + grp;
@@ -848,7 +848,13 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const int qs = u * BQS;
                 ++my_iters;
                 FDBG(7);
-                // statistics of the sub-block: float4 (-lse * log2e, -lse' * log2e, -delta, -delta') per PAIR of query columns
+                // statistics of the sub-block: float4 (-lse * log2e, -lse' * log2e, -delta, -delta') per PAIR of query columns,
+                // staged in shared memory by the group's first four warps from values prefetched under the previous
+                // sub-iteration's arithmetic; the buffer's mbarrier (four arrivals) replaces a 256-thread named barrier
+                // (10 % of the kernel's stall samples).  Staging at the END of the previous sub-iteration instead was
+                // measured: 175.6 vs 164.1 us (72 bytes of spills in the arithmetic).  The other buffer was last read in the
+                // arithmetic of sub-iteration k - 2, which every warp finished before the products of k - 2 were issued —
+                // and this warp waited for those before its tcgen05.st of k - 1.
                 float* st = stat + (k & 1) * 128;
                 auto load_stat = [&](size_t base_, int q0_) -> float {   // thread gt < 64: lse of query gt; 64 <= gt < 128: delta
                     const int qi = q0_ + (gt & 63);        // (raw values: nothing here may depend on the load, it is in flight)
@@ -856,8 +862,15 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (gt < 128 && qi < p.Tq) v = (gt < 64 ? p.lse : p.delta)[base_ + qi];
                     return v;
                 };
+                auto stage = [&](float* dst, int buf) {
+                    if (gt < 128) {   // (warp-uniform)
+                        dst[((gt & 63) >> 1) * 4 + (gt >> 6) * 2 + (gt & 1)] = -cur_stat * (gt < 64 ? 1.4426950408889634f : 1.f);
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&bar_stat[grp * 2 + buf]);
+                    }
+                };
                 if (!have_stat) cur_stat = load_stat(stat_base, qs);
-                if (gt < 128) st[((gt & 63) >> 1) * 4 + (gt >> 6) * 2 + (gt & 1)] = -cur_stat * (gt < 64 ? 1.4426950408889634f : 1.f);
+                stage(st, k & 1);
                 // this group's next sub-block — of this item or, at its last one, of the CTA's next item — is in flight under
                 // the arithmetic
                 have_stat = u + 2 < it.nsub;
@@ -868,14 +881,13 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     if (nx < num_items) {
                         BwdIter nt;
                         bwd_item_setup(nt, p, nx, B);
-                        if (nt.u0 < nt.nsub) {
+                        if (nt.u0 < nt.nsub) {   // (the next item this CTA processes: empty items have no sub-iteration)
                             cur_stat = load_stat((static_cast<size_t>(nt.b) * p.H + nt.h) * p.Tq, (nt.u0 + grp) * BQS);
                             have_stat = true;
-                            pref_item = nx;
                         }
                     }
                 }
-                ptx::named_bar_sync(1 + grp, 256);
+                ptx::mbar_wait(&bar_stat[grp * 2 + (k & 1)], (k >> 1) & 1);
                 FDBG(0);
                 const float4* st4 = reinterpret_cast<const float4*>(st) + (col_h >> 1);
                 ptx::mbar_wait(&bar_s[slot], k & 1);
