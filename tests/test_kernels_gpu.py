@@ -71,6 +71,16 @@ def test_embed_concat(cuda):
     assert relerr(out2, wte.float()[ids] + wpe.float()[:31]) < 1e-2
 
 
+_GUARD = 8192
+
+
+def _guarded(like):
+    """A contiguous bf16 tensor shaped like `like` inside a flat buffer with _GUARD sentinel elements on either side."""
+    n = like.numel()
+    buf = torch.full((n + 2 * _GUARD,), -77.0, device=like.device, dtype=torch.bfloat16)
+    return buf, buf[_GUARD:_GUARD + n].view(like.shape)
+
+
 def _attn_ref(q, k, v, H, causal):
     from oracle import torch_oracle as O
     return O.sdpa(q, k, v, H, causal)
@@ -99,8 +109,13 @@ def test_attention_fwd_bwd(cuda, B, H, Tq, Tk, causal):
     assert relerr(o, ref) < 1.5e-2
     d_o = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
     ref.backward(d_o.float())
-    dq, dk, dv = torch.empty_like(q.contiguous()), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
+    # the outputs sit between guard zones of a sentinel value: the kernels store rows through pointer arithmetic relative
+    # to rows that may lie past the sequence (and, streaming kernels, through transposed lane quads) — nothing may land
+    # outside the three gradients
+    (bq, dq), (bk, dk), (bv, dv) = _guarded(q), _guarded(k), _guarded(v)
     ops.attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, H, causal)
+    for buf in (bq, bk, bv):
+        assert bool((buf[:_GUARD] == -77.0).all()) and bool((buf[-_GUARD:] == -77.0).all())
     assert relerr(dq, qr.grad) < 2e-2
     assert relerr(dk, kr.grad) < 2e-2
     assert relerr(dv, vr.grad) < 2e-2
@@ -170,8 +185,13 @@ def test_flash_attention_long_sequences(cuda, B, H, Tq, Tk, causal):
     assert relerr(o, ref) < 1.5e-2
     d_o = torch.randn(B, Tq, C, device=cuda, generator=g).bfloat16()
     ref.backward(d_o.float())
-    dq, dk, dv = torch.empty_like(q.contiguous()), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
+    # the outputs sit between guard zones of a sentinel value: the kernels store rows through pointer arithmetic relative
+    # to rows that may lie past the sequence (and, streaming kernels, through transposed lane quads) — nothing may land
+    # outside the three gradients
+    (bq, dq), (bk, dk), (bv, dv) = _guarded(q), _guarded(k), _guarded(v)
     ops.attention_bwd(q, k, v, o, d_o, lse, dq, dk, dv, H, causal)
+    for buf in (bq, bk, bv):
+        assert bool((buf[:_GUARD] == -77.0).all()) and bool((buf[-_GUARD:] == -77.0).all())
     assert relerr(dq, qr.grad) < 2e-2
     assert relerr(dk, kr.grad) < 2e-2
     assert relerr(dv, vr.grad) < 2e-2
