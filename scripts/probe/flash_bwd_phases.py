@@ -1,5 +1,6 @@
-"""Bring-up build only: cycles per phase of the dK/dV backward kernel (softmax group 0 thread 0, group 1 thread 256, the
-issue warp's lane 0), summed over a CTA's sub-iterations, for the first 20 CTAs."""
+"""Bring-up build only: cycles per phase of the persistent backward kernels (softmax group 0 thread 0, group 1 thread 256),
+summed over a CTA's sub-iterations, for the first 20 CTAs.  Both kernels dump into the same table and the dQ kernel runs
+last, so the numbers are the dQ kernel's; stamp the dK/dV kernel alone by disabling the dQ dump in the bring-up build."""
 import ctypes, os, sys
 import torch
 here = os.path.dirname(os.path.abspath(__file__))
@@ -38,11 +39,9 @@ which = os.environ.get("VLK_PROBE_KERNEL", "dq")   # the LAST kernel of the call
 grp_dq = ["wait S/dP", "tcgen05.ld + arrive", "exp2 / dS / pack / mask", "wait product(k-1) + tcgen05.st + arrive", "read-out (wait item, ld, stores)", "loop + item setup", "-", "-", "-", "-"]
 grp = ["stats + group barrier", "wait S^T/dP^T", "tcgen05.ld", "exp2 / dS / pack", "wait products(k-1) + tcgen05.st + arrive", "read-out tcgen05.ld + arrive", "wait item",
        "sub-iteration loop", "8=stores", "9=next item setup"]
-iss = ["wait P^T/dS^T", "wait read-out", "wait S read", "request loads (+ wait retired)", "issue products", "issue scores(G+2)", "wait Q/dO, K/V tiles", "loop"]
 print("group phases (dQ kernel: it runs last and overwrites the dump):", " | ".join(f"{i}={n}" for i, n in enumerate(grp_dq)))
-print("issue phases:", " | ".join(f"{i}={n}" for i, n in enumerate(iss)))
 for cta in range(0, 20, 3):
-    for t, name in enumerate(("group0 t0  ", "group1 t256", "issue lane0")):
+    for t, name in enumerate(("group0 t0  ", "group1 t256")):   # (row 2 of a CTA is unused since the issue side became three warps)
         base = (cta * 3 + t) * 16
         r = [buf[base + i] for i in range(9)]
         it = max(r[8], 1)
