@@ -151,9 +151,10 @@ __device__ __forceinline__ bool fwd_advance(FwdIter& it, const FlashFwdParams& p
 //   * warps 0..7 = softmax: a query row is shared by two threads (warp w and w + 4 own the same 32 TMEM lanes), each
 //     holding 64 of the row's 128 scores in registers after ONE tcgen05.ld pass (max, then exp2 from the same registers);
 //     the two partial row maxima meet in shared memory under a 64-thread named barrier;
-//   * warp 8 = TMA + MMA issue (converged, one elected lane): QK(g+1) is issued as soon as the eight softmax warps have
-//     S(g) in registers (mbarrier s_free) and runs under the exponentials of iteration g; PV(g) is issued when P(g) is
-//     complete (mbarrier p_ready) and runs under the loads of iteration g+1;
+//   * warps 8..11 = PV issue | QK issue | K and Q loads | V loads (each converged, one elected lane, its own cursor):
+//     QK(g+1) is issued as soon as the eight softmax warps have S(g) in registers (mbarrier s_free) and runs under the
+//     exponentials of iteration g; PV(g) is issued when P(g) is complete (mbarrier p_ready) and runs under the loads
+//     of iteration g+1;
 //   * O accumulates in tensor memory across key blocks (tcgen05.mma accumulate), it is NOT read out every iteration;
 //     the running maximum is only raised when it grows by more than 2^8 (a stale maximum is exact arithmetic: P and the
 //     row sum are scaled by the same factor, bounded by 256), and only then is O rescaled in tensor memory;
