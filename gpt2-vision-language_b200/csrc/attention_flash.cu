@@ -89,6 +89,17 @@ inline FastDiv make_fastdiv(int d) {
     }
     return f;
 }
+// Items are dealt to the CTAs in boustrophedon order (round r: CTA x takes item r * grid + x, round r + 1: (r + 1) * grid +
+// grid - 1 - x): the items are sorted heaviest first, so plain striding gives CTA 0 the heaviest item of EVERY round
+// (backward, T = 1024: 51 vs 46.7 128-query blocks on average, 48 with the snake; forward with two CTAs per SM: 27 vs
+// 23.4, 24 with the snake).
+__device__ __forceinline__ int bwd_first_item() { return static_cast<int>(blockIdx.x); }
+__device__ __forceinline__ int bwd_next_item(int item, const FastDiv& div_grid) {
+    const int g = static_cast<int>(gridDim.x);
+    if (item < 0) return bwd_first_item();   // the "before the first item" state of a cursor
+    const int r = div_grid.div(item), x = item - r * g;
+    return (r + 1) * g + (g - 1 - x);
+}
 struct FlashFwdParams {
     bf16* o;
     float* lse;
@@ -98,7 +109,7 @@ struct FlashFwdParams {
     int nqb;           // query blocks per (b, h) = ceil(q_rows / 128)
     int wide_store;    // output rows are 32-byte aligned: 256-bit stores
     float scale, scale_log2e;
-    FastDiv div_hb, div_h, div_nqb;   // by H * B, by H, by nqb
+    FastDiv div_hb, div_h, div_nqb, div_grid;   // by H * B, by H, by nqb, by the grid size
 };
 
 // One step of a CTA's flat sequence of (work item, key block) iterations.  A work item is one 128-row query block of one
@@ -129,7 +140,7 @@ __device__ __forceinline__ void fwd_item_setup(FwdIter& it, const FlashFwdParams
 __device__ __forceinline__ bool fwd_advance(FwdIter& it, const FlashFwdParams& p, int num_items, int nkb_all) {
     if (it.item < 0) return false;
     if (++it.j < it.nkb) return true;
-    const int next = it.item + static_cast<int>(gridDim.x);
+    const int next = bwd_next_item(it.item, p.div_grid);
     if (next >= num_items) {
         it.item = -1;
         return false;
@@ -325,7 +336,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int g = 0;
         FwdIter it;
         it.n = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it.n) {
+        for (int item = blockIdx.x; item < num_items; item = bwd_next_item(item, p.div_grid), ++it.n) {
             fwd_item_setup(it, p, item, nkb_all);
             const int nkb = it.nkb;
             const int qi = it.q0 + row;
@@ -551,16 +562,6 @@ __device__ __forceinline__ void bwd_item_setup(BwdIter& it, const FlashBwdParams
     it.nsub = 2 * ((p.Tq + 2 * BQS - 1) / (2 * BQS));
     it.u0 = p.causal ? 2 * (max(0, it.k0 - (p.Tk - p.Tq)) / (2 * BQS)) : 0;
     it.u = it.u0;
-}
-// Items are dealt to the CTAs in boustrophedon order (round r: CTA x takes item r * grid + x, round r + 1: (r + 1) * grid +
-// grid - 1 - x): the items are sorted heaviest first, so plain striding gives CTA 0 the heaviest item of EVERY round
-// (51 vs 46.7 128-query blocks on average at T = 1024); the snake brings the maximum to 48.
-__device__ __forceinline__ int bwd_first_item() { return static_cast<int>(blockIdx.x); }
-__device__ __forceinline__ int bwd_next_item(int item, const FastDiv& div_grid) {
-    const int g = static_cast<int>(gridDim.x);
-    if (item < 0) return bwd_first_item();   // the "before the first item" state of a cursor
-    const int r = div_grid.div(item), x = item - r * g;
-    return (r + 1) * g + (g - 1 - x);
 }
 __device__ __forceinline__ bool bwd_advance(BwdIter& it, const FlashBwdParams& p, int num_items, int B) {
     if (it.item == kBwdEnd) return false;
@@ -1387,6 +1388,7 @@ int attn_flash_fwd(const void* q, const void* k, const void* v, void* o, float* 
     VLK_REQUIRE(sms > 0, VLK_ERR_ARCH, "vlk_attn_fwd: no sm_100 device");
     const long long items = static_cast<long long>(p.nqb) * H * B;
     const int grid = static_cast<int>(items < 2LL * sms ? items : 2LL * sms);   // persistent: two CTAs per SM
+    p.div_grid = make_fastdiv(grid);
     flash_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, stream>>>(tq, tk, tv, p);
     VLK_CHECK_LAUNCH("vlk_attn_fwd(flash)");
     return VLK_OK;
